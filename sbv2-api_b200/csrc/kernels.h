@@ -1,0 +1,118 @@
+// Launch wrappers of the hand-written kernels.  All activations of the fp32 ("exact") path are
+// time-major: a packed [rows, C] float32 matrix holding the utterances of a batch back to back,
+// rows of utterance b being [seg_start[b], seg_start[b]+seg_len[b]).  Convolutions zero-pad at the
+// boundaries of each utterance's own segment, so a batched run is bit-identical to batch-1 runs.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace sbv2 {
+
+struct Segs {             // device pointers
+  const int* start = nullptr;  // [n] first row of each utterance
+  const int* len = nullptr;    // [n] rows of each utterance
+  int n = 0;
+  int max_len = 0;  // host-side max over len (grid sizing)
+};
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 /*0.1*/, ACT_GELU = 3, ACT_LRELU01 = 4 /*0.01*/, ACT_TANH = 5 };
+enum AccumMode { ACC_NONE = 0, ACC_SET = 1, ACC_ADD = 2, ACC_ADD_SCALE = 3 };
+
+struct LaunchCtx {
+  cudaStream_t stream = nullptr;
+  int64_t* launches = nullptr;  // host counter
+  void count(int n = 1) const {
+    if (launches) *launches += n;
+  }
+};
+
+// out[orow(t), co] = epi( bias[co] + bias_utt[b, co] + sum_{m<taps} sum_ci W[m][ci][co] * act_in(in[t + off + m*dil, ci]) )
+//   orow(t) = seg_out_start[b] + t*out_row_mul + out_row_off;   t in [0, seg.len[b])
+//   epi(v)  = act_out(v + residual[orow]) ; optional accumulate into accum_out.
+struct ConvArgs {
+  const float* in = nullptr;
+  int in_ld = 0;            // floats between consecutive rows of `in`
+  const float* w = nullptr;  // [taps][Cin][Cout]
+  const float* bias = nullptr;
+  const float* bias_utt = nullptr;  // [n_utt][Cout] or null
+  float* out = nullptr;
+  int out_ld = 0;
+  const float* residual = nullptr;  // same indexing as out
+  float* accum_out = nullptr;       // same indexing as out
+  int accum_mode = ACC_NONE;
+  float accum_div = 1.f;  // ACC_ADD_SCALE: accum = (accum + v) / accum_div
+  int cin = 0, cout = 0, taps = 1, dil = 1, off = 0;
+  int act_in = ACT_NONE, act_out = ACT_NONE;
+  int out_row_mul = 1, out_row_off = 0;
+  const int* seg_out_start = nullptr;  // null: same as seg.start (times out_row_mul is NOT applied to it)
+  Segs seg;
+};
+void launch_conv(const LaunchCtx& ctx, const ConvArgs& a);
+
+// [C, T_b] channel-major blocks (utterance b at src + src_off[b]) -> packed [rows, C]
+void launch_cm_to_rm(const LaunchCtx& ctx, const float* src, const int64_t* src_off, const int* src_ld, float* dst, int C, const Segs& seg);
+// packed [rows, C] -> per-utterance [C, T_b] blocks
+void launch_rm_to_cm(const LaunchCtx& ctx, const float* src, float* dst, const int64_t* dst_off, int C, const Segs& seg);
+
+// h = (emb[x] + tone_emb[tone] + lang_emb[lang] + h + style_emb[b]) * sqrt(C)
+void launch_embed_combine(const LaunchCtx& ctx, float* h, const int* x, const int* tone, const int* lang, const float* emb,
+                          const float* tone_emb, const float* lang_emb, const float* style_emb, int C, int n_vocab,
+                          int n_tones, int n_lang, const Segs& seg);
+// gather rows: out[b, :] = table[idx[b], :]
+void launch_gather_rows(const LaunchCtx& ctx, float* out, const float* table, const int64_t* idx, int n, int C, int n_rows);
+// x[row, c] (+)= v[b, c]; out may alias x.
+void launch_add_utt_vec(const LaunchCtx& ctx, float* out, const float* x, const float* v, int C, int v_ld, const Segs& seg);
+
+// out = res + act(LN(a + addin)) over channels (gamma/beta, eps); res/addin optional.
+void launch_layernorm(const LaunchCtx& ctx, float* out, const float* a, const float* addin, const float* res,
+                      const float* gamma, const float* beta, float eps, int act, int C, int rows);
+
+// window-relative multi-head attention (enc_p / transformer flow). qkv: [rows, 3*H*D].
+void launch_rel_attention(const LaunchCtx& ctx, float* out, const float* qkv, const float* rel_k, const float* rel_v,
+                          int heads, int head_dim, int window, const Segs& seg);
+
+// depthwise dilated conv k=3 (DDSConv.convs_sep): w [C][3]
+void launch_dwconv3(const LaunchCtx& ctx, float* out, const float* in, const float* w, const float* bias, int C, int dil,
+                    const Segs& seg);
+
+// SDP pieces on z [rows, 2]
+void launch_sdp_init(const LaunchCtx& ctx, float* z, const float* noise_rm /*[rows,2]*/, const float* noise_scale_w_utt,
+                     const Segs& seg);
+void launch_sdp_flip(const LaunchCtx& ctx, float* z, int rows);
+// h[t,c] = w[c]*z[t,0] + b[c] + g[t,c]   (ConvFlow.pre followed by DDSConv's "x + g")
+void launch_convflow_pre(const LaunchCtx& ctx, float* h, const float* z, const float* w, const float* b, const float* g,
+                         int C, int rows);
+// z[t,1] <- RQS^{-1}(z[t,1]; proj[t, 0:29]) with linear tails; proj rows have ld floats
+void launch_convflow_spline(const LaunchCtx& ctx, float* z, const float* proj, int ld, int num_bins, float tail_bound,
+                            float inv_sqrt_filter, int rows);
+void launch_sdp_affine(const LaunchCtx& ctx, float* z, const float* m, const float* logs, int rows);
+
+// durations: logw = sdp*ratio + dp*(1-ratio); w = exp(logw)*length_scale; d = ceil(w);
+// cum = inclusive scan per utterance; ylen[b] = max(1, sum d)
+void launch_durations(const LaunchCtx& ctx, const float* logw_dp, const float* z_sdp /*[rows,2] or null*/,
+                      const float* sdp_ratio_utt, const float* length_scale_utt, float* w_out, int* dur, int* cum,
+                      int* ylen, const Segs& seg);
+// frame2ph + gather + prior sample: z_p[j,c] = m_p[i,c] + eps[j,c]*exp(logs_p[i,c])*noise_scale[b]
+void launch_expand(const LaunchCtx& ctx, float* z_p, int* frame2ph, const float* stats /*[rows_x, 2C]: m_p | logs_p*/,
+                   const int* cum, const float* eps_rm /*[rows_y, C]*/, const float* noise_scale_utt, int C,
+                   const Segs& xseg, const Segs& yseg);
+// Philox-based N(0,1) fill (used when the caller does not inject noise)
+void launch_randn(const LaunchCtx& ctx, float* out, int64_t n, uint64_t seed, uint64_t offset);
+
+// flow helpers on z [rows, C]
+void launch_flip_channels(const LaunchCtx& ctx, float* out, const float* in, int C, int64_t rows);
+// z[:, C/2:] -= m   (m: [rows, C/2])
+void launch_coupling_sub(const LaunchCtx& ctx, float* z, const float* m, int C, int64_t rows);
+// WN gate: acts = tanh(a[:, :H] + g[b, goff:goff+H]) * sigmoid(a[:, H:] + g[b, goff+H:goff+2H])
+void launch_wn_gate(const LaunchCtx& ctx, float* acts, const float* a, const float* g_utt, int g_ld, int goff, int H,
+                    const Segs& seg);
+// WN res/skip update: x += rs[:, :H]; skip (+)= rs[:, H:]  (last layer: skip += rs[:, :H])
+void launch_wn_res_skip(const LaunchCtx& ctx, float* x, float* skip, const float* rs, int H, int last, int first,
+                        int64_t rows);
+
+// decoder post: out[t] = tanh(sum_j sum_c w[c][j] * lrelu_0.01(x[t+j-3, c])), x [rows, C] fp32
+void launch_dec_post(const LaunchCtx& ctx, float* out, const float* x, const float* w, int C, int k, const Segs& seg);
+
+}  // namespace sbv2

@@ -1,0 +1,73 @@
+// sbv2_model base: device binding, weight uploads, out-pointer registry.
+#include "model.h"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace sbv2 {
+namespace {
+std::mutex g_out_mu;
+std::unordered_map<void*, bool> g_out;  // ptr -> pinned?
+thread_local std::string g_last_error;
+}  // namespace
+
+void set_last_error(const std::string& m) { g_last_error = m; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+void* alloc_out(size_t bytes, bool pinned) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 1;
+  if (pinned) {
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      pinned = false;
+    }
+  }
+  if (!p) {
+    p = malloc(bytes);
+    pinned = false;
+    if (!p) throw std::bad_alloc();
+  }
+  std::lock_guard<std::mutex> lk(g_out_mu);
+  g_out[p] = pinned;
+  return p;
+}
+
+void free_out(void* p) {
+  if (!p) return;
+  bool pinned = false, found = false;
+  {
+    std::lock_guard<std::mutex> lk(g_out_mu);
+    auto it = g_out.find(p);
+    if (it != g_out.end()) {
+      pinned = it->second;
+      found = true;
+      g_out.erase(it);
+    }
+  }
+  if (!found) return;  // not ours: ignore rather than corrupt the heap
+  if (pinned) cudaFreeHost(p);
+  else free(p);
+}
+
+}  // namespace sbv2
+
+sbv2_model::~sbv2_model() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  for (void* p : owned_device) cudaFree(p);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void sbv2_model::bind_device() const { CUDA_CHECK(cudaSetDevice(device)); }
+
+void* sbv2_model::upload_bytes(const void* host, size_t bytes) {
+  void* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, bytes ? bytes : 16));
+  owned_device.push_back(d);
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream));
+  // `host` is usually a temporary vector: make the copy complete before returning
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  return d;
+}

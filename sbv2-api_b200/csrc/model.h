@@ -1,0 +1,99 @@
+// Device-side model objects behind the C ABI.  One sbv2_model = one ort::Session of the reference.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "kernels.h"
+#include "onnx_reader.h"
+
+namespace sbv2 {
+
+// Growable device buffer. Growth synchronises the owning stream first.
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  void ensure(size_t bytes);
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  void ensure(size_t bytes);
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// Registry of every allocation made through sbv2_* out-pointers so sbv2_free can tell pinned from malloc.
+void* alloc_out(size_t bytes, bool pinned);
+void free_out(void* p);
+
+struct DebugView {
+  const void* ptr;
+  int64_t rows, cols;
+  int elt;  // 4 = float32, -4 = int32
+};
+
+}  // namespace sbv2
+
+// The opaque C type. Concrete models derive from it.
+struct sbv2_model {
+  int device = 0;
+  bool is_bert = false;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  std::map<std::string, std::string> metadata;
+  std::string describe_json;
+  std::map<std::string, sbv2::DebugView> debug;
+  std::vector<void*> owned_device;  // weights
+
+  virtual ~sbv2_model();
+  sbv2::LaunchCtx ctx() { return sbv2::LaunchCtx{stream, &launches}; }
+  void bind_device() const;
+  // uploads host data, tracked for release at destroy
+  void* upload_bytes(const void* host, size_t bytes);
+  float* upload_f32(const std::vector<float>& v) { return static_cast<float*>(upload_bytes(v.data(), v.size() * 4)); }
+};
+
+struct sbv2_device_batch;
+
+namespace sbv2 {
+
+sbv2_model* create_synth_model(const OnnxModel& m, int device);
+sbv2_model* create_bert_model(const OnnxModel& m, int device);
+
+// synthesizer entry points (synth_model.cu)
+sbv2_device_batch* synth_upload(sbv2_model* m, const sbv2_utterance* utts, int batch);
+void synth_run(sbv2_model* m, sbv2_device_batch* b);
+void synth_download(sbv2_model* m, sbv2_device_batch* b, float** out_samples, int64_t* out_n, int32_t** out_dur,
+                    int32_t** out_f2p);
+int64_t synth_total_samples(sbv2_model* m, const sbv2_device_batch* b);
+void synth_batch_ty(const sbv2_device_batch* b, int64_t* ty);
+void synth_batch_free(sbv2_device_batch* b);
+void synth_set_seed(sbv2_model* m, uint64_t seed);
+void synth_decode(sbv2_model* m, const float* const* z, const int64_t* t_y, const int64_t* sid, int batch,
+                  float** out_samples, int64_t* out_n);
+
+// bert entry points (bert_model.cu)
+void bert_predict(sbv2_model* m, const int64_t* ids, const int64_t* mask, int batch, int64_t s, float* out);
+int bert_hidden(const sbv2_model* m);
+
+}  // namespace sbv2

@@ -1,0 +1,1290 @@
+// JP-Extra synthesizer (Style-Bert-VITS2 SynthesizerTrn.infer) as a static kernel plan.
+// Replaces the `ort::Session::run` of crates/sbv2_core/src/model.rs:91-103 for model.onnx.
+// Graph restated in SURVEY.md §A; oracle in oracle/vits.py.
+#include <algorithm>
+#include <cmath>
+#include <sstream>
+
+#include "model.h"
+#include "umma_conv.h"
+
+namespace sbv2 {
+namespace {
+
+struct ConvW {
+  float* w = nullptr;  // [taps][Cin][Cout]
+  float* b = nullptr;
+  int cin = 0, cout = 0, k = 1;
+};
+struct LNW {
+  float* g = nullptr;
+  float* b = nullptr;
+  int c = 0;
+};
+struct EncLayerW {
+  ConvW qkv, o, f1, f2;
+  float* rel_k = nullptr;
+  float* rel_v = nullptr;
+  LNW n1, n2;
+};
+struct EncoderW {
+  std::vector<EncLayerW> layers;
+  ConvW spk;  // Linear gin -> hidden, applied at cond_idx
+  bool has_spk = false;
+  int cond_idx = 2;
+  int heads = 2, head_dim = 96, window = 4, hidden = 192, filter = 768, ksize = 3;
+};
+struct DDSW {
+  struct L {
+    float* sep_w = nullptr;  // [C][3]
+    float* sep_b = nullptr;
+    ConvW pw;
+    LNW n1, n2;
+    int dil = 1;
+  };
+  std::vector<L> layers;
+};
+struct ConvFlowW {
+  float* pre_w = nullptr;  // [C]
+  float* pre_b = nullptr;
+  DDSW dds;
+  ConvW proj;  // C -> 3*bins-1
+};
+struct UpW {
+  // ConvTranspose1d(Cin -> Cout, k, stride u, pad (k-u)/2) as u phase convolutions of k/u taps
+  std::vector<float*> phase_w;  // [u] each [k/u][Cin][Cout]
+  std::vector<int> phase_off;   // input row offset c of each phase
+  float* b = nullptr;
+  int cin = 0, cout = 0, k = 0, u = 0;
+};
+struct ResBlockW {
+  std::vector<ConvW> c1, c2;
+  std::vector<int> dil;
+  int k = 3;
+};
+struct WNW {
+  ConvW cond;  // gin -> 2*H*n_layers
+  std::vector<ConvW> in_layers, res_skip;
+  int k = 5;
+};
+struct CouplingW {
+  ConvW pre, post;
+  EncoderW enc;  // transformer variant
+  WNW wn;        // WN variant
+};
+
+struct HParams {
+  int n_vocab = 0, n_tones = 0, n_lang = 0, hidden = 0, inter = 0, gin = 0, n_speakers = 0, bert_dim = 0, style_dim = 0;
+  int dp_filter = 0, sdp_bins = 10, sdp_flows = 0;
+  bool transformer_flow = true;
+  int n_flows = 0, flow_layers = 0, wn_layers = 0;
+  std::vector<int> up_rates, up_kernels, res_kernels;
+  std::vector<std::vector<int>> res_dils;
+  int up_initial = 0;
+  int hop = 1;
+};
+
+}  // namespace
+
+struct SynthModel : sbv2_model {
+  HParams hp;
+  // weights
+  float *emb = nullptr, *tone_emb = nullptr, *lang_emb = nullptr, *emb_g = nullptr;
+  ConvW bert_proj, style_proj, enc_proj;
+  EncoderW enc;
+  ConvW dp_c1, dp_c2, dp_proj, dp_cond;
+  LNW dp_n1, dp_n2;
+  ConvW sdp_pre, sdp_proj, sdp_cond;
+  DDSW sdp_dds;
+  std::vector<ConvFlowW> sdp_cf;  // in module order (flows.1, .3, .5, .7)
+  float *sdp_ea_m = nullptr, *sdp_ea_logs = nullptr;
+  std::vector<CouplingW> flow;  // flows.0, .2, .4, .6
+  ConvW dec_pre, dec_cond;
+  std::vector<UpW> ups;
+  std::vector<ResBlockW> resblocks;
+  float* dec_post_w = nullptr;  // [1][C][k]
+  int dec_post_k = 7, dec_post_c = 16;
+  UmmaDecoder* umma = nullptr;  // tensor-core decoder plan (umma_conv.cu); null -> fp32 path
+  bool use_umma = true;
+
+  uint64_t seed = 0x5b2b200ULL, rng_offset = 0;
+  // workspaces
+  DBuf ws[32];
+  DecoderHostWeights dec_host;  // original-layout decoder weights, consumed by umma_decoder_create
+  PinnedBuf pin_in, pin_ylen;
+  ~SynthModel() override {
+    if (umma) umma_decoder_free(umma);
+  }
+};
+
+}  // namespace sbv2
+
+// One uploaded batch: host bookkeeping + device inputs/outputs.
+struct sbv2_device_batch {
+  int B = 0;
+  int64_t Nx = 0, Ny = 0;
+  std::vector<int> xlen, xstart, ylen, ystart;
+  std::vector<int64_t> zp_frames;
+  bool has_noise_sdp = false, has_noise_zp = false, any_sdp = false;
+  sbv2::DBuf in;    // one blob, see synth_upload
+  sbv2::DBuf zp;    // caller-provided noise_zp blocks (channel-major)
+  sbv2::DBuf ymeta; // ystart, ylen, zp offsets
+  sbv2::DBuf wave, dur, cum, f2p, ylen_dev;
+  // offsets (bytes) into `in`
+  size_t o_x = 0, o_tone = 0, o_lang = 0, o_sid = 0, o_sdp_ratio = 0, o_ls = 0, o_ns = 0, o_nsw = 0, o_xstart = 0, o_xlen = 0,
+         o_bert_off = 0, o_nsdp_off = 0, o_style = 0, o_bert = 0, o_nsdp = 0, o_zp_off = 0, o_zp_ld = 0;
+  bool ran = false;
+  bool decode_only = false;
+};
+
+namespace sbv2 {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// weight loading
+// ---------------------------------------------------------------------------------------------
+struct Loader {
+  const OnnxModel& m;
+  SynthModel& M;
+  std::map<std::string, std::string> alias;  // canonical name -> initializer name (structural binding)
+
+  const OnnxTensor* find(const std::string& n) const {
+    auto it = alias.find(n);
+    return m.find(it == alias.end() ? n : it->second);
+  }
+  bool has(const std::string& n) const { return find(n) != nullptr; }
+  const OnnxTensor& get(const std::string& n) const {
+    const OnnxTensor* t = find(n);
+    if (!t) fail(SBV2_ERR_UNSUPPORTED, "synthesizer graph lacks initializer '" + n + "'");
+    return *t;
+  }
+  std::vector<float> f32(const std::string& n) const { return m.as_f32(get(n)); }
+  float* vec(const std::string& n, int expect = -1) const {
+    auto v = f32(n);
+    if (expect >= 0 && int(v.size()) != expect)
+      fail(SBV2_ERR_UNSUPPORTED, "initializer '" + n + "' has " + std::to_string(v.size()) + " elements, expected " + std::to_string(expect));
+    return M.upload_f32(v);
+  }
+  // Conv1d weight [Cout, Cin, k] (or Linear [out, in]) -> [k][Cin][Cout]
+  ConvW conv(const std::string& prefix, bool bias = true) const {
+    const OnnxTensor& t = get(prefix + ".weight");
+    if (t.dims.size() != 3 && t.dims.size() != 2) fail(SBV2_ERR_UNSUPPORTED, "'" + prefix + ".weight' must be 2-D or 3-D");
+    ConvW c;
+    c.cout = int(t.dims[0]);
+    c.cin = int(t.dims[1]);
+    c.k = t.dims.size() == 3 ? int(t.dims[2]) : 1;
+    auto w = m.as_f32(t);
+    std::vector<float> r(w.size());
+    for (int co = 0; co < c.cout; ++co)
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int j = 0; j < c.k; ++j) r[(size_t(j) * c.cin + ci) * c.cout + co] = w[(size_t(co) * c.cin + ci) * c.k + j];
+    c.w = M.upload_f32(r);
+    if (bias) c.b = vec(prefix + ".bias", c.cout);
+    return c;
+  }
+  LNW ln(const std::string& prefix) const {
+    LNW l;
+    const OnnxTensor& t = get(prefix + ".gamma");
+    l.c = int(t.numel());
+    l.g = vec(prefix + ".gamma", l.c);
+    l.b = vec(prefix + ".beta", l.c);
+    return l;
+  }
+  int count(const std::string& fmt_prefix, const std::string& suffix, int step = 1) const {
+    int n = 0;
+    while (has(fmt_prefix + std::to_string(n * step) + suffix)) ++n;
+    return n;
+  }
+  EncoderW encoder(const std::string& p) const {
+    EncoderW E;
+    int n = count(p + ".attn_layers.", ".conv_q.weight");
+    if (n == 0) fail(SBV2_ERR_UNSUPPORTED, "encoder '" + p + "' has no attention layers");
+    for (int i = 0; i < n; ++i) {
+      EncLayerW L;
+      std::string a = p + ".attn_layers." + std::to_string(i);
+      ConvW q = conv(a + ".conv_q"), k = conv(a + ".conv_k"), v = conv(a + ".conv_v");
+      // fuse q|k|v along Cout
+      int H = q.cout, C = q.cin;
+      auto wq = f32(a + ".conv_q.weight"), wk = f32(a + ".conv_k.weight"), wv = f32(a + ".conv_v.weight");
+      std::vector<float> w(size_t(C) * 3 * H), b(size_t(3) * H);
+      for (int ci = 0; ci < C; ++ci)
+        for (int co = 0; co < H; ++co) {
+          w[size_t(ci) * 3 * H + co] = wq[size_t(co) * C + ci];
+          w[size_t(ci) * 3 * H + H + co] = wk[size_t(co) * C + ci];
+          w[size_t(ci) * 3 * H + 2 * H + co] = wv[size_t(co) * C + ci];
+        }
+      auto bq = f32(a + ".conv_q.bias"), bk = f32(a + ".conv_k.bias"), bv = f32(a + ".conv_v.bias");
+      for (int co = 0; co < H; ++co) {
+        b[co] = bq[co];
+        b[H + co] = bk[co];
+        b[2 * H + co] = bv[co];
+      }
+      L.qkv.w = M.upload_f32(w);
+      L.qkv.b = M.upload_f32(b);
+      L.qkv.cin = C;
+      L.qkv.cout = 3 * H;
+      L.qkv.k = 1;
+      L.o = conv(a + ".conv_o");
+      const OnnxTensor& rk = get(a + ".emb_rel_k");
+      if (rk.dims.size() != 3 || rk.dims[0] != 1) fail(SBV2_ERR_UNSUPPORTED, "emb_rel_k must be [1, 2w+1, d] (heads_share)");
+      E.window = int(rk.dims[1] - 1) / 2;
+      E.head_dim = int(rk.dims[2]);
+      E.heads = H / E.head_dim;
+      E.hidden = H;
+      L.rel_k = vec(a + ".emb_rel_k");
+      L.rel_v = vec(a + ".emb_rel_v");
+      L.n1 = ln(p + ".norm_layers_1." + std::to_string(i));
+      L.n2 = ln(p + ".norm_layers_2." + std::to_string(i));
+      L.f1 = conv(p + ".ffn_layers." + std::to_string(i) + ".conv_1");
+      L.f2 = conv(p + ".ffn_layers." + std::to_string(i) + ".conv_2");
+      E.filter = L.f1.cout;
+      E.ksize = L.f1.k;
+      E.layers.push_back(L);
+    }
+    if (has(p + ".spk_emb_linear.weight")) {
+      E.spk = conv(p + ".spk_emb_linear");
+      E.has_spk = true;
+      E.cond_idx = 2;
+      if (E.cond_idx >= n) fail(SBV2_ERR_UNSUPPORTED, "encoder '" + p + "': cond_layer_idx 2 needs >= 3 layers");
+    }
+    return E;
+  }
+  DDSW dds(const std::string& p) const {
+    DDSW D;
+    int n = count(p + ".convs_sep.", ".weight");
+    int dil = 1;
+    for (int i = 0; i < n; ++i) {
+      DDSW::L L;
+      std::string s = p + ".convs_sep." + std::to_string(i);
+      const OnnxTensor& t = get(s + ".weight");
+      if (t.dims.size() != 3 || t.dims[1] != 1 || t.dims[2] != 3) fail(SBV2_ERR_UNSUPPORTED, "DDSConv depthwise weight must be [C,1,3]");
+      L.sep_w = vec(s + ".weight");
+      L.sep_b = vec(s + ".bias");
+      L.pw = conv(p + ".convs_1x1." + std::to_string(i));
+      L.n1 = ln(p + ".norms_1." + std::to_string(i));
+      L.n2 = ln(p + ".norms_2." + std::to_string(i));
+      L.dil = dil;
+      dil *= 3;
+      D.layers.push_back(L);
+    }
+    return D;
+  }
+};
+
+int attr_first(const OnnxNode& n, const char* name, int dflt) {
+  auto it = n.int_attrs.find(name);
+  if (it == n.int_attrs.end() || it->second.empty()) return dflt;
+  return int(it->second[0]);
+}
+
+// Real exports constant-fold weight-normed convs into anonymous initializers.
+// Bind them by walking Conv / ConvTranspose nodes in graph (= execution) order after conv_pre.
+void bind_decoder_structurally(Loader& L) {
+  const OnnxModel& m = L.m;
+  if (m.find("dec.ups.0.weight")) return;
+  size_t start = m.nodes.size();
+  for (size_t i = 0; i < m.nodes.size(); ++i) {
+    const auto& n = m.nodes[i];
+    if (n.op_type == "Conv" && n.inputs.size() >= 2 && n.inputs[1] == "dec.conv_pre.weight") {
+      start = i + 1;
+      break;
+    }
+  }
+  if (start == m.nodes.size()) fail(SBV2_ERR_UNSUPPORTED, "cannot locate dec.conv_pre in the graph to bind decoder weights");
+  // sequence: (ConvTranspose, then per resblock: c1.0 c2.0 c1.1 c2.1 c1.2 c2.2) ...
+  int up = -1, rb = -1, pos = 0;
+  int n_res_per = 0;
+  std::vector<std::string> seq;
+  for (size_t i = start; i < m.nodes.size(); ++i) {
+    const auto& n = m.nodes[i];
+    if (n.inputs.size() < 2 || !m.find(n.inputs[1])) continue;
+    if (n.op_type == "ConvTranspose") {
+      if (up >= 0 && n_res_per == 0) n_res_per = (rb + 1);
+      ++up;
+      L.alias["dec.ups." + std::to_string(up) + ".weight"] = n.inputs[1];
+      if (n.inputs.size() > 2) L.alias["dec.ups." + std::to_string(up) + ".bias"] = n.inputs[2];
+      pos = 0;
+    } else if (n.op_type == "Conv" && up >= 0) {
+      if (n.inputs[1] == "dec.conv_post.weight") break;
+      const OnnxTensor* w = m.find(n.inputs[1]);
+      if (w->dims.size() != 3) continue;
+      // each resblock contributes 2 * n_dil convs; a new resblock starts when the kernel size changes or after 6 convs
+      int idx_in_rb = pos % 6;
+      if (idx_in_rb == 0) ++rb;
+      std::string which = (idx_in_rb % 2 == 0) ? "convs1" : "convs2";
+      std::string nm = "dec.resblocks." + std::to_string(rb) + "." + which + "." + std::to_string(idx_in_rb / 2);
+      L.alias[nm + ".weight"] = n.inputs[1];
+      if (n.inputs.size() > 2) L.alias[nm + ".bias"] = n.inputs[2];
+      ++pos;
+    }
+  }
+  if (up < 0) fail(SBV2_ERR_UNSUPPORTED, "no ConvTranspose nodes found while binding decoder weights");
+}
+
+void load_weights(SynthModel& M, const OnnxModel& m) {
+  Loader L{m, M, {}};
+  HParams& hp = M.hp;
+  if (!L.has("enc_p.emb.weight") || !L.has("dec.conv_pre.weight"))
+    fail(SBV2_ERR_UNSUPPORTED, "not a Style-Bert-VITS2 synthesizer graph (enc_p.emb.weight / dec.conv_pre.weight missing)");
+  bind_decoder_structurally(L);
+
+  auto dims = [&](const std::string& n) { return L.get(n).dims; };
+  hp.n_vocab = int(dims("enc_p.emb.weight")[0]);
+  hp.hidden = int(dims("enc_p.emb.weight")[1]);
+  hp.n_tones = int(dims("enc_p.tone_emb.weight")[0]);
+  hp.n_lang = int(dims("enc_p.language_emb.weight")[0]);
+  hp.n_speakers = int(dims("emb_g.weight")[0]);
+  hp.gin = int(dims("emb_g.weight")[1]);
+  hp.bert_dim = int(dims("enc_p.bert_proj.weight")[1]);
+  hp.style_dim = int(dims("enc_p.style_proj.weight")[1]);
+
+  M.emb = L.vec("enc_p.emb.weight");
+  M.tone_emb = L.vec("enc_p.tone_emb.weight");
+  M.lang_emb = L.vec("enc_p.language_emb.weight");
+  M.emb_g = L.vec("emb_g.weight");
+  M.bert_proj = L.conv("enc_p.bert_proj");
+  M.style_proj = L.conv("enc_p.style_proj");
+  M.enc = L.encoder("enc_p.encoder");
+  M.enc_proj = L.conv("enc_p.proj");
+  hp.inter = M.enc_proj.cout / 2;
+  if (M.enc.hidden != hp.hidden) fail(SBV2_ERR_UNSUPPORTED, "enc_p hidden size mismatch");
+
+  // duration predictor
+  M.dp_c1 = L.conv("dp.conv_1");
+  M.dp_c2 = L.conv("dp.conv_2");
+  M.dp_proj = L.conv("dp.proj");
+  M.dp_cond = L.conv("dp.cond");
+  M.dp_n1 = L.ln("dp.norm_1");
+  M.dp_n2 = L.ln("dp.norm_2");
+  hp.dp_filter = M.dp_c1.cout;
+
+  // stochastic duration predictor
+  M.sdp_pre = L.conv("sdp.pre");
+  M.sdp_proj = L.conv("sdp.proj");
+  M.sdp_cond = L.conv("sdp.cond");
+  M.sdp_dds = L.dds("sdp.convs");
+  M.sdp_ea_m = L.vec("sdp.flows.0.m", 2);
+  M.sdp_ea_logs = L.vec("sdp.flows.0.logs", 2);
+  for (int i = 1; L.has("sdp.flows." + std::to_string(i) + ".pre.weight"); i += 2) {
+    std::string p = "sdp.flows." + std::to_string(i);
+    ConvFlowW cf;
+    const OnnxTensor& pw = L.get(p + ".pre.weight");
+    if (pw.dims.size() != 3 || pw.dims[1] != 1 || pw.dims[2] != 1) fail(SBV2_ERR_UNSUPPORTED, "ConvFlow.pre must be [C,1,1]");
+    cf.pre_w = L.vec(p + ".pre.weight");
+    cf.pre_b = L.vec(p + ".pre.bias");
+    cf.dds = L.dds(p + ".convs");
+    cf.proj = L.conv(p + ".proj");
+    hp.sdp_bins = (cf.proj.cout + 1) / 3;
+    M.sdp_cf.push_back(cf);
+  }
+  hp.sdp_flows = int(M.sdp_cf.size());
+  if (hp.sdp_flows < 2) fail(SBV2_ERR_UNSUPPORTED, "stochastic duration predictor needs >= 2 ConvFlows");
+
+  // flow
+  hp.transformer_flow = L.has("flow.flows.0.enc.attn_layers.0.conv_q.weight");
+  for (int i = 0; L.has("flow.flows." + std::to_string(i) + ".pre.weight"); i += 2) {
+    std::string p = "flow.flows." + std::to_string(i);
+    CouplingW c;
+    c.pre = L.conv(p + ".pre");
+    c.post = L.conv(p + ".post");
+    if (c.post.cout != hp.inter / 2) fail(SBV2_ERR_UNSUPPORTED, "coupling layer must be mean_only");
+    if (hp.transformer_flow) {
+      c.enc = L.encoder(p + ".enc");
+      hp.flow_layers = int(c.enc.layers.size());
+    } else {
+      c.wn.cond = L.conv(p + ".enc.cond_layer");
+      int n = L.count(p + ".enc.in_layers.", ".weight");
+      if (n == 0) fail(SBV2_ERR_UNSUPPORTED, "flow is neither transformer nor WN coupling");
+      for (int l = 0; l < n; ++l) {
+        c.wn.in_layers.push_back(L.conv(p + ".enc.in_layers." + std::to_string(l)));
+        c.wn.res_skip.push_back(L.conv(p + ".enc.res_skip_layers." + std::to_string(l)));
+      }
+      c.wn.k = c.wn.in_layers[0].k;
+      hp.wn_layers = n;
+    }
+    M.flow.push_back(c);
+  }
+  hp.n_flows = int(M.flow.size());
+  if (hp.n_flows == 0) fail(SBV2_ERR_UNSUPPORTED, "no coupling layers found under flow.flows");
+
+  // decoder
+  M.dec_pre = L.conv("dec.conv_pre");
+  M.dec_cond = L.conv("dec.cond");
+  hp.up_initial = M.dec_pre.cout;
+  int n_ups = L.count("dec.ups.", ".weight");
+  if (n_ups == 0) fail(SBV2_ERR_UNSUPPORTED, "decoder has no upsampling layers");
+  // strides / dilations from the graph nodes when present
+  std::map<std::string, const OnnxNode*> node_of_weight;
+  for (const auto& n : m.nodes)
+    if ((n.op_type == "Conv" || n.op_type == "ConvTranspose") && n.inputs.size() >= 2) node_of_weight[n.inputs[1]] = &n;
+  auto node_for = [&](const std::string& canonical) -> const OnnxNode* {
+    auto a = L.alias.find(canonical);
+    auto it = node_of_weight.find(a == L.alias.end() ? canonical : a->second);
+    return it == node_of_weight.end() ? nullptr : it->second;
+  };
+  static const int default_rates_k16[] = {8, 8, 2, 2, 2};
+  hp.hop = 1;
+  for (int i = 0; i < n_ups; ++i) {
+    std::string p = "dec.ups." + std::to_string(i);
+    const OnnxTensor& t = L.get(p + ".weight");
+    if (t.dims.size() != 3) fail(SBV2_ERR_UNSUPPORTED, p + ".weight must be [Cin,Cout,k]");
+    UpW U;
+    U.cin = int(t.dims[0]);
+    U.cout = int(t.dims[1]);
+    U.k = int(t.dims[2]);
+    const OnnxNode* n = node_for(p + ".weight");
+    if (n) U.u = attr_first(*n, "strides", 0);
+    if (U.u <= 0) {
+      if (n_ups == 5 && i < 5) U.u = default_rates_k16[i];  // JP-Extra default [8,8,2,2,2]
+      else fail(SBV2_ERR_UNSUPPORTED, "cannot determine the stride of " + p);
+    }
+    if (U.k % U.u != 0 || (U.k - U.u) % 2 != 0) fail(SBV2_ERR_UNSUPPORTED, p + ": kernel/stride combination not supported");
+    auto w = m.as_f32(t);
+    int pad = (U.k - U.u) / 2, taps = U.k / U.u;
+    for (int r = 0; r < U.u; ++r) {  // r = output index mod u
+      int s = r + pad;
+      int rr = s % U.u, c = s / U.u;
+      std::vector<float> pw(size_t(taps) * U.cin * U.cout);
+      for (int mm = 0; mm < taps; ++mm)
+        for (int ci = 0; ci < U.cin; ++ci)
+          for (int co = 0; co < U.cout; ++co)
+            pw[(size_t(mm) * U.cin + ci) * U.cout + co] = w[(size_t(ci) * U.cout + co) * U.k + rr + U.u * mm];
+      U.phase_w.push_back(M.upload_f32(pw));
+      U.phase_off.push_back(c);
+    }
+    U.b = L.vec(p + ".bias", U.cout);
+    hp.up_rates.push_back(U.u);
+    hp.up_kernels.push_back(U.k);
+    hp.hop *= U.u;
+    M.ups.push_back(U);
+  }
+  int n_rb = L.count("dec.resblocks.", ".convs1.0.weight");
+  if (n_rb == 0 || n_rb % n_ups != 0) fail(SBV2_ERR_UNSUPPORTED, "unexpected number of decoder resblocks");
+  int per = n_rb / n_ups;
+  static const int default_dils[] = {1, 3, 5};
+  for (int r = 0; r < n_rb; ++r) {
+    std::string p = "dec.resblocks." + std::to_string(r);
+    ResBlockW R;
+    int nl = L.count(p + ".convs1.", ".weight");
+    for (int l = 0; l < nl; ++l) {
+      R.c1.push_back(L.conv(p + ".convs1." + std::to_string(l)));
+      R.c2.push_back(L.conv(p + ".convs2." + std::to_string(l)));
+      const OnnxNode* n = node_for(p + ".convs1." + std::to_string(l) + ".weight");
+      int d = n ? attr_first(*n, "dilations", 0) : 0;
+      if (d <= 0) d = l < 3 ? default_dils[l] : 1;
+      R.dil.push_back(d);
+    }
+    R.k = R.c1[0].k;
+    if (R.k % 2 == 0) fail(SBV2_ERR_UNSUPPORTED, "even resblock kernel size");
+    if (r < per) {
+      hp.res_kernels.push_back(R.k);
+      hp.res_dils.push_back(R.dil);
+    }
+    M.resblocks.push_back(R);
+  }
+  {
+    const OnnxTensor& t = L.get("dec.conv_post.weight");
+    if (t.dims.size() != 3 || t.dims[0] != 1) fail(SBV2_ERR_UNSUPPORTED, "dec.conv_post.weight must be [1,C,k]");
+    M.dec_post_c = int(t.dims[1]);
+    M.dec_post_k = int(t.dims[2]);
+    M.dec_post_w = L.vec("dec.conv_post.weight");
+    if (L.has("dec.conv_post.bias")) fail(SBV2_ERR_UNSUPPORTED, "dec.conv_post with bias is not a JP-Extra decoder");
+  }
+
+  // original-layout copies for the tensor-core decoder's fp16 repacking
+  {
+    auto host_conv = [&](const std::string& p, bool bias) {
+      HostConv hc;
+      const OnnxTensor& t = L.get(p + ".weight");
+      hc.d0 = int(t.dims[0]);
+      hc.d1 = int(t.dims[1]);
+      hc.k = t.dims.size() > 2 ? int(t.dims[2]) : 1;
+      hc.w = m.as_f32(t);
+      if (bias) hc.b = L.f32(p + ".bias");
+      return hc;
+    };
+    DecoderHostWeights& D = M.dec_host;
+    D.pre = host_conv("dec.conv_pre", true);
+    D.cond = host_conv("dec.cond", true);
+    D.post = host_conv("dec.conv_post", false);
+    D.gin = hp.gin;
+    D.per = per;
+    for (int i = 0; i < n_ups; ++i) {
+      D.ups.push_back(host_conv("dec.ups." + std::to_string(i), true));
+      D.up_u.push_back(M.ups[i].u);
+    }
+    for (int r = 0; r < n_rb; ++r) {
+      std::vector<HostConv> c1, c2;
+      for (size_t l = 0; l < M.resblocks[r].c1.size(); ++l) {
+        c1.push_back(host_conv("dec.resblocks." + std::to_string(r) + ".convs1." + std::to_string(l), true));
+        c2.push_back(host_conv("dec.resblocks." + std::to_string(r) + ".convs2." + std::to_string(l), true));
+      }
+      D.res_c1.push_back(c1);
+      D.res_c2.push_back(c2);
+      D.res_dil.push_back(M.resblocks[r].dil);
+    }
+  }
+
+  std::ostringstream js;
+  js << "{\"kind\":\"synthesizer\",\"n_vocab\":" << hp.n_vocab << ",\"num_tones\":" << hp.n_tones << ",\"num_languages\":" << hp.n_lang
+     << ",\"hidden_channels\":" << hp.hidden << ",\"inter_channels\":" << hp.inter << ",\"gin_channels\":" << hp.gin
+     << ",\"n_speakers\":" << hp.n_speakers << ",\"n_layers\":" << M.enc.layers.size() << ",\"n_heads\":" << M.enc.heads
+     << ",\"filter_channels\":" << M.enc.filter << ",\"kernel_size\":" << M.enc.ksize << ",\"window_size\":" << M.enc.window
+     << ",\"use_transformer_flow\":" << (hp.transformer_flow ? "true" : "false") << ",\"n_flow_layer\":" << hp.n_flows
+     << ",\"n_layers_trans_flow\":" << hp.flow_layers << ",\"wn_layers\":" << hp.wn_layers << ",\"sdp_flows\":" << hp.sdp_flows
+     << ",\"upsample_rates\":[";
+  for (size_t i = 0; i < hp.up_rates.size(); ++i) js << (i ? "," : "") << hp.up_rates[i];
+  js << "],\"upsample_kernel_sizes\":[";
+  for (size_t i = 0; i < hp.up_kernels.size(); ++i) js << (i ? "," : "") << hp.up_kernels[i];
+  js << "],\"resblock_kernel_sizes\":[";
+  for (size_t i = 0; i < hp.res_kernels.size(); ++i) js << (i ? "," : "") << hp.res_kernels[i];
+  js << "],\"hop\":" << hp.hop << ",\"structural_binding\":" << (L.alias.empty() ? "false" : "true") << "}";
+  M.describe_json = js.str();
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward pieces
+// ---------------------------------------------------------------------------------------------
+enum WS { W_BERT = 0, W_H, W_QKV, W_CTX, W_Y, W_F1, W_STATS, W_G, W_STYLE, W_GG, W_DPX, W_DP1, W_DP2, W_LOGW, W_SDPX, W_SDPH,
+          W_SDPT, W_SDPZ, W_NSDP, W_W, W_EPS, W_Z, W_Z2, W_M, W_HF, W_META };
+
+struct Fwd {
+  SynthModel& M;
+  LaunchCtx ctx;
+
+  void conv(const ConvW& c, const float* in, int in_ld, float* out, int out_ld, const Segs& seg, int dil = 1, int act_in = ACT_NONE,
+            int act_out = ACT_NONE, const float* residual = nullptr, const float* bias_utt = nullptr) {
+    ConvArgs a;
+    a.in = in;
+    a.in_ld = in_ld;
+    a.w = c.w;
+    a.bias = c.b;
+    a.bias_utt = bias_utt;
+    a.out = out;
+    a.out_ld = out_ld;
+    a.residual = residual;
+    a.cin = c.cin;
+    a.cout = c.cout;
+    a.taps = c.k;
+    a.dil = dil;
+    a.off = -dil * ((c.k - 1) / 2);
+    a.act_in = act_in;
+    a.act_out = act_out;
+    a.seg = seg;
+    launch_conv(ctx, a);
+  }
+
+  // attentions.Encoder: h [rows, H] in place. g_lin: [B, H] = spk_emb_linear(g) or null.
+  void encoder(const EncoderW& E, float* h, const Segs& seg, int rows, const float* g /*[B,gin]*/, int gin, const Segs& bseg) {
+    const int H = E.hidden;
+    float* qkv = M.ws[W_QKV].as<float>();
+    float* ctxb = M.ws[W_CTX].as<float>();
+    float* y = M.ws[W_Y].as<float>();
+    float* f1 = M.ws[W_F1].as<float>();
+    for (size_t i = 0; i < E.layers.size(); ++i) {
+      const EncLayerW& L = E.layers[i];
+      if (E.has_spk && int(i) == E.cond_idx && g) {
+        float* gg = M.ws[W_GG].as<float>();
+        conv(E.spk, g, gin, gg, H, bseg);
+        launch_add_utt_vec(ctx, h, h, gg, H, H, seg);
+      }
+      conv(L.qkv, h, H, qkv, 3 * H, seg);
+      launch_rel_attention(ctx, ctxb, qkv, L.rel_k, L.rel_v, E.heads, E.head_dim, E.window, seg);
+      conv(L.o, ctxb, H, y, H, seg);
+      launch_layernorm(ctx, h, h, y, nullptr, L.n1.g, L.n1.b, 1e-5f, ACT_NONE, H, rows);
+      conv(L.f1, h, H, f1, E.filter, seg, 1, ACT_NONE, ACT_RELU);
+      // FFN uses asymmetric "same" padding ((k-1)/2, k/2); identical to symmetric for odd k
+      conv(L.f2, f1, E.filter, y, H, seg);
+      launch_layernorm(ctx, h, h, y, nullptr, L.n2.g, L.n2.b, 1e-5f, ACT_NONE, H, rows);
+    }
+  }
+
+  // DDSConv on x [rows, C] in place; t1/t2 scratch [rows, C]
+  void dds(const DDSW& D, float* x, float* t1, float* t2, int C, const Segs& seg, int rows) {
+    for (const auto& L : D.layers) {
+      launch_dwconv3(ctx, t1, x, L.sep_w, L.sep_b, C, L.dil, seg);
+      launch_layernorm(ctx, t1, t1, nullptr, nullptr, L.n1.g, L.n1.b, 1e-5f, ACT_GELU, C, rows);
+      conv(L.pw, t1, C, t2, C, seg);
+      launch_layernorm(ctx, x, t2, nullptr, x, L.n2.g, L.n2.b, 1e-5f, ACT_GELU, C, rows);
+    }
+  }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+void DBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return;
+  if (p) {
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    CUDA_CHECK(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+  }
+  size_t want = align_up(bytes + bytes / 4, 1 << 20);
+  CUDA_CHECK(cudaMalloc(&p, want));
+  cap = want;
+}
+
+void PinnedBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return;
+  if (p) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+  }
+  size_t want = align_up(bytes + bytes / 4, 1 << 16);
+  CUDA_CHECK(cudaMallocHost(&p, want));
+  cap = want;
+}
+
+sbv2_model* create_synth_model(const OnnxModel& m, int device) {
+  std::unique_ptr<SynthModel> M(new SynthModel());
+  M->device = device;
+  M->is_bert = false;
+  CUDA_CHECK(cudaSetDevice(device));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+  for (auto& w : M->ws) w.stream = M->stream;
+  M->metadata = m.metadata;
+  load_weights(*M, m);
+  // SBV2_B200_DECODER=fp32 selects the CUDA-core fp32 decoder kernels (debugging / kernel cross-checks).
+  const char* env = getenv("SBV2_B200_DECODER");
+  M->use_umma = !(env && std::string(env) == "fp32");
+  if (M->use_umma) M->umma = umma_decoder_create(M->dec_host, M.get());
+  M->dec_host = DecoderHostWeights();
+  CUDA_CHECK(cudaStreamSynchronize(M->stream));
+  return M.release();
+}
+
+void synth_set_seed(sbv2_model* m, uint64_t seed) {
+  auto* M = static_cast<SynthModel*>(m);
+  M->seed = seed;
+  M->rng_offset = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------------
+sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int batch) {
+  auto* M = static_cast<SynthModel*>(mm);
+  SBV2_REQUIRE(!M->is_bert, "synthesize called on a BERT model");
+  SBV2_REQUIRE(utts && batch > 0, "empty batch");
+  M->bind_device();
+  const HParams& hp = M->hp;
+  std::unique_ptr<sbv2_device_batch> b(new sbv2_device_batch());
+  b->B = batch;
+  b->xlen.resize(batch);
+  b->xstart.resize(batch);
+  b->zp_frames.assign(batch, 0);
+  int64_t nx = 0;
+  int n_nsdp = 0, n_nzp = 0;
+  for (int i = 0; i < batch; ++i) {
+    const sbv2_utterance& u = utts[i];
+    SBV2_REQUIRE(u.t_x > 0, "t_x must be positive");
+    SBV2_REQUIRE(u.t_x < (1 << 20), "t_x too large");
+    SBV2_REQUIRE(u.bert && u.x_tst && u.tones && u.lang_ids && u.style_vec, "null input pointer");
+    SBV2_REQUIRE(u.sid >= 0 && u.sid < hp.n_speakers, "speaker id out of range");
+    SBV2_REQUIRE(std::isfinite(u.sdp_ratio) && std::isfinite(u.length_scale) && std::isfinite(u.noise_scale) && std::isfinite(u.noise_scale_w),
+                 "non-finite scalar input");
+    for (int64_t t = 0; t < u.t_x; ++t) {
+      SBV2_REQUIRE(u.x_tst[t] >= 0 && u.x_tst[t] < hp.n_vocab, "symbol id out of range");
+      SBV2_REQUIRE(u.tones[t] >= 0 && u.tones[t] < hp.n_tones, "tone id out of range");
+      SBV2_REQUIRE(u.lang_ids[t] >= 0 && u.lang_ids[t] < hp.n_lang, "language id out of range");
+    }
+    b->xlen[i] = int(u.t_x);
+    b->xstart[i] = int(nx);
+    nx += u.t_x;
+    if (u.noise_sdp) ++n_nsdp;
+    if (u.noise_zp) {
+      ++n_nzp;
+      SBV2_REQUIRE(u.noise_zp_frames > 0, "noise_zp_frames must be positive when noise_zp is given");
+      b->zp_frames[i] = u.noise_zp_frames;
+    }
+    if (u.sdp_ratio != 0.f) b->any_sdp = true;
+  }
+  SBV2_REQUIRE(n_nsdp == 0 || n_nsdp == batch, "noise_sdp must be given for all utterances or none");
+  SBV2_REQUIRE(n_nzp == 0 || n_nzp == batch, "noise_zp must be given for all utterances or none");
+  b->has_noise_sdp = n_nsdp > 0;
+  b->has_noise_zp = n_nzp > 0;
+  b->Nx = nx;
+
+  // blob layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  b->o_x = take(nx * 4);
+  b->o_tone = take(nx * 4);
+  b->o_lang = take(nx * 4);
+  b->o_sid = take(batch * 8);
+  b->o_sdp_ratio = take(batch * 4);
+  b->o_ls = take(batch * 4);
+  b->o_ns = take(batch * 4);
+  b->o_nsw = take(batch * 4);
+  b->o_xstart = take(batch * 4);
+  b->o_xlen = take(batch * 4);
+  b->o_bert_off = take(batch * 8);
+  b->o_nsdp_off = take(batch * 8);
+  b->o_style = take(size_t(batch) * hp.style_dim * 4);
+  b->o_bert = take(size_t(nx) * hp.bert_dim * 4);
+  b->o_nsdp = take(size_t(nx) * 2 * 4);
+  const size_t total = off;
+
+  M->pin_in.ensure(total);
+  uint8_t* h = M->pin_in.as<uint8_t>();
+  int32_t* hx = reinterpret_cast<int32_t*>(h + b->o_x);
+  int32_t* htone = reinterpret_cast<int32_t*>(h + b->o_tone);
+  int32_t* hlang = reinterpret_cast<int32_t*>(h + b->o_lang);
+  int64_t* hsid = reinterpret_cast<int64_t*>(h + b->o_sid);
+  float* hratio = reinterpret_cast<float*>(h + b->o_sdp_ratio);
+  float* hls = reinterpret_cast<float*>(h + b->o_ls);
+  float* hns = reinterpret_cast<float*>(h + b->o_ns);
+  float* hnsw = reinterpret_cast<float*>(h + b->o_nsw);
+  int32_t* hxs = reinterpret_cast<int32_t*>(h + b->o_xstart);
+  int32_t* hxl = reinterpret_cast<int32_t*>(h + b->o_xlen);
+  int64_t* hboff = reinterpret_cast<int64_t*>(h + b->o_bert_off);
+  int64_t* hnoff = reinterpret_cast<int64_t*>(h + b->o_nsdp_off);
+  float* hstyle = reinterpret_cast<float*>(h + b->o_style);
+  float* hbert = reinterpret_cast<float*>(h + b->o_bert);
+  float* hnsdp = reinterpret_cast<float*>(h + b->o_nsdp);
+  for (int i = 0; i < batch; ++i) {
+    const sbv2_utterance& u = utts[i];
+    int s = b->xstart[i], n = b->xlen[i];
+    for (int t = 0; t < n; ++t) {
+      hx[s + t] = int32_t(u.x_tst[t]);
+      htone[s + t] = int32_t(u.tones[t]);
+      hlang[s + t] = int32_t(u.lang_ids[t]);
+    }
+    hsid[i] = u.sid;
+    hratio[i] = u.sdp_ratio;
+    hls[i] = u.length_scale;
+    hns[i] = u.noise_scale;
+    hnsw[i] = u.noise_scale_w;
+    hxs[i] = s;
+    hxl[i] = n;
+    hboff[i] = int64_t(s) * hp.bert_dim;
+    hnoff[i] = int64_t(s) * 2;
+    memcpy(hstyle + size_t(i) * hp.style_dim, u.style_vec, size_t(hp.style_dim) * 4);
+    memcpy(hbert + size_t(s) * hp.bert_dim, u.bert, size_t(n) * hp.bert_dim * 4);
+    if (u.noise_sdp) memcpy(hnsdp + size_t(s) * 2, u.noise_sdp, size_t(n) * 2 * 4);
+  }
+  b->in.stream = M->stream;
+  b->in.ensure(total);
+  CUDA_CHECK(cudaMemcpyAsync(b->in.p, h, total, cudaMemcpyHostToDevice, M->stream));
+  if (b->has_noise_zp) {
+    size_t tot = 0;
+    for (int i = 0; i < batch; ++i) tot += size_t(b->zp_frames[i]) * hp.inter;
+    b->zp.stream = M->stream;
+    b->zp.ensure(tot * 4);
+    size_t o = 0;
+    for (int i = 0; i < batch; ++i) {
+      size_t n = size_t(b->zp_frames[i]) * hp.inter;
+      CUDA_CHECK(cudaMemcpyAsync(b->zp.as<float>() + o, utts[i].noise_zp, n * 4, cudaMemcpyHostToDevice, M->stream));
+      o += n;
+    }
+  }
+  // the pinned staging buffer is reused by the next upload: wait for the copy
+  CUDA_CHECK(cudaStreamSynchronize(M->stream));
+  return b.release();
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder (fp32 reference path; the tensor-core path lives in umma_conv.cu)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct StageSegs {
+  Segs seg;           // rows at this stage
+  const int* dstart;  // device start array
+};
+
+void decoder_fp32(SynthModel& M, const float* z, const float* g /*[B,gin]*/, const Segs& yseg, const Segs& bseg,
+                  const std::vector<int>& ystart, const std::vector<int>& ylen, float* wave, DBuf& meta_buf) {
+  Fwd F{M, M.ctx()};
+  const HParams& hp = M.hp;
+  const int B = yseg.n;
+  const int n_st = int(M.ups.size());
+  // per-stage segment tables
+  std::vector<int> meta(size_t(2) * B * (n_st + 1));
+  std::vector<int64_t> rows(n_st + 1);
+  {
+    int mul = 1;
+    for (int s = 0; s <= n_st; ++s) {
+      if (s > 0) mul *= M.ups[s - 1].u;
+      for (int i = 0; i < B; ++i) {
+        meta[(size_t(2) * s) * B + i] = ystart[i] * mul;
+        meta[(size_t(2) * s + 1) * B + i] = ylen[i] * mul;
+      }
+      rows[s] = int64_t(ystart[B - 1] + ylen[B - 1]) * mul;
+    }
+  }
+  meta_buf.stream = M.stream;
+  meta_buf.ensure(meta.size() * 4);
+  CUDA_CHECK(cudaMemcpyAsync(meta_buf.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, M.stream));
+  CUDA_CHECK(cudaStreamSynchronize(M.stream));  // `meta` is a stack vector
+  auto segs_of = [&](int s) {
+    Segs g2;
+    g2.n = B;
+    g2.start = meta_buf.as<int>() + (size_t(2) * s) * B;
+    g2.len = meta_buf.as<int>() + (size_t(2) * s + 1) * B;
+    int mul = 1;
+    for (int q = 0; q < s; ++q) mul *= M.ups[q].u;
+    g2.max_len = yseg.max_len * mul;
+    return g2;
+  };
+  // cond(g) -> [B, C0]
+  float* gcond = M.ws[W_GG].as<float>();
+  M.ws[W_GG].ensure(size_t(B) * std::max(hp.up_initial, hp.hidden) * 4);
+  gcond = M.ws[W_GG].as<float>();
+  F.conv(M.dec_cond, g, hp.gin, gcond, hp.up_initial, bseg);
+  // buffers
+  size_t max_elems = 0;
+  for (int s = 0; s <= n_st; ++s) {
+    int C = s == 0 ? hp.up_initial : M.ups[s - 1].cout;
+    max_elems = std::max(max_elems, size_t(rows[s]) * C);
+  }
+  DBuf &bx = M.ws[W_QKV], &br = M.ws[W_CTX], &bt = M.ws[W_Y], &bs = M.ws[W_F1];
+  bx.ensure(max_elems * 4);
+  br.ensure(max_elems * 4);
+  bt.ensure(max_elems * 4);
+  bs.ensure(max_elems * 4);
+  float* x = bx.as<float>();
+  float* r = br.as<float>();
+  float* t1 = bt.as<float>();
+  float* xs = bs.as<float>();
+
+  Segs s0 = segs_of(0);
+  F.conv(M.dec_pre, z, hp.inter, xs, hp.up_initial, s0, 1, ACT_NONE, ACT_NONE, nullptr, gcond);
+  M.debug["dec_pre"] = DebugView{xs, rows[0], hp.up_initial, 4};
+  const int per = int(M.resblocks.size()) / n_st;
+  for (int s = 0; s < n_st; ++s) {
+    const UpW& U = M.ups[s];
+    Segs sin = segs_of(s), sout = segs_of(s + 1);
+    for (int ph = 0; ph < U.u; ++ph) {
+      ConvArgs a;
+      a.in = xs;
+      a.in_ld = U.cin;
+      a.w = U.phase_w[ph];
+      a.bias = U.b;
+      a.out = x;
+      a.out_ld = U.cout;
+      a.cin = U.cin;
+      a.cout = U.cout;
+      a.taps = U.k / U.u;
+      a.dil = -1;
+      a.off = U.phase_off[ph];
+      a.act_in = ACT_LRELU;
+      a.out_row_mul = U.u;
+      a.out_row_off = ph;
+      a.seg = sin;
+      a.seg_out_start = sout.start;
+      launch_conv(F.ctx, a);
+    }
+    const int C = U.cout;
+    for (int j = 0; j < per; ++j) {
+      const ResBlockW& R = M.resblocks[size_t(s) * per + j];
+      const float* cur = x;
+      for (size_t l = 0; l < R.c1.size(); ++l) {
+        F.conv(R.c1[l], cur, C, t1, C, sout, R.dil[l], ACT_LRELU, ACT_NONE);
+        bool last = l + 1 == R.c1.size();
+        ConvArgs a;
+        a.in = t1;
+        a.in_ld = C;
+        a.w = R.c2[l].w;
+        a.bias = R.c2[l].b;
+        a.out = last ? nullptr : r;
+        a.out_ld = C;
+        a.residual = cur;
+        a.cin = C;
+        a.cout = C;
+        a.taps = R.c2[l].k;
+        a.dil = 1;
+        a.off = -((R.c2[l].k - 1) / 2);
+        a.act_in = ACT_LRELU;
+        a.seg = sout;
+        if (last) {
+          a.accum_out = xs;
+          a.accum_mode = j == 0 ? ACC_SET : (j + 1 == per ? ACC_ADD_SCALE : ACC_ADD);
+          a.accum_div = float(per);
+          if (per == 1) {
+            a.accum_mode = ACC_SET;
+          }
+        }
+        launch_conv(F.ctx, a);
+        cur = r;
+      }
+    }
+  }
+  Segs sl = segs_of(n_st);
+  M.debug["dec_last"] = DebugView{xs, rows[n_st], M.dec_post_c, 4};
+  launch_dec_post(F.ctx, wave, xs, M.dec_post_w, M.dec_post_c, M.dec_post_k, sl);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// run
+// ---------------------------------------------------------------------------------------------
+void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
+  auto* Mp = static_cast<SynthModel*>(mm);
+  SynthModel& M = *Mp;
+  M.bind_device();
+  const HParams& hp = M.hp;
+  Fwd F{M, M.ctx()};
+  const LaunchCtx& ctx = F.ctx;
+  const int B = b->B;
+  const int H = hp.hidden;
+  const int64_t Nx = b->Nx;
+  uint8_t* in = b->in.as<uint8_t>();
+  const int* d_x = reinterpret_cast<const int*>(in + b->o_x);
+  const int* d_tone = reinterpret_cast<const int*>(in + b->o_tone);
+  const int* d_lang = reinterpret_cast<const int*>(in + b->o_lang);
+  const int64_t* d_sid = reinterpret_cast<const int64_t*>(in + b->o_sid);
+  const float* d_ratio = reinterpret_cast<const float*>(in + b->o_sdp_ratio);
+  const float* d_ls = reinterpret_cast<const float*>(in + b->o_ls);
+  const float* d_ns = reinterpret_cast<const float*>(in + b->o_ns);
+  const float* d_nsw = reinterpret_cast<const float*>(in + b->o_nsw);
+  const float* d_style = reinterpret_cast<const float*>(in + b->o_style);
+  Segs xseg;
+  xseg.start = reinterpret_cast<const int*>(in + b->o_xstart);
+  xseg.len = reinterpret_cast<const int*>(in + b->o_xlen);
+  xseg.n = B;
+  xseg.max_len = *std::max_element(b->xlen.begin(), b->xlen.end());
+  // "batch rows" segment: one segment of B rows, for per-utterance linears
+  // (start = 0, len = B) lives in the ylen_dev buffer's first two ints
+  b->ylen_dev.stream = M.stream;
+  b->ylen_dev.ensure(size_t(B + 2) * 4);
+  {
+    int two[2] = {0, B};
+    CUDA_CHECK(cudaMemcpyAsync(b->ylen_dev.p, two, 8, cudaMemcpyHostToDevice, M.stream));
+  }
+  Segs bseg;
+  bseg.start = b->ylen_dev.as<int>();
+  bseg.len = b->ylen_dev.as<int>() + 1;
+  bseg.n = 1;
+  bseg.max_len = B;
+  int* d_ylen = b->ylen_dev.as<int>() + 2;
+
+  auto ens = [&](int id, size_t floats) { M.ws[id].ensure(floats * 4); return M.ws[id].as<float>(); };
+  const int Cmax = std::max(std::max(3 * H, M.enc.filter), std::max(hp.dp_filter, 2 * hp.inter));
+  float* bert = ens(W_BERT, size_t(Nx) * hp.bert_dim);
+  float* h = ens(W_H, size_t(Nx) * H);
+  ens(W_QKV, size_t(Nx) * 3 * H);
+  ens(W_CTX, size_t(Nx) * H);
+  ens(W_Y, size_t(Nx) * H);
+  ens(W_F1, size_t(Nx) * Cmax);
+  float* stats = ens(W_STATS, size_t(Nx) * 2 * hp.inter);
+  float* g = ens(W_G, size_t(B) * hp.gin);
+  float* style_emb = ens(W_STYLE, size_t(B) * H);
+  ens(W_GG, size_t(B) * std::max(H, hp.up_initial));
+  float* dpx = ens(W_DPX, size_t(Nx) * H);
+  float* dp1 = ens(W_DP1, size_t(Nx) * hp.dp_filter);
+  float* dp2 = ens(W_DP2, size_t(Nx) * hp.dp_filter);
+  float* logw = ens(W_LOGW, size_t(Nx));
+  float* wbuf = ens(W_W, size_t(Nx));
+
+  // ---- speaker embedding, text encoder ------------------------------------------------------
+  launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
+  launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_bert), reinterpret_cast<const int64_t*>(in + b->o_bert_off),
+                  nullptr, bert, hp.bert_dim, xseg);
+  F.conv(M.bert_proj, bert, hp.bert_dim, h, H, xseg);
+  F.conv(M.style_proj, d_style, hp.style_dim, style_emb, H, bseg);
+  launch_embed_combine(ctx, h, d_x, d_tone, d_lang, M.emb, M.tone_emb, M.lang_emb, style_emb, H, hp.n_vocab, hp.n_tones,
+                       hp.n_lang, xseg);
+  F.encoder(M.enc, h, xseg, int(Nx), g, hp.gin, bseg);
+  F.conv(M.enc_proj, h, H, stats, 2 * hp.inter, xseg);
+  M.debug["enc_x"] = DebugView{h, Nx, H, 4};
+  M.debug["stats"] = DebugView{stats, Nx, 2 * hp.inter, 4};
+
+  // ---- duration predictor -------------------------------------------------------------------
+  {
+    float* gc = M.ws[W_GG].as<float>();
+    F.conv(M.dp_cond, g, hp.gin, gc, H, bseg);
+    launch_add_utt_vec(ctx, dpx, h, gc, H, H, xseg);
+    F.conv(M.dp_c1, dpx, H, dp1, hp.dp_filter, xseg, 1, ACT_NONE, ACT_RELU);
+    launch_layernorm(ctx, dp1, dp1, nullptr, nullptr, M.dp_n1.g, M.dp_n1.b, 1e-5f, ACT_NONE, hp.dp_filter, int(Nx));
+    F.conv(M.dp_c2, dp1, hp.dp_filter, dp2, hp.dp_filter, xseg, 1, ACT_NONE, ACT_RELU);
+    launch_layernorm(ctx, dp2, dp2, nullptr, nullptr, M.dp_n2.g, M.dp_n2.b, 1e-5f, ACT_NONE, hp.dp_filter, int(Nx));
+    F.conv(M.dp_proj, dp2, hp.dp_filter, logw, 1, xseg);
+    M.debug["logw_dp"] = DebugView{logw, Nx, 1, 4};
+  }
+
+  // ---- stochastic duration predictor (reverse) -----------------------------------------------
+  float* zs = nullptr;
+  if (b->any_sdp) {
+    float* sx = ens(W_SDPX, size_t(Nx) * H);
+    float* sh = ens(W_SDPH, size_t(Nx) * H);
+    float* t1 = ens(W_SDPT, size_t(Nx) * H * 2);
+    float* t2 = t1 + size_t(Nx) * H;
+    zs = ens(W_SDPZ, size_t(Nx) * 2);
+    float* nrm = ens(W_NSDP, size_t(Nx) * 2);
+    float* gc = M.ws[W_GG].as<float>();
+    F.conv(M.sdp_cond, g, hp.gin, gc, H, bseg);
+    F.conv(M.sdp_pre, h, H, sx, H, xseg, 1, ACT_NONE, ACT_NONE, nullptr, gc);
+    F.dds(M.sdp_dds, sx, t1, t2, H, xseg, int(Nx));
+    F.conv(M.sdp_proj, sx, H, sh, H, xseg);  // conditioning for the flows
+    float* cond = sh;
+    if (b->has_noise_sdp) {
+      launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_nsdp), reinterpret_cast<const int64_t*>(in + b->o_nsdp_off),
+                      nullptr, nrm, 2, xseg);
+    } else {
+      launch_randn(ctx, nrm, Nx * 2, M.seed, M.rng_offset);
+      M.rng_offset += uint64_t(Nx) * 2;
+    }
+    launch_sdp_init(ctx, zs, nrm, d_nsw, xseg);
+    // reversed flow list with the first ConvFlow dropped: Flip, CF[n-1], Flip, ..., CF[1], Flip, EA
+    float* hh = sx;  // sx no longer needed after sdp_proj
+    const float inv_sqrt = 1.0f / sqrtf(float(H));
+    for (int i = int(M.sdp_cf.size()) - 1; i >= 1; --i) {
+      const ConvFlowW& cf = M.sdp_cf[i];
+      launch_sdp_flip(ctx, zs, int(Nx));
+      launch_convflow_pre(ctx, hh, zs, cf.pre_w, cf.pre_b, cond, H, int(Nx));
+      F.dds(cf.dds, hh, t1, t2, H, xseg, int(Nx));
+      F.conv(cf.proj, hh, H, t1, cf.proj.cout, xseg);
+      launch_convflow_spline(ctx, zs, t1, cf.proj.cout, hp.sdp_bins, 5.0f, inv_sqrt, int(Nx));
+    }
+    launch_sdp_flip(ctx, zs, int(Nx));
+    launch_sdp_affine(ctx, zs, M.sdp_ea_m, M.sdp_ea_logs, int(Nx));
+    M.debug["z_sdp"] = DebugView{zs, Nx, 2, 4};
+  }
+
+  // ---- durations / alignment -------------------------------------------------------------------
+  b->dur.stream = b->cum.stream = M.stream;
+  b->dur.ensure(size_t(Nx) * 4);
+  b->cum.ensure(size_t(Nx) * 4);
+  launch_durations(ctx, logw, zs, d_ratio, d_ls, wbuf, b->dur.as<int>(), b->cum.as<int>(), d_ylen, xseg);
+  M.debug["w"] = DebugView{wbuf, Nx, 1, 4};
+  M.pin_ylen.ensure(size_t(B) * 4);
+  CUDA_CHECK(cudaMemcpyAsync(M.pin_ylen.p, d_ylen, size_t(B) * 4, cudaMemcpyDeviceToHost, M.stream));
+  CUDA_CHECK(cudaStreamSynchronize(M.stream));
+  b->ylen.assign(M.pin_ylen.as<int>(), M.pin_ylen.as<int>() + B);
+  b->ystart.resize(B);
+  int64_t ny = 0;
+  int ymax = 0;
+  for (int i = 0; i < B; ++i) {
+    b->ystart[i] = int(ny);
+    ny += b->ylen[i];
+    ymax = std::max(ymax, b->ylen[i]);
+    if (b->has_noise_zp && b->zp_frames[i] < b->ylen[i])
+      fail(SBV2_ERR_INVALID_ARGUMENT, "noise_zp has " + std::to_string(b->zp_frames[i]) + " frames but utterance " +
+                                          std::to_string(i) + " needs T_y = " + std::to_string(b->ylen[i]));
+  }
+  if (ny * hp.hop > (int64_t(1) << 31) - 1) fail(SBV2_ERR_INVALID_ARGUMENT, "batch too long: more than 2^31 samples");
+  b->Ny = ny;
+  {
+    // ymeta: ystart[B], ylen[B], zp_ld[B] (ints) then zp_off[B] (int64)
+    std::vector<int> meta(size_t(3) * B);
+    std::vector<int64_t> zoff(B);
+    int64_t o = 0;
+    for (int i = 0; i < B; ++i) {
+      meta[i] = b->ystart[i];
+      meta[B + i] = b->ylen[i];
+      meta[2 * B + i] = int(b->zp_frames[i]);
+      zoff[i] = o;
+      o += b->zp_frames[i] * hp.inter;
+    }
+    size_t ibytes = align_up(meta.size() * 4, 256);
+    b->ymeta.stream = M.stream;
+    b->ymeta.ensure(ibytes + zoff.size() * 8);
+    CUDA_CHECK(cudaMemcpyAsync(b->ymeta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, M.stream));
+    CUDA_CHECK(cudaMemcpyAsync(b->ymeta.as<uint8_t>() + ibytes, zoff.data(), zoff.size() * 8, cudaMemcpyHostToDevice, M.stream));
+    CUDA_CHECK(cudaStreamSynchronize(M.stream));
+    b->o_zp_off = ibytes;
+  }
+  Segs yseg;
+  yseg.start = b->ymeta.as<int>();
+  yseg.len = b->ymeta.as<int>() + B;
+  yseg.n = B;
+  yseg.max_len = ymax;
+
+  // ---- expand + prior sample ---------------------------------------------------------------------
+  const int C = hp.inter;
+  float* eps = ens(W_EPS, size_t(ny) * C);
+  float* z = ens(W_Z, size_t(ny) * C);
+  float* z2 = ens(W_Z2, size_t(ny) * C);
+  float* mbuf = ens(W_M, size_t(ny) * C);
+  b->f2p.stream = M.stream;
+  b->f2p.ensure(size_t(ny) * 4);
+  if (b->has_noise_zp) {
+    launch_cm_to_rm(ctx, b->zp.as<float>(), reinterpret_cast<const int64_t*>(b->ymeta.as<uint8_t>() + b->o_zp_off),
+                    b->ymeta.as<int>() + 2 * B, eps, C, yseg);
+  } else {
+    launch_randn(ctx, eps, ny * C, M.seed ^ 0x9E3779B97F4A7C15ULL, M.rng_offset);
+    M.rng_offset += uint64_t(ny) * C;
+  }
+  launch_expand(ctx, z, b->f2p.as<int>(), stats, b->cum.as<int>(), eps, d_ns, C, xseg, yseg);
+  M.debug["z_p"] = DebugView{z, ny, C, 4};
+
+  // ---- flow (reverse) ------------------------------------------------------------------------------
+  ens(W_QKV, size_t(ny) * 3 * H);
+  ens(W_CTX, size_t(ny) * H);
+  ens(W_Y, size_t(ny) * H);
+  ens(W_F1, size_t(ny) * std::max(hp.transformer_flow ? M.flow[0].enc.filter : 2 * H, 2 * H));
+  float* hf = ens(W_HF, size_t(ny) * H);
+  float* zc = z;
+  float* zn = z2;
+  for (int i = hp.n_flows - 1; i >= 0; --i) {
+    const CouplingW& cp = M.flow[i];
+    launch_flip_channels(ctx, zn, zc, C, ny);
+    std::swap(zc, zn);
+    // x0 = zc[:, :C/2]
+    F.conv(cp.pre, zc, C, hf, H, yseg);
+    if (hp.transformer_flow) {
+      F.encoder(cp.enc, hf, yseg, int(ny), g, hp.gin, bseg);
+      F.conv(cp.post, hf, H, mbuf, C / 2, yseg);
+    } else {
+      // WN: cond = cond_layer(g) [B, 2H*n]; per layer gate + res/skip
+      const WNW& W = cp.wn;
+      const int nl = int(W.in_layers.size());
+      float* gcond = ens(W_STYLE, size_t(B) * 2 * H * nl);
+      F.conv(W.cond, g, hp.gin, gcond, 2 * H * nl, bseg);
+      float* a = M.ws[W_F1].as<float>();    // [ny, 2H]
+      float* acts = M.ws[W_CTX].as<float>();  // [ny, H]
+      float* rs = M.ws[W_QKV].as<float>();   // [ny, 2H]
+      float* skip = M.ws[W_Y].as<float>();   // [ny, H]
+      for (int l = 0; l < nl; ++l) {
+        F.conv(W.in_layers[l], hf, H, a, 2 * H, yseg);
+        launch_wn_gate(ctx, acts, a, gcond, 2 * H * nl, l * 2 * H, H, yseg);
+        F.conv(W.res_skip[l], acts, H, rs, W.res_skip[l].cout, yseg);
+        launch_wn_res_skip(ctx, hf, skip, rs, H, l == nl - 1, l == 0, ny);
+      }
+      F.conv(cp.post, skip, H, mbuf, C / 2, yseg);
+    }
+    launch_coupling_sub(ctx, zc, mbuf, C, ny);
+  }
+  M.debug["z"] = DebugView{zc, ny, C, 4};
+
+  // ---- decoder ---------------------------------------------------------------------------------------
+  b->wave.stream = M.stream;
+  b->wave.ensure(size_t(ny) * hp.hop * 4);
+  if (M.use_umma && M.umma) {
+    umma_decoder_run(M.umma, &M, zc, g, B, b->ystart, b->ylen, b->wave.as<float>());
+  } else {
+    decoder_fp32(M, zc, g, yseg, bseg, b->ystart, b->ylen, b->wave.as<float>(), M.ws[W_META]);
+  }
+  b->ran = true;
+}
+
+int64_t synth_total_samples(sbv2_model* m, const sbv2_device_batch* b) { return b->Ny * static_cast<SynthModel*>(m)->hp.hop; }
+
+void synth_batch_ty(const sbv2_device_batch* b, int64_t* ty) {
+  for (int i = 0; i < b->B; ++i) ty[i] = b->ylen[i];
+}
+
+void synth_download(sbv2_model* mm, sbv2_device_batch* b, float** out_samples, int64_t* out_n, int32_t** out_dur, int32_t** out_f2p) {
+  auto* M = static_cast<SynthModel*>(mm);
+  SBV2_REQUIRE(b->ran, "batch has not been run");
+  M->bind_device();
+  const int64_t total = b->Ny * M->hp.hop;
+  float* host = static_cast<float*>(alloc_out(size_t(std::max<int64_t>(total, 1)) * 4, true));
+  int32_t* hdur = nullptr;
+  int32_t* hf2p = nullptr;
+  try {
+    CUDA_CHECK(cudaMemcpyAsync(host, b->wave.p, size_t(total) * 4, cudaMemcpyDeviceToHost, M->stream));
+    if (out_dur && !b->decode_only) {
+      hdur = static_cast<int32_t*>(alloc_out(size_t(b->Nx) * 4, true));
+      CUDA_CHECK(cudaMemcpyAsync(hdur, b->dur.p, size_t(b->Nx) * 4, cudaMemcpyDeviceToHost, M->stream));
+    }
+    if (out_f2p && !b->decode_only) {
+      hf2p = static_cast<int32_t*>(alloc_out(size_t(b->Ny) * 4, true));
+      CUDA_CHECK(cudaMemcpyAsync(hf2p, b->f2p.p, size_t(b->Ny) * 4, cudaMemcpyDeviceToHost, M->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(M->stream));
+  } catch (...) {
+    free_out(host);
+    free_out(hdur);
+    free_out(hf2p);
+    throw;
+  }
+  *out_samples = host;
+  if (out_n)
+    for (int i = 0; i < b->B; ++i) out_n[i] = int64_t(b->ylen[i]) * M->hp.hop;
+  if (out_dur) *out_dur = hdur;
+  if (out_f2p) *out_f2p = hf2p;
+}
+
+void synth_batch_free(sbv2_device_batch* b) { delete b; }
+
+// HiFi-GAN decoder alone (config 3)
+void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, const int64_t* sid, int batch, float** out_samples,
+                  int64_t* out_n) {
+  auto* Mp = static_cast<SynthModel*>(mm);
+  SynthModel& M = *Mp;
+  SBV2_REQUIRE(!M.is_bert, "decode called on a BERT model");
+  SBV2_REQUIRE(z && t_y && sid && batch > 0, "empty batch");
+  M.bind_device();
+  const HParams& hp = M.hp;
+  sbv2_device_batch b;
+  b.B = batch;
+  b.decode_only = true;
+  b.ylen.resize(batch);
+  b.ystart.resize(batch);
+  int64_t ny = 0;
+  int ymax = 0;
+  for (int i = 0; i < batch; ++i) {
+    SBV2_REQUIRE(t_y[i] > 0 && t_y[i] < (1 << 22), "t_y out of range");
+    SBV2_REQUIRE(sid[i] >= 0 && sid[i] < hp.n_speakers, "speaker id out of range");
+    b.ylen[i] = int(t_y[i]);
+    b.ystart[i] = int(ny);
+    ny += t_y[i];
+    ymax = std::max(ymax, b.ylen[i]);
+  }
+  SBV2_REQUIRE(ny * hp.hop < (int64_t(1) << 31), "batch too long");
+  b.Ny = ny;
+  const int C = hp.inter;
+  // stage z (channel-major) + meta
+  size_t meta_ints = size_t(2) * batch + 2;
+  size_t o_meta = 0, o_off = align_up(meta_ints * 4, 256), o_sid = align_up(o_off + size_t(batch) * 8, 256),
+         o_z = align_up(o_sid + size_t(batch) * 8, 256), total = o_z + size_t(ny) * C * 4;
+  M.pin_in.ensure(total);
+  uint8_t* hbuf = M.pin_in.as<uint8_t>();
+  int* hmeta = reinterpret_cast<int*>(hbuf + o_meta);
+  int64_t* hoff = reinterpret_cast<int64_t*>(hbuf + o_off);
+  int64_t* hsid = reinterpret_cast<int64_t*>(hbuf + o_sid);
+  float* hz = reinterpret_cast<float*>(hbuf + o_z);
+  for (int i = 0; i < batch; ++i) {
+    hmeta[i] = b.ystart[i];
+    hmeta[batch + i] = b.ylen[i];
+    hoff[i] = int64_t(b.ystart[i]) * C;
+    hsid[i] = sid[i];
+    memcpy(hz + size_t(b.ystart[i]) * C, z[i], size_t(b.ylen[i]) * C * 4);
+  }
+  hmeta[2 * batch] = 0;
+  hmeta[2 * batch + 1] = batch;
+  b.in.stream = M.stream;
+  b.in.ensure(total);
+  CUDA_CHECK(cudaMemcpyAsync(b.in.p, hbuf, total, cudaMemcpyHostToDevice, M.stream));
+  uint8_t* in = b.in.as<uint8_t>();
+  Segs yseg;
+  yseg.start = reinterpret_cast<const int*>(in + o_meta);
+  yseg.len = yseg.start + batch;
+  yseg.n = batch;
+  yseg.max_len = ymax;
+  Segs bseg;
+  bseg.start = yseg.start + 2 * batch;
+  bseg.len = bseg.start + 1;
+  bseg.n = 1;
+  bseg.max_len = batch;
+  M.ws[W_Z].ensure(size_t(ny) * C * 4);
+  M.ws[W_G].ensure(size_t(batch) * hp.gin * 4);
+  float* zr = M.ws[W_Z].as<float>();
+  float* g = M.ws[W_G].as<float>();
+  LaunchCtx ctx = M.ctx();
+  launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + o_z), reinterpret_cast<const int64_t*>(in + o_off), nullptr, zr, C, yseg);
+  launch_gather_rows(ctx, g, M.emb_g, reinterpret_cast<const int64_t*>(in + o_sid), batch, hp.gin, hp.n_speakers);
+  b.wave.stream = M.stream;
+  b.wave.ensure(size_t(ny) * hp.hop * 4);
+  if (M.use_umma && M.umma) {
+    umma_decoder_run(M.umma, &M, zr, g, batch, b.ystart, b.ylen, b.wave.as<float>());
+  } else {
+    decoder_fp32(M, zr, g, yseg, bseg, b.ystart, b.ylen, b.wave.as<float>(), M.ws[W_META]);
+  }
+  b.ran = true;
+  synth_download(mm, &b, out_samples, out_n, nullptr, nullptr);
+}
+
+}  // namespace sbv2

@@ -1,0 +1,237 @@
+"""Writers for the asset formats the backend loads: ONNX ModelProto (hand-encoded protobuf — the
+``onnx`` package is not available offline), ``.sbv2`` (zstd(tar)), ``style_vectors.json`` and the
+``.aivmx`` metadata entry.  Used to mint synthetic models for tests and benchmarks; the layouts
+follow /root/reference/scripts/convert/convert_model.py:39-46,115-174 and
+crates/sbv2_core/src/tts.rs:93-108.
+"""
+from __future__ import annotations
+
+import base64
+import ctypes
+import io
+import json
+import struct
+import tarfile
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# ---- protobuf wire helpers -------------------------------------------------------------------
+
+
+def _varint(v: int) -> bytes:
+    if v < 0:
+        v += 1 << 64
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _key(field: int, wt: int) -> bytes:
+    return _varint((field << 3) | wt)
+
+
+def _ld(field: int, payload: bytes) -> bytes:
+    return _key(field, 2) + _varint(len(payload)) + payload
+
+
+def _vi(field: int, v: int) -> bytes:
+    return _key(field, 0) + _varint(v)
+
+
+def _s(field: int, s: str) -> bytes:
+    return _ld(field, s.encode("utf-8"))
+
+
+_DTYPES = {np.dtype("float32"): 1, np.dtype("int64"): 7, np.dtype("float16"): 10, np.dtype("int32"): 6,
+           np.dtype("float64"): 11}
+
+
+def tensor_proto(name: str, arr: np.ndarray, raw: bool = True) -> bytes:
+    arr = np.ascontiguousarray(arr)
+    out = b"".join(_vi(1, int(d)) for d in arr.shape)
+    out += _vi(2, _DTYPES[arr.dtype])
+    out += _s(8, name)
+    if raw:
+        out += _ld(9, arr.tobytes())
+    else:
+        assert arr.dtype == np.float32
+        out += _ld(4, arr.tobytes())  # packed float_data
+    return out
+
+
+def attribute_ints(name: str, vals: Sequence[int]) -> bytes:
+    out = _s(1, name)
+    out += _ld(8, b"".join(_varint(int(v)) for v in vals))
+    out += _vi(20, 7)  # AttributeType.INTS
+    return out
+
+
+def attribute_int(name: str, v: int) -> bytes:
+    return _s(1, name) + _vi(3, int(v)) + _vi(20, 2)
+
+
+def node_proto(op_type: str, inputs: Sequence[str], outputs: Sequence[str], name: str = "",
+               attrs: Iterable[bytes] = ()) -> bytes:
+    out = b"".join(_s(1, i) for i in inputs)
+    out += b"".join(_s(2, o) for o in outputs)
+    if name:
+        out += _s(3, name)
+    out += _s(4, op_type)
+    out += b"".join(_ld(5, a) for a in attrs)
+    return out
+
+
+def value_info(name: str) -> bytes:
+    return _s(1, name)
+
+
+def model_proto(initializers: Dict[str, np.ndarray], nodes: Sequence[bytes] = (), inputs: Sequence[str] = (),
+                outputs: Sequence[str] = (), metadata: Optional[Dict[str, str]] = None,
+                producer: str = "sbv2_b200.assets", packed_float_names: Sequence[str] = ()) -> bytes:
+    g = b"".join(_ld(1, n) for n in nodes)
+    g += _s(2, "main_graph")
+    for name, arr in initializers.items():
+        g += _ld(5, tensor_proto(name, arr, raw=name not in packed_float_names))
+    g += b"".join(_ld(11, value_info(n)) for n in inputs)
+    g += b"".join(_ld(12, value_info(n)) for n in outputs)
+    m = _vi(1, 8) + _s(2, producer) + _ld(7, g)
+    m += _ld(8, _s(1, "") + _vi(2, 17))  # opset_import
+    for k, v in (metadata or {}).items():
+        m += _ld(14, _s(1, k) + _s(2, v))
+    return m
+
+
+# ---- synthesizer / deberta graphs --------------------------------------------------------------
+
+SYNTH_INPUTS = ["x_tst", "x_tst_lengths", "sid", "tones", "language", "bert", "style_vec", "length_scale",
+                "sdp_ratio", "noise_scale", "noise_scale_w"]  # convert_model.py:141-153
+
+
+def synth_onnx(state: Dict[str, np.ndarray], upsample_rates: Sequence[int], resblock_dilations: Sequence[Sequence[int]],
+               anonymize_weight_norm: bool = False, metadata: Optional[Dict[str, str]] = None) -> bytes:
+    """ModelProto for a JP-Extra synthesizer whose initializers are ``state`` (upstream state_dict
+    names, weight-norm folded).  The decoder's Conv / ConvTranspose nodes are emitted in execution
+    order with their strides / dilations, as a traced export carries them; with
+    ``anonymize_weight_norm`` the weight-normed decoder convs get ``onnx::Conv_N`` names like a real
+    export after constant folding."""
+    inits: Dict[str, np.ndarray] = {}
+    rename: Dict[str, str] = {}
+    counter = [1000]
+
+    def reg(name: str) -> str:
+        if anonymize_weight_norm and (name.startswith("dec.ups") or name.startswith("dec.resblocks")) \
+                and name.endswith(".weight"):
+            op = "ConvTranspose" if name.startswith("dec.ups") else "Conv"
+            counter[0] += 1
+            rename[name] = f"onnx::{op}_{counter[0]}"
+            return rename[name]
+        return name
+
+    nodes: List[bytes] = []
+    n_ups = sum(1 for k in state if k.startswith("dec.ups.") and k.endswith(".weight"))
+    n_res_per = len(resblock_dilations)
+    cur = "dec_in"
+    nodes.append(node_proto("Conv", [cur, "dec.conv_pre.weight", "dec.conv_pre.bias"], ["dec_pre"], "/dec/conv_pre/Conv",
+                            [attribute_ints("dilations", [1]), attribute_ints("kernel_shape", [7]),
+                             attribute_ints("pads", [3, 3]), attribute_ints("strides", [1]), attribute_int("group", 1)]))
+    cur = "dec_pre"
+    for i in range(n_ups):
+        w = state[f"dec.ups.{i}.weight"]
+        k, u = w.shape[2], int(upsample_rates[i])
+        p = (k - u) // 2
+        nodes.append(node_proto("ConvTranspose", [cur, reg(f"dec.ups.{i}.weight"), f"dec.ups.{i}.bias"], [f"up{i}"],
+                                f"/dec/ups.{i}/ConvTranspose",
+                                [attribute_ints("dilations", [1]), attribute_ints("kernel_shape", [k]),
+                                 attribute_ints("pads", [p, p]), attribute_ints("strides", [u]), attribute_int("group", 1)]))
+        cur = f"up{i}"
+        for j in range(n_res_per):
+            rb = i * n_res_per + j
+            x = cur
+            for l, d in enumerate(resblock_dilations[j]):
+                for which, dd in (("convs1", d), ("convs2", 1)):
+                    nm = f"dec.resblocks.{rb}.{which}.{l}"
+                    kk = state[nm + ".weight"].shape[2]
+                    pad = (kk * dd - dd) // 2
+                    nodes.append(node_proto("Conv", [x, reg(nm + ".weight"), nm + ".bias"], [nm + "_out"],
+                                            f"/dec/resblocks.{rb}/{which}.{l}/Conv",
+                                            [attribute_ints("dilations", [dd]), attribute_ints("kernel_shape", [kk]),
+                                             attribute_ints("pads", [pad, pad]), attribute_ints("strides", [1]),
+                                             attribute_int("group", 1)]))
+                    x = nm + "_out"
+    for k_, v in state.items():
+        inits[rename.get(k_, k_)] = np.asarray(v)
+    return model_proto(inits, nodes, SYNTH_INPUTS, ["output"], metadata)
+
+
+def deberta_onnx(state: Dict[str, np.ndarray], metadata: Optional[Dict[str, str]] = None) -> bytes:
+    """ModelProto for the DeBERTa-v2 feature encoder; initializers keep HF ``state_dict`` names
+    (``deberta.embeddings.word_embeddings.weight`` ...). scripts/convert/convert_deberta.py:47-48."""
+    return model_proto({k: np.asarray(v) for k, v in state.items()}, (), ["input_ids", "token_type_ids", "attention_mask"],
+                       ["output"], metadata)
+
+
+# ---- containers --------------------------------------------------------------------------------
+
+_zstd = None
+
+
+def _libzstd():
+    global _zstd
+    if _zstd is None:
+        lib = ctypes.CDLL("libzstd.so.1")
+        lib.ZSTD_compressBound.restype = ctypes.c_size_t
+        lib.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+        lib.ZSTD_compress.restype = ctypes.c_size_t
+        lib.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        lib.ZSTD_isError.restype = ctypes.c_uint
+        lib.ZSTD_isError.argtypes = [ctypes.c_size_t]
+        _zstd = lib
+    return _zstd
+
+
+def zstd_compress(data: bytes, level: int = 3) -> bytes:
+    lib = _libzstd()
+    bound = lib.ZSTD_compressBound(len(data))
+    dst = ctypes.create_string_buffer(bound)
+    n = lib.ZSTD_compress(dst, bound, data, len(data), level)
+    if lib.ZSTD_isError(n):
+        raise RuntimeError("zstd compress failed")
+    return dst.raw[:n]
+
+
+def style_json(style_vectors: np.ndarray) -> bytes:
+    arr = np.asarray(style_vectors, dtype=np.float32)
+    return json.dumps({"data": arr.tolist(), "shape": list(arr.shape)}).encode("utf-8")
+
+
+def sbv2_file(onnx_bytes: bytes, style_vectors: np.ndarray, level: int = 3, extra: Optional[Dict[str, bytes]] = None,
+              omit: Sequence[str] = ()) -> bytes:
+    """zstd(tar{version.txt, model.onnx, style_vectors.json}) — convert_model.py:159-174."""
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w") as w:
+        def add(name: str, b: bytes):
+            ti = tarfile.TarInfo(name)
+            ti.size = len(b)
+            w.addfile(ti, io.BytesIO(b))
+        entries = {"version.txt": b"1", "model.onnx": onnx_bytes, "style_vectors.json": style_json(style_vectors)}
+        entries.update(extra or {})
+        for k, v in entries.items():
+            if k not in omit:
+                add(k, v)
+    return zstd_compress(buf.getvalue(), level)
+
+
+def aivmx_metadata(style_vectors: np.ndarray, fortran: bool = False) -> Dict[str, str]:
+    arr = np.asarray(style_vectors, dtype=np.float32)
+    if fortran:
+        arr = np.asfortranarray(arr)
+    b = io.BytesIO()
+    np.save(b, arr)
+    return {"aivm_style_vectors": base64.b64encode(b.getvalue()).decode("ascii")}
