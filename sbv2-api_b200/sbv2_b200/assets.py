@@ -95,16 +95,17 @@ def value_info(name: str) -> bytes:
 def model_proto(initializers: Dict[str, np.ndarray], nodes: Sequence[bytes] = (), inputs: Sequence[str] = (),
                 outputs: Sequence[str] = (), metadata: Optional[Dict[str, str]] = None,
                 producer: str = "sbv2_b200.assets", packed_float_names: Sequence[str] = ()) -> bytes:
-    g = b"".join(_ld(1, n) for n in nodes)
-    g += _s(2, "main_graph")
+    parts = [_ld(1, n) for n in nodes]
+    parts.append(_s(2, "main_graph"))
     for name, arr in initializers.items():
-        g += _ld(5, tensor_proto(name, arr, raw=name not in packed_float_names))
-    g += b"".join(_ld(11, value_info(n)) for n in inputs)
-    g += b"".join(_ld(12, value_info(n)) for n in outputs)
-    m = _vi(1, 8) + _s(2, producer) + _ld(7, g)
-    m += _ld(8, _s(1, "") + _vi(2, 17))  # opset_import
+        parts.append(_ld(5, tensor_proto(name, arr, raw=name not in packed_float_names)))
+    parts += [_ld(11, value_info(n)) for n in inputs]
+    parts += [_ld(12, value_info(n)) for n in outputs]
+    g = b"".join(parts)
+    mparts = [_vi(1, 8), _s(2, producer), _ld(7, g), _ld(8, _s(1, "") + _vi(2, 17))]  # ir_version, producer, graph, opset
     for k, v in (metadata or {}).items():
-        m += _ld(14, _s(1, k) + _s(2, v))
+        mparts.append(_ld(14, _s(1, k) + _s(2, v)))
+    m = b"".join(mparts)
     return m
 
 
