@@ -146,6 +146,13 @@ int64_t sbv2_model_launch_count(const sbv2_model* model);
 /* CUDA stream the model launches on (cudaStream_t as void*), so callers can record events on it. */
 void* sbv2_model_stream(const sbv2_model* model);
 
+/* Region timing with CUDA events on the model's stream (off by default). Regions of a synthesizer
+ * run: "text" (enc_p + duration predictors + durations), "flow" (expand + flow), "decoder". */
+int sbv2_model_enable_timing(sbv2_model* model, int on);
+int sbv2_model_region_ms(sbv2_model* model, const char* region, float* ms);
+/* Test hook: float32 copy [rows, cols] of a named intermediate of the last run (sbv2_free). */
+int sbv2_debug_fetch(sbv2_model* model, const char* name, float** out, int64_t* rows, int64_t* cols);
+
 /* HiFi-GAN decoder alone (BASELINE config 3): z float32 [batch][192, t_y[b]] channel-major per
  * utterance, g = emb_g[sid]; output as sbv2_synthesize_batch. */
 int sbv2_decode_batch(sbv2_model* synth, const float* const* z, const int64_t* t_y, const int64_t* sid,

@@ -79,7 +79,7 @@ class HParams:
 
 def tiny_hparams(**kw) -> HParams:
     """A reduced configuration used by fast CPU tests (same structure, fewer layers)."""
-    base = dict(n_layers=2, n_layers_trans_flow=2, n_speakers=2)
+    base = dict(n_layers=3, n_layers_trans_flow=3, n_speakers=2)
     base.update(kw)
     return HParams(**base)
 

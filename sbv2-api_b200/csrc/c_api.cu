@@ -220,6 +220,21 @@ int sbv2_decode_batch(sbv2_model* synth, const float* const* z, const int64_t* t
   });
 }
 
+int sbv2_model_enable_timing(sbv2_model* model, int on) {
+  return guarded([&] {
+    SBV2_REQUIRE(model, "null argument");
+    model->timing = on != 0;
+  });
+}
+
+int sbv2_model_region_ms(sbv2_model* model, const char* region, float* ms) {
+  return guarded([&] {
+    SBV2_REQUIRE(model && region && ms, "null argument");
+    model->bind_device();
+    *ms = model->region_ms(region);
+  });
+}
+
 // Test hook (not part of the reference API): copies a named intermediate of the last run.
 int sbv2_debug_fetch(sbv2_model* model, const char* name, float** out, int64_t* rows, int64_t* cols) {
   return guarded([&] {

@@ -56,6 +56,10 @@ void free_out(void* p) {
 sbv2_model::~sbv2_model() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
+  for (auto& kv : regions) {
+    cudaEventDestroy(kv.second.first);
+    cudaEventDestroy(kv.second.second);
+  }
   for (void* p : owned_device) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -70,4 +74,32 @@ void* sbv2_model::upload_bytes(const void* host, size_t bytes) {
   // `host` is usually a temporary vector: make the copy complete before returning
   CUDA_CHECK(cudaStreamSynchronize(stream));
   return d;
+}
+
+void sbv2_model::region_begin(const std::string& name) {
+  if (!timing) return;
+  auto it = regions.find(name);
+  if (it == regions.end()) {
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b));
+    it = regions.emplace(name, std::make_pair(a, b)).first;
+  }
+  CUDA_CHECK(cudaEventRecord(it->second.first, stream));
+}
+
+void sbv2_model::region_end(const std::string& name) {
+  if (!timing) return;
+  auto it = regions.find(name);
+  if (it == regions.end()) return;
+  CUDA_CHECK(cudaEventRecord(it->second.second, stream));
+}
+
+float sbv2_model::region_ms(const std::string& name) {
+  auto it = regions.find(name);
+  if (it == regions.end()) sbv2::fail(SBV2_ERR_INVALID_ARGUMENT, "no timed region named " + name);
+  CUDA_CHECK(cudaEventSynchronize(it->second.second));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, it->second.first, it->second.second));
+  return ms;
 }

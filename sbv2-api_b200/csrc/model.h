@@ -64,6 +64,12 @@ struct sbv2_model {
   std::string describe_json;
   std::map<std::string, sbv2::DebugView> debug;
   std::vector<void*> owned_device;  // weights
+  // optional region timing (CUDA events on `stream`), see sbv2_model_enable_timing
+  bool timing = false;
+  std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> regions;
+  void region_begin(const std::string& name);
+  void region_end(const std::string& name);
+  float region_ms(const std::string& name);
 
   virtual ~sbv2_model();
   sbv2::LaunchCtx ctx() { return sbv2::LaunchCtx{stream, &launches}; }

@@ -988,6 +988,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   float* wbuf = ens(W_W, size_t(Nx));
 
   // ---- speaker embedding, text encoder ------------------------------------------------------
+  M.region_begin("text");
   launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
   launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_bert), reinterpret_cast<const int64_t*>(in + b->o_bert_off),
                   nullptr, bert, hp.bert_dim, xseg);
@@ -1058,6 +1059,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   b->cum.ensure(size_t(Nx) * 4);
   launch_durations(ctx, logw, zs, d_ratio, d_ls, wbuf, b->dur.as<int>(), b->cum.as<int>(), d_ylen, xseg);
   M.debug["w"] = DebugView{wbuf, Nx, 1, 4};
+  M.region_end("text");
   M.pin_ylen.ensure(size_t(B) * 4);
   CUDA_CHECK(cudaMemcpyAsync(M.pin_ylen.p, d_ylen, size_t(B) * 4, cudaMemcpyDeviceToHost, M.stream));
   CUDA_CHECK(cudaStreamSynchronize(M.stream));
@@ -1102,6 +1104,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   yseg.max_len = ymax;
 
   // ---- expand + prior sample ---------------------------------------------------------------------
+  M.region_begin("flow");
   const int C = hp.inter;
   float* eps = ens(W_EPS, size_t(ny) * C);
   float* z = ens(W_Z, size_t(ny) * C);
@@ -1157,15 +1160,18 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     launch_coupling_sub(ctx, zc, mbuf, C, ny);
   }
   M.debug["z"] = DebugView{zc, ny, C, 4};
+  M.region_end("flow");
 
   // ---- decoder ---------------------------------------------------------------------------------------
   b->wave.stream = M.stream;
   b->wave.ensure(size_t(ny) * hp.hop * 4);
+  M.region_begin("decoder");
   if (M.use_umma && M.umma) {
     umma_decoder_run(M.umma, &M, zc, g, B, b->ystart, b->ylen, b->wave.as<float>());
   } else {
     decoder_fp32(M, zc, g, yseg, bseg, b->ystart, b->ylen, b->wave.as<float>(), M.ws[W_META]);
   }
+  M.region_end("decoder");
   b->ran = true;
 }
 
@@ -1278,11 +1284,13 @@ void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, con
   launch_gather_rows(ctx, g, M.emb_g, reinterpret_cast<const int64_t*>(in + o_sid), batch, hp.gin, hp.n_speakers);
   b.wave.stream = M.stream;
   b.wave.ensure(size_t(ny) * hp.hop * 4);
+  M.region_begin("decoder");
   if (M.use_umma && M.umma) {
     umma_decoder_run(M.umma, &M, zr, g, batch, b.ystart, b.ylen, b.wave.as<float>());
   } else {
     decoder_fp32(M, zr, g, yseg, bseg, b.ystart, b.ylen, b.wave.as<float>(), M.ws[W_META]);
   }
+  M.region_end("decoder");
   b.ran = true;
   synth_download(mm, &b, out_samples, out_n, nullptr, nullptr);
 }

@@ -74,6 +74,8 @@ def _load() -> C.CDLL:
         "sbv2_model_stream": (vp, [vp]),
         "sbv2_decode_batch": (C.c_int, [vp, C.POINTER(pf), pi64, pi64, C.c_int, C.POINTER(pf), pi64]),
         "sbv2_debug_fetch": (C.c_int, [vp, C.c_char_p, C.POINTER(pf), pi64, pi64]),
+        "sbv2_model_enable_timing": (C.c_int, [vp, C.c_int]),
+        "sbv2_model_region_ms": (C.c_int, [vp, C.c_char_p, pf]),
         "sbv2_parse_sbv2file": (C.c_int, [vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]),
         "sbv2_load_style": (C.c_int, [vp, sz, C.POINTER(pf), pi64, pi64]),
         "sbv2_load_style_npy_base64": (C.c_int, [C.c_char_p, sz, C.POINTER(pf), pi64, pi64]),
@@ -233,6 +235,14 @@ class Model:
     @property
     def stream(self) -> int:
         return int(lib.sbv2_model_stream(self._h) or 0)
+
+    def enable_timing(self, on: bool = True) -> None:
+        _check(lib.sbv2_model_enable_timing(self._h, 1 if on else 0))
+
+    def region_ms(self, region: str) -> float:
+        ms = C.c_float()
+        _check(lib.sbv2_model_region_ms(self._h, region.encode(), C.byref(ms)))
+        return float(ms.value)
 
     def seed(self, seed: int) -> None:
         _check(lib.sbv2_model_seed(self._h, seed))
