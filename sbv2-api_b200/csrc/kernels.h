@@ -116,3 +116,27 @@ void launch_wn_res_skip(const LaunchCtx& ctx, float* x, float* skip, const float
 void launch_dec_post(const LaunchCtx& ctx, float* out, const float* x, const float* w, int C, int k, const Segs& seg);
 
 }  // namespace sbv2
+
+// ---- transformer-flow glue around the tensor-core kernels (flow_kernels.cu) ----------------------
+// Planar buffers: fp16 [C/8][rows_tot][8] or fp32 with the same indexing; utterance b occupies planar
+// rows [pstart[b], pstart[b]+len[b]) and packed fp32 rows [start[b], start[b]+len[b]).
+namespace sbv2 {
+struct PlanarSegs {
+  const int* start = nullptr;   // packed fp32 rows
+  const int* pstart = nullptr;  // planar rows
+  const int* len = nullptr;
+  int n = 0, max_len = 0;
+  long long plane_stride = 0;   // elements between planes (= rows_tot * 8)
+};
+// h_out[row, :] = (src32 ? src32(planar fp32) : h_in[row, :]) + (vec ? vec[b, :] : 0); hp = fp16(h_out) planar
+void launch_flow_mix(const LaunchCtx& ctx, float* h_out, __half* hp, const float* h_in, const float* src32, const float* vec,
+                     int vec_ld, int C, const PlanarSegs& s);
+// h = LN(h + y32) * gamma + beta (in place, fp32 packed); hp = fp16(h) planar
+void launch_ln_planar(const LaunchCtx& ctx, float* h, __half* hp, const float* y32, const float* gamma, const float* beta, float eps,
+                      int C, const PlanarSegs& s);
+// window-relative attention on planar fp16 q|k|v (3*H*D channels) -> planar fp16 ctx (H*D channels)
+void launch_rel_attention_planar(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* rel_k, const float* rel_v,
+                                 int heads, int head_dim, int window, const PlanarSegs& s);
+// z[row, C/2:] -= m32 (planar fp32, C/2 channels)
+void launch_coupling_sub_planar(const LaunchCtx& ctx, float* z, const float* m32, int C, const PlanarSegs& s);
+}  // namespace sbv2

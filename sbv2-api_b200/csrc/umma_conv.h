@@ -1,16 +1,20 @@
-// Tensor-core (tcgen05 / TMEM) implicit-GEMM convolution path of the HiFi-GAN decoder.
-// Activations live in HBM as fp16 "planar" tiles [C/8][rows][8] so that any row-shifted window
-// of any 8-channel plane is a dense run of 16-byte rows: exactly the no-swizzle K-major core-matrix
-// layout tcgen05.mma reads, which lets one halo'd tile serve every filter tap through a shifted
-// shared-memory descriptor.  See DESIGN.md §kernels.
+// Tensor-core (tcgen05 / TMEM) implicit-GEMM convolution used by the HiFi-GAN decoder and the
+// transformer flow.  See umma_conv.cu for the kernel and the data layout ("planar fp16").
 #pragma once
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "common.h"
+#include "kernels.h"
 
 struct sbv2_model;
 
 namespace sbv2 {
+
+constexpr int UMMA_GAP = 32;         // zero rows around each utterance (>= largest halo: 5*(11-1)/2 = 25)
+constexpr int UMMA_TAIL_ROWS = 640;  // slack rows after the last utterance (a tile may over-read)
+constexpr int UMMA_MAX_TAPS = 16;
 
 struct HostConv {
   std::vector<float> w, b;  // PyTorch layout: Conv1d [d0=Cout, d1=Cin, k]; ConvTranspose1d [d0=Cin, d1=Cout, k]
@@ -27,8 +31,65 @@ struct DecoderHostWeights {
   int gin = 512;
 };
 
+// One convolution prepared for the tensor-core kernel (weights repacked to fp16 on the device).
+struct ConvLayer {
+  __half* w = nullptr;   // [nblk][kc][tap][KC/8][NB][8]
+  float* bias = nullptr; // [cout]
+  int cin = 0, cout = 0, nb = 0, n_nblk = 1, taps = 1, kc = 64, nkc = 1, mt = 1, sps = 1, nstages = 2, nloads = 1, total_steps = 1;
+  int a_slots = 1;
+  int tap_shift[UMMA_MAX_TAPS] = {0};
+  int halo_lo = 0, halo_hi = 0;
+  size_t smem = 0;
+  int tmem_cols = 32;
+  unsigned idesc = 0;
+};
+
+// Conv1d weight [Cout][Cin][k], "same" padding, dilation dil.
+ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref);
+// phase r (= output index mod u) of ConvTranspose1d weight [Cin][Cout][k], stride u, pad (k-u)/2
+ConvLayer make_up_phase_layer(sbv2_model* owner, const HostConv& c, int u, int r, int mt_pref);
+
+// One time resolution of one packed batch.
+struct Geom {
+  int mul = 1;
+  long long rows_tot = 0;
+  std::vector<int> pstart, len;
+  const int* d_pstart = nullptr;
+  const int* d_len = nullptr;
+  const int* d_prefix[3] = {nullptr, nullptr, nullptr};  // tiles of 128 * {1, 2, 4} rows
+  int n_tiles[3] = {0, 0, 0};
+  int max_len = 0;
+};
+struct BatchGeom {
+  std::vector<Geom> g;
+  const int* d_ystart = nullptr;  // first row of each utterance in the packed fp32 [rows, C] matrices
+  const int* d_wstart = nullptr;  // sample offset of each utterance in the waveform buffer
+};
+struct DBuf;
+struct PinnedBuf;
+BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::vector<int>& ystart, const std::vector<int>& ylen,
+                      const std::vector<int>& muls);
+
+enum UAccum { UACC_NONE = 0, UACC_SET = 1, UACC_ADD = 2, UACC_FINAL = 3 };
+struct ConvCall {
+  const __half* in = nullptr;
+  __half* out = nullptr;          // planar fp16 (optional)
+  const __half* residual = nullptr;  // planar fp16 stored post-lrelu(0.1): x = y >= 0 ? y : 10 y is added
+  float* accum = nullptr;         // planar fp32 (geometry of out)
+  int accum_mode = UACC_NONE;
+  float accum_div = 1.f;
+  int act_out = ACT_NONE;         // ACT_NONE / ACT_RELU / ACT_LRELU / ACT_LRELU01
+  const float* bias_utt = nullptr;
+  int out_mul = 1, out_off = 0;
+};
+void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt);
+void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, int n_utt);
+// packed fp32 [rows, in_ld] (first C columns) -> planar fp16
+void launch_to_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
+                      int n_utt, int act);
+void launch_from_planar(const LaunchCtx& ctx, float* out, const __half* in, int C, const int* d_start, const Geom& g, int n_utt);
+
 struct UmmaDecoder;
-// Returns nullptr when the decoder shape is outside what the tensor-core plan supports.
 UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner);
 void umma_decoder_free(UmmaDecoder* d);
 // z: packed [Ny, Cin] fp32 (time-major), g: [B, gin] fp32, wave: [Ny*hop] fp32 (all device).

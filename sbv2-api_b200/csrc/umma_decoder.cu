@@ -1,0 +1,319 @@
+// Tensor-core HiFi-GAN decoder plan (conv_pre, 5 x [polyphase ConvTranspose + 3 ResBlock1 (MRF)],
+// conv_post) on top of the tcgen05 conv kernel of umma_conv.cu.  Every stored activation is the
+// post-LeakyReLU value in planar fp16; the residual x is recovered exactly-invertibly from it
+// (x = y >= 0 ? y : 10 y), the MRF mean is accumulated in fp32.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "kernels.h"
+#include "model.h"
+#include "umma_conv.h"
+
+namespace sbv2 {
+namespace {
+
+constexpr int GAP = UMMA_GAP;
+
+// decoder post: out[t] = tanh(sum_j sum_c w[c][j] * x[t+j-pad][c]); x planar fp16 already activated (lrelu 0.01)
+__global__ void post_planar_kernel(float* wave, const __half* x, long long plane_stride, const float* w, int C, int k, const int* pstart,
+                                   const int* wstart, const int* len) {
+  extern __shared__ float ws[];  // [k][C]
+  for (int i = threadIdx.x; i < C * k; i += blockDim.x) {
+    int c = i / k, j = i % k;
+    ws[j * C + c] = w[i];
+  }
+  __syncthreads();
+  int b = blockIdx.y;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len[b]) return;
+  const int pad = (k - 1) / 2;
+  float acc = 0.f;
+  for (int j = 0; j < k; ++j) {
+    long long r = (long long)pstart[b] + t + j - pad;  // gap rows are zero: no bounds test needed
+    for (int pl = 0; pl < C / 8; ++pl) {
+      uint4 q = *reinterpret_cast<const uint4*>(x + (size_t)pl * plane_stride + r * 8);
+      const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 y = __half22float2(qh[e]);
+        acc = fmaf(ws[j * C + pl * 8 + 2 * e], y.x, acc);
+        acc = fmaf(ws[j * C + pl * 8 + 2 * e + 1], y.y, acc);
+      }
+    }
+  }
+  wave[(size_t)wstart[b] + t] = tanhf(acc);
+}
+
+}  // namespace
+
+// ---- decoder plan -----------------------------------------------------------------------------------------
+struct UmmaDecoder {
+  int gin = 0, cin0 = 0, c0 = 0, n_stages = 0, per = 0, post_c = 0, post_k = 0;
+  ConvLayer pre;
+  float* cond_w = nullptr;  // fp32 [1][gin][c0]
+  float* cond_b = nullptr;
+  std::vector<std::vector<ConvLayer>> ups;  // [stage][phase]
+  std::vector<int> up_u, stage_c;
+  std::vector<std::vector<ConvLayer>> c1, c2;  // [resblock][layer]
+  float* post_w = nullptr;
+  DBuf zp, xs, xu, t1, r, sum, meta, gcond;
+  PinnedBuf pin_meta;
+};
+
+UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner) {
+  std::unique_ptr<UmmaDecoder> D(new UmmaDecoder());
+  D->gin = w.gin;
+  D->cin0 = w.pre.d1;
+  D->c0 = w.pre.d0;
+  D->n_stages = int(w.ups.size());
+  D->per = w.per;
+  D->pre = make_conv1d_layer(owner, w.pre, 1, 2);
+  {
+    // cond: Conv1d(gin -> c0, 1) evaluated on [B, gin] rows with the fp32 kernel
+    std::vector<float> t(size_t(w.cond.d0) * w.cond.d1);
+    for (int co = 0; co < w.cond.d0; ++co)
+      for (int ci = 0; ci < w.cond.d1; ++ci) t[size_t(ci) * w.cond.d0 + co] = w.cond.w[size_t(co) * w.cond.d1 + ci];
+    D->cond_w = owner->upload_f32(t);
+    D->cond_b = owner->upload_f32(w.cond.b);
+  }
+  int C = D->c0;
+  for (int s = 0; s < D->n_stages; ++s) {
+    const HostConv& U = w.ups[s];
+    if (U.d0 != C) fail(SBV2_ERR_UNSUPPORTED, "decoder upsample channel mismatch");
+    std::vector<ConvLayer> phases;
+    for (int r = 0; r < w.up_u[s]; ++r) phases.push_back(make_up_phase_layer(owner, U, w.up_u[s], r, 4));
+    D->ups.push_back(phases);
+    D->up_u.push_back(w.up_u[s]);
+    C = U.d1;
+    D->stage_c.push_back(C);
+    for (int j = 0; j < w.per; ++j) {
+      size_t rb = size_t(s) * w.per + j;
+      std::vector<ConvLayer> l1, l2;
+      for (size_t l = 0; l < w.res_c1[rb].size(); ++l) {
+        l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 4));
+        l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 4));
+      }
+      D->c1.push_back(l1);
+      D->c2.push_back(l2);
+    }
+  }
+  D->post_c = w.post.d1;
+  D->post_k = w.post.k;
+  if (D->post_c != C || D->post_c % 8 != 0) fail(SBV2_ERR_UNSUPPORTED, "decoder conv_post channel mismatch");
+  D->post_w = owner->upload_f32(w.post.w);
+  for (DBuf* b : {&D->zp, &D->xs, &D->xu, &D->t1, &D->r, &D->sum, &D->meta, &D->gcond}) b->stream = owner->stream;
+  return D.release();
+}
+
+void umma_decoder_free(UmmaDecoder* d) { delete d; }
+
+void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const float* g, int B, const std::vector<int>& ystart,
+                      const std::vector<int>& ylen, float* wave) {
+  LaunchCtx ctx = owner->ctx();
+  std::vector<int> muls(1, 1);
+  for (int s = 0; s < D->n_stages; ++s) muls.push_back(muls.back() * D->up_u[s]);
+  BatchGeom bg = build_geoms(owner, D->meta, D->pin_meta, ystart, ylen, muls);
+  // buffer sizes
+  size_t max_half = size_t(bg.g[0].rows_tot) * D->c0;
+  for (int s = 0; s < D->n_stages; ++s) max_half = std::max(max_half, size_t(bg.g[s + 1].rows_tot) * D->stage_c[s]);
+  D->zp.ensure(size_t(bg.g[0].rows_tot) * D->cin0 * 2);
+  D->xs.ensure(max_half * 2);
+  D->xu.ensure(max_half * 2);
+  D->t1.ensure(max_half * 2);
+  D->r.ensure(max_half * 2);
+  D->sum.ensure(max_half * 4);
+  D->gcond.ensure(size_t(B) * D->c0 * 4);
+  __half* zp = D->zp.as<__half>();
+  __half* xs = D->xs.as<__half>();
+  __half* xu = D->xu.as<__half>();
+  __half* t1 = D->t1.as<__half>();
+  __half* r = D->r.as<__half>();
+  float* sum = D->sum.as<float>();
+  float* gcond = D->gcond.as<float>();
+
+  // cond(g) -> per-utterance bias of conv_pre
+  {
+    // one segment of B rows: reuse the first geometry's arrays is not possible; a tiny dedicated pair lives after wstart
+    // (start = 0, len = B) — build it on the fly in the gcond buffer's tail is overkill: launch with an explicit Segs
+    // whose arrays are the (ystart-independent) prefix of geometry 0: prefix[0] == 0 and we need len == B.
+    static_assert(sizeof(int) == 4, "");
+  }
+  {
+    // Segs {start=[0], len=[B]}: store in pinned+device meta tail
+    // (appended by build_geoms would complicate its layout; use a small separate upload)
+    int two[2] = {0, B};
+    D->gcond.ensure(size_t(B) * D->c0 * 4 + 64);
+    gcond = D->gcond.as<float>();
+    int* d_two = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(gcond) + size_t(B) * D->c0 * 4);
+    CUDA_CHECK(cudaMemcpyAsync(d_two, two, 8, cudaMemcpyHostToDevice, owner->stream));
+    ConvArgs a;
+    a.in = g;
+    a.in_ld = D->gin;
+    a.w = D->cond_w;
+    a.bias = D->cond_b;
+    a.out = gcond;
+    a.out_ld = D->c0;
+    a.cin = D->gin;
+    a.cout = D->c0;
+    a.seg.start = d_two;
+    a.seg.len = d_two + 1;
+    a.seg.n = 1;
+    a.seg.max_len = B;
+    launch_conv(ctx, a);
+  }
+
+  const Geom& G0 = bg.g[0];
+  launch_zero_gaps(ctx, zp, D->cin0, G0, B);
+  launch_to_planar(ctx, zp, z, D->cin0, D->cin0, bg.d_ystart, G0, B, ACT_NONE);
+  launch_zero_gaps(ctx, xs, D->c0, G0, B);
+  {
+    ConvCall c;
+    c.in = zp;
+    c.out = xs;
+    c.act_out = ACT_LRELU;
+    c.bias_utt = gcond;
+    launch_umma(ctx, D->pre, G0, G0, c, B);
+  }
+  for (int s = 0; s < D->n_stages; ++s) {
+    const Geom& Gi = bg.g[s];
+    const Geom& Go = bg.g[s + 1];
+    const int C = D->stage_c[s];
+    const int u = D->up_u[s];
+    launch_zero_gaps(ctx, xu, C, Go, B);
+    for (int ph = 0; ph < u; ++ph) {
+      ConvCall c;
+      c.in = xs;
+      c.out = xu;
+      c.act_out = ACT_LRELU;
+      c.out_mul = u;
+      c.out_off = ph;
+      launch_umma(ctx, D->ups[s][ph], Gi, Go, c, B);
+    }
+    launch_zero_gaps(ctx, t1, C, Go, B);
+    launch_zero_gaps(ctx, r, C, Go, B);
+    const bool last_stage = s + 1 == D->n_stages;
+    for (int j = 0; j < D->per; ++j) {
+      size_t rb = size_t(s) * D->per + j;
+      const __half* cur = xu;
+      const size_t nl = D->c1[rb].size();
+      for (size_t l = 0; l < nl; ++l) {
+        {
+          ConvCall c;
+          c.in = cur;
+          c.out = t1;
+          c.act_out = ACT_LRELU;
+          launch_umma(ctx, D->c1[rb][l], Go, Go, c, B);
+        }
+        ConvCall c;
+        c.in = t1;
+        c.residual = cur;
+        if (l + 1 < nl) {
+          c.out = r;
+          c.act_out = ACT_LRELU;
+        } else {
+          c.accum = sum;
+          c.accum_div = float(D->per);
+          if (D->per == 1) {
+            c.accum_mode = UACC_FINAL;  // (0 + v)/1 — needs sum zero: use SET semantics via out only
+          }
+          if (j == 0 && D->per > 1) c.accum_mode = UACC_SET;
+          else if (j + 1 < D->per) c.accum_mode = UACC_ADD;
+          else c.accum_mode = UACC_FINAL;
+          if (c.accum_mode == UACC_FINAL) {
+            launch_zero_gaps(ctx, xs, C, Go, B);
+            c.out = xs;
+            c.act_out = last_stage ? ACT_LRELU01 : ACT_LRELU;
+          }
+        }
+        launch_umma(ctx, D->c2[rb][l], Go, Go, c, B);
+        cur = r;
+      }
+    }
+  }
+  const Geom& GL = bg.g.back();
+  {
+    dim3 grid((GL.max_len + 255) / 256, B);
+    post_planar_kernel<<<grid, 256, sizeof(float) * D->post_c * D->post_k, ctx.stream>>>(wave, xs, GL.rows_tot * 8, D->post_w, D->post_c,
+                                                                                        D->post_k, GL.d_pstart, bg.d_wstart, GL.d_len);
+    CUDA_CHECK(cudaGetLastError());
+    ctx.count();
+  }
+  // the pinned geometry blob is rewritten by the next run: make sure its upload finished
+  // (it did: every kernel above depends on it and the caller synchronises before returning results)
+}
+
+}  // namespace sbv2
+
+// ---- test hook: one convolution through both the fp32 kernel and the tensor-core kernel -------------------
+extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const float* w, const float* bias, int cout, int k,
+                                       int dil, int mt_pref, int with_residual, int dbg_swap, float* out_umma, float* out_ref) {
+  using namespace sbv2;
+  return guarded([&] {
+    SBV2_REQUIRE(x && w && out_umma && out_ref && T > 0, "bad arguments");
+    sbv2_model owner;
+    owner.device = 0;
+    CUDA_CHECK(cudaSetDevice(0));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&owner.stream, cudaStreamNonBlocking));
+    LaunchCtx ctx = owner.ctx();
+    HostConv hc;
+    hc.d0 = cout;
+    hc.d1 = cin;
+    hc.k = k;
+    hc.w.assign(w, w + size_t(cout) * cin * k);
+    if (bias) hc.b.assign(bias, bias + cout);
+    ConvLayer L = make_conv1d_layer(&owner, hc, dil, mt_pref);
+    // fp32 reference weights [k][cin][cout]
+    std::vector<float> wr(size_t(k) * cin * cout);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int j = 0; j < k; ++j) wr[(size_t(j) * cin + ci) * cout + co] = w[(size_t(co) * cin + ci) * k + j];
+    float* d_wr = owner.upload_f32(wr);
+    float* d_b = bias ? static_cast<float*>(owner.upload_bytes(bias, size_t(cout) * 4)) : nullptr;
+    float* d_x = static_cast<float*>(owner.upload_bytes(x, size_t(T) * cin * 4));
+    DBuf meta, xin, xout, xres, ref, back;
+    PinnedBuf pin;
+    for (DBuf* b : {&meta, &xin, &xout, &xres, &ref, &back}) b->stream = owner.stream;
+    std::vector<int> ystart{0}, ylen{int(T)}, muls{1};
+    BatchGeom bg = build_geoms(&owner, meta, pin, ystart, ylen, muls);
+    const Geom& G = bg.g[0];
+    xin.ensure(size_t(G.rows_tot) * cin * 2);
+    xout.ensure(size_t(G.rows_tot) * cout * 2);
+    ref.ensure(size_t(T) * cout * 4);
+    back.ensure(size_t(T) * cout * 4);
+    launch_zero_gaps(ctx, xin.as<__half>(), cin, G, 1);
+    launch_to_planar(ctx, xin.as<__half>(), d_x, cin, cin, bg.d_ystart, G, 1, ACT_NONE);
+    ConvCall c;
+    c.in = xin.as<__half>();
+    c.out = xout.as<__half>();
+    if (with_residual) {
+      SBV2_REQUIRE(cin == cout, "residual test needs cin == cout");
+      c.residual = xin.as<__half>();  // interpreted as lrelu-stored values
+    }
+    (void)dbg_swap;
+    launch_umma(ctx, L, G, G, c, 1);
+    launch_from_planar(ctx, back.as<float>(), xout.as<__half>(), cout, bg.d_ystart, G, 1);
+    // reference
+    ConvArgs a;
+    a.in = d_x;
+    a.in_ld = cin;
+    a.w = d_wr;
+    a.bias = d_b;
+    a.out = ref.as<float>();
+    a.out_ld = cout;
+    a.cin = cin;
+    a.cout = cout;
+    a.taps = k;
+    a.dil = dil;
+    a.off = -dil * ((k - 1) / 2);
+    a.seg.start = bg.d_ystart;      // [0]
+    a.seg.len = G.d_len;            // [T]
+    a.seg.n = 1;
+    a.seg.max_len = int(T);
+    launch_conv(ctx, a);
+    CUDA_CHECK(cudaMemcpyAsync(out_umma, back.p, size_t(T) * cout * 4, cudaMemcpyDeviceToHost, owner.stream));
+    CUDA_CHECK(cudaMemcpyAsync(out_ref, ref.p, size_t(T) * cout * 4, cudaMemcpyDeviceToHost, owner.stream));
+    CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+  });
+}
