@@ -73,6 +73,14 @@ struct CouplingW {
   WNW wn;        // WN variant
 };
 
+struct FlowTCLayer {
+  ConvLayer qkv, o, f1, f2;
+};
+struct FlowTC {
+  ConvLayer pre, post;
+  std::vector<FlowTCLayer> layers;
+};
+
 struct HParams {
   int n_vocab = 0, n_tones = 0, n_lang = 0, hidden = 0, inter = 0, gin = 0, n_speakers = 0, bert_dim = 0, style_dim = 0;
   int dp_filter = 0, sdp_bins = 10, sdp_flows = 0;
@@ -104,8 +112,13 @@ struct SynthModel : sbv2_model {
   std::vector<ResBlockW> resblocks;
   float* dec_post_w = nullptr;  // [1][C][k]
   int dec_post_k = 7, dec_post_c = 16;
-  UmmaDecoder* umma = nullptr;  // tensor-core decoder plan (umma_conv.cu); null -> fp32 path
+  UmmaDecoder* umma = nullptr;  // tensor-core decoder plan (umma_decoder.cu); null -> fp32 path
   bool use_umma = true;
+  std::vector<FlowTC> flow_tc;  // tensor-core transformer flow (fp16 operands, fp32 residual stream)
+  bool use_tc_flow = true;
+  std::vector<std::vector<HostConv>> flow_host;  // consumed at create: per coupling [pre, post, (qkv, o, f1, f2) x L]
+  DBuf fl_x0p, fl_hp, fl_qkvp, fl_ctxp, fl_f1p, fl_y32, fl_m32, fl_meta;
+  PinnedBuf fl_pin;
 
   uint64_t seed = 0x5b2b200ULL, rng_offset = 0;
   // workspaces
@@ -491,18 +504,43 @@ void load_weights(SynthModel& M, const OnnxModel& m) {
     if (L.has("dec.conv_post.bias")) fail(SBV2_ERR_UNSUPPORTED, "dec.conv_post with bias is not a JP-Extra decoder");
   }
 
-  // original-layout copies for the tensor-core decoder's fp16 repacking
+  // original-layout copies for the tensor-core kernels' fp16 repacking
+  auto host_conv = [&](const std::string& p, bool bias) {
+    HostConv hc;
+    const OnnxTensor& t = L.get(p + ".weight");
+    hc.d0 = int(t.dims[0]);
+    hc.d1 = int(t.dims[1]);
+    hc.k = t.dims.size() > 2 ? int(t.dims[2]) : 1;
+    hc.w = m.as_f32(t);
+    if (bias) hc.b = L.f32(p + ".bias");
+    return hc;
+  };
+  if (hp.transformer_flow) {
+    for (int i = 0; i < hp.n_flows; ++i) {
+      std::string p = "flow.flows." + std::to_string(2 * i);
+      std::vector<HostConv> v;
+      v.push_back(host_conv(p + ".pre", true));
+      v.push_back(host_conv(p + ".post", true));
+      for (int l = 0; l < hp.flow_layers; ++l) {
+        std::string a = p + ".enc.attn_layers." + std::to_string(l);
+        HostConv q = host_conv(a + ".conv_q", true), k = host_conv(a + ".conv_k", true), vv = host_conv(a + ".conv_v", true);
+        HostConv qkv;
+        qkv.d0 = q.d0 + k.d0 + vv.d0;
+        qkv.d1 = q.d1;
+        qkv.k = 1;
+        for (const HostConv* hc : {&q, &k, &vv}) {
+          qkv.w.insert(qkv.w.end(), hc->w.begin(), hc->w.end());
+          qkv.b.insert(qkv.b.end(), hc->b.begin(), hc->b.end());
+        }
+        v.push_back(qkv);
+        v.push_back(host_conv(a + ".conv_o", true));
+        v.push_back(host_conv(p + ".enc.ffn_layers." + std::to_string(l) + ".conv_1", true));
+        v.push_back(host_conv(p + ".enc.ffn_layers." + std::to_string(l) + ".conv_2", true));
+      }
+      M.flow_host.push_back(std::move(v));
+    }
+  }
   {
-    auto host_conv = [&](const std::string& p, bool bias) {
-      HostConv hc;
-      const OnnxTensor& t = L.get(p + ".weight");
-      hc.d0 = int(t.dims[0]);
-      hc.d1 = int(t.dims[1]);
-      hc.k = t.dims.size() > 2 ? int(t.dims[2]) : 1;
-      hc.w = m.as_f32(t);
-      if (bias) hc.b = L.f32(p + ".bias");
-      return hc;
-    };
     DecoderHostWeights& D = M.dec_host;
     D.pre = host_conv("dec.conv_pre", true);
     D.cond = host_conv("dec.cond", true);
@@ -654,6 +692,28 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
   M->use_umma = !(env && std::string(env) == "fp32");
   if (M->use_umma) M->umma = umma_decoder_create(M->dec_host, M.get());
   M->dec_host = DecoderHostWeights();
+  // SBV2_B200_FLOW=fp32 selects the CUDA-core fp32 flow kernels (debugging / kernel cross-checks).
+  const char* fenv = getenv("SBV2_B200_FLOW");
+  M->use_tc_flow = M->hp.transformer_flow && !(fenv && std::string(fenv) == "fp32") && M->hp.hidden % 16 == 0 &&
+                   M->hp.hidden / 8 <= 32 && (M->hp.inter / 2) % 16 == 0;
+  if (M->use_tc_flow) {
+    for (auto& v : M->flow_host) {
+      FlowTC f;
+      f.pre = make_conv1d_layer(M.get(), v[0], 1, 2);
+      f.post = make_conv1d_layer(M.get(), v[1], 1, 2);
+      for (size_t l = 0; 2 + 4 * l + 3 < v.size(); ++l) {
+        FlowTCLayer fl;
+        fl.qkv = make_conv1d_layer(M.get(), v[2 + 4 * l], 1, 2);
+        fl.o = make_conv1d_layer(M.get(), v[3 + 4 * l], 1, 2);
+        fl.f1 = make_conv1d_layer(M.get(), v[4 + 4 * l], 1, 2);
+        fl.f2 = make_conv1d_layer(M.get(), v[5 + 4 * l], 1, 2);
+        f.layers.push_back(fl);
+      }
+      M->flow_tc.push_back(std::move(f));
+    }
+    for (DBuf* b : {&M->fl_x0p, &M->fl_hp, &M->fl_qkvp, &M->fl_ctxp, &M->fl_f1p, &M->fl_y32, &M->fl_m32, &M->fl_meta}) b->stream = M->stream;
+  }
+  M->flow_host.clear();
   CUDA_CHECK(cudaStreamSynchronize(M->stream));
   return M.release();
 }
@@ -1130,6 +1190,73 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   float* hf = ens(W_HF, size_t(ny) * H);
   float* zc = z;
   float* zn = z2;
+  if (M.use_tc_flow) {
+    // tensor-core path: fp16 planar operands, fp32 residual stream hf
+    std::vector<int> muls(1, 1);
+    BatchGeom bg = build_geoms(&M, M.fl_meta, M.fl_pin, b->ystart, b->ylen, muls);
+    const Geom& G = bg.g[0];
+    PlanarSegs ps;
+    ps.start = bg.d_ystart;
+    ps.pstart = G.d_pstart;
+    ps.len = G.d_len;
+    ps.n = B;
+    ps.max_len = ymax;
+    ps.plane_stride = G.rows_tot * 8;
+    const int filt = M.flow[0].enc.filter;
+    M.fl_x0p.ensure(size_t(G.rows_tot) * (C / 2) * 2);
+    M.fl_hp.ensure(size_t(G.rows_tot) * H * 2);
+    M.fl_qkvp.ensure(size_t(G.rows_tot) * 3 * H * 2);
+    M.fl_ctxp.ensure(size_t(G.rows_tot) * H * 2);
+    M.fl_f1p.ensure(size_t(G.rows_tot) * filt * 2);
+    M.fl_y32.ensure(size_t(G.rows_tot) * H * 4);
+    M.fl_m32.ensure(size_t(G.rows_tot) * (C / 2) * 4);
+    __half* x0p = M.fl_x0p.as<__half>();
+    __half* hp16 = M.fl_hp.as<__half>();
+    __half* qkvp = M.fl_qkvp.as<__half>();
+    __half* ctxp = M.fl_ctxp.as<__half>();
+    __half* f1p = M.fl_f1p.as<__half>();
+    float* y32 = M.fl_y32.as<float>();
+    float* m32 = M.fl_m32.as<float>();
+    launch_zero_gaps(ctx, hp16, H, G, B);
+    launch_zero_gaps(ctx, f1p, filt, G, B);
+    auto umma = [&](const ConvLayer& L, const __half* in, __half* out, float* acc32, int act) {
+      ConvCall c;
+      c.in = in;
+      c.out = out;
+      c.accum = acc32;
+      c.accum_mode = acc32 ? UACC_SET : UACC_NONE;
+      c.act_out = act;
+      launch_umma(ctx, L, G, G, c, B);
+    };
+    for (int i = hp.n_flows - 1; i >= 0; --i) {
+      const CouplingW& cp = M.flow[i];
+      const FlowTC& T = M.flow_tc[i];
+      launch_flip_channels(ctx, zn, zc, C, ny);
+      std::swap(zc, zn);
+      launch_to_planar(ctx, x0p, zc, C, C / 2, bg.d_ystart, G, B, ACT_NONE);
+      umma(T.pre, x0p, nullptr, y32, ACT_NONE);
+      launch_flow_mix(ctx, hf, hp16, nullptr, y32, nullptr, 0, H, ps);
+      const EncoderW& E = cp.enc;
+      for (size_t l = 0; l < E.layers.size(); ++l) {
+        const EncLayerW& Lw = E.layers[l];
+        const FlowTCLayer& Lt = T.layers[l];
+        if (E.has_spk && int(l) == E.cond_idx) {
+          float* gg = M.ws[W_GG].as<float>();
+          F.conv(E.spk, g, hp.gin, gg, H, bseg);
+          launch_flow_mix(ctx, hf, hp16, hf, nullptr, gg, H, H, ps);
+        }
+        umma(Lt.qkv, hp16, qkvp, nullptr, ACT_NONE);
+        launch_rel_attention_planar(ctx, ctxp, qkvp, Lw.rel_k, Lw.rel_v, E.heads, E.head_dim, E.window, ps);
+        umma(Lt.o, ctxp, nullptr, y32, ACT_NONE);
+        launch_ln_planar(ctx, hf, hp16, y32, Lw.n1.g, Lw.n1.b, 1e-5f, H, ps);
+        umma(Lt.f1, hp16, f1p, nullptr, ACT_RELU);
+        umma(Lt.f2, f1p, nullptr, y32, ACT_NONE);
+        launch_ln_planar(ctx, hf, hp16, y32, Lw.n2.g, Lw.n2.b, 1e-5f, H, ps);
+      }
+      umma(T.post, hp16, nullptr, m32, ACT_NONE);
+      launch_coupling_sub_planar(ctx, zc, m32, C, ps);
+    }
+  } else
   for (int i = hp.n_flows - 1; i >= 0; --i) {
     const CouplingW& cp = M.flow[i];
     launch_flip_channels(ctx, zn, zc, C, ny);
