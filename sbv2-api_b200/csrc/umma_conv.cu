@@ -35,11 +35,12 @@ namespace {
 constexpr int GAP = UMMA_GAP;
 constexpr int TAIL_ROWS = UMMA_TAIL_ROWS;
 constexpr int MAX_TAPS = UMMA_MAX_TAPS;
-constexpr int MAX_ASLOTS = 4;
+constexpr int MAX_ASLOTS = 8;
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_TWO_CTAS = 113 * 1024;
 constexpr int NUM_THREADS = 320;
+constexpr int NUM_EPI_WARPS = 8;
 
 struct UmmaConvArgs {
   const __half* in;
@@ -56,7 +57,7 @@ struct UmmaConvArgs {
   const int* pstart_out;
   const int* len;              // [n_utt] rows (input resolution)
   int n_utt;
-  int cin, nb, taps, kc, nkc, mt, sps, nstages, nloads, total_steps, a_slots;
+  int cin, nb, n_nblk, n_items, taps, kc, nkc, mt, sps, nstages, nloads, total_steps, a_slots, b_resident;
   int tap_shift[MAX_TAPS];
   int halo_lo, halo_hi;
   int out_mul, out_off;
@@ -139,7 +140,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // Epilogue of NCH (16 or 32) accumulator columns of one row.
 template <int NCH, bool ACC>
 __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t taddr, bool valid, long long orow, int co0_global,
-                                              const float* bias, const float* bias_u) {
+                                              const float* bias) {
   constexpr int NPL = NCH / 8;
   uint32_t v[NCH];
 #pragma unroll
@@ -166,9 +167,12 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
     float f[8];
     const int co = 8 * pl;  // offset within this item
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      f[e] = __uint_as_float(v[co + e]) + bias[co + e];
-      if (bias_u) f[e] += bias_u[co + e];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + co), b1 = *reinterpret_cast<const float4*>(bias + co + 4);
+      f[0] = __uint_as_float(v[co + 0]) + b0.x; f[1] = __uint_as_float(v[co + 1]) + b0.y;
+      f[2] = __uint_as_float(v[co + 2]) + b0.z; f[3] = __uint_as_float(v[co + 3]) + b0.w;
+      f[4] = __uint_as_float(v[co + 4]) + b1.x; f[5] = __uint_as_float(v[co + 5]) + b1.y;
+      f[6] = __uint_as_float(v[co + 6]) + b1.z; f[7] = __uint_as_float(v[co + 7]) + b1.w;
     }
     if (p.has_res) {
       const __half2* rh = reinterpret_cast<const __half2*>(&r[pl]);
@@ -205,25 +209,33 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NUM_THREADS, 2) umma_conv_kernel(const __grid_constant__ UmmaConvArgs p) {
+// Persistent: one CTA per SM walks work items (tile, N block) round-robin.  The producer streams
+// activation chunks and weight stages through their rings without regard to item boundaries, the
+// MMA thread alternates between two TMEM accumulator sets, and the epilogue warps drain set i while
+// the MMA thread fills set i^1 — loads, tensor work and stores of neighbouring tiles overlap.
+struct TileInfo {
+  int b, t0, len, nblk;
+};
+__device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item) {
+  TileInfo ti;
+  const int tile = item / p.n_nblk;
+  ti.nblk = item - tile * p.n_nblk;
+  int lo = 0, hi = p.n_utt;  // largest b with tile_prefix[b] <= tile
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.tile_prefix[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  ti.b = lo;
+  ti.t0 = (tile - p.tile_prefix[lo]) * 128 * p.mt;
+  ti.len = p.len[lo];
+  return ti;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int TM = 128 * p.mt;
-  // tile -> (utterance, first row)
-  int b;
-  {
-    int lo = 0, hi = p.n_utt;  // largest b with tile_prefix[b] <= tile
-    const int tile = blockIdx.x;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (p.tile_prefix[mid] <= tile) lo = mid;
-      else hi = mid;
-    }
-    b = lo;
-  }
-  const int t0 = (blockIdx.x - p.tile_prefix[b]) * TM;
-  const int len = p.len[b];
-  const int nblk = blockIdx.y;
   const int RA = TM + p.halo_lo + p.halo_hi;
   const int planes_per_chunk = p.kc / 8;
   const uint32_t slot_bytes = (uint32_t)planes_per_chunk * RA * 16;
@@ -232,11 +244,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) umma_conv_kernel(const __grid_
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + ((slot_bytes * p.a_slots + 127u) & ~127u);
   const uint32_t sBar = sB + stage_bytes * p.nstages;
-  // barriers: a_full[4], a_empty[4], b_full[4], b_empty[4], acc_full ; then tmem slot
+  // barriers: a_full[8], a_empty[8], b_full[4], b_empty[4], acc_full[2], acc_empty[2]; tmem slot; bias[2][NB]
   const uint32_t bar_af = sBar, bar_ae = bar_af + 8 * MAX_ASLOTS, bar_bf = bar_ae + 8 * MAX_ASLOTS, bar_be = bar_bf + 8 * MAX_STAGES,
-                 bar_acc = bar_be + 8 * MAX_STAGES;
-  const uint32_t tmem_slot = bar_acc + 8;
+                 bar_accf = bar_be + 8 * MAX_STAGES, bar_acce = bar_accf + 16;
+  const uint32_t tmem_slot = bar_acce + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sA));
+  float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 256);  // [2][NB]
+  const int acc_cols = p.mt * p.nb;  // TMEM columns of one accumulator set
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) {
@@ -247,7 +261,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) umma_conv_kernel(const __grid_
       mbar_init(bar_bf + 8 * i, 1);
       mbar_init(bar_be + 8 * i, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_accf + 8 * i, 1);
+      mbar_init(bar_acce + 8 * i, NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -262,34 +279,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) umma_conv_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- producer ----------------
-      const __half* wbase = p.w + (size_t)nblk * p.total_steps * (step_bytes / 2);
-      const long long in_row0 = (long long)p.pstart_in[b] + t0 - p.halo_lo;
-      auto load_a_chunk = [&](int kc) {
-        const int slot = kc % p.a_slots;
-        mbar_wait(bar_ae + 8 * slot, ((kc / p.a_slots) & 1) ^ 1);
-        mbar_expect_tx(bar_af + 8 * slot, slot_bytes);
-        for (int q = 0; q < planes_per_chunk; ++q) {
-          const int plane = kc * planes_per_chunk + q;
-          bulk_g2s(sA + slot_bytes * slot + (uint32_t)q * RA * 16, p.in + (size_t)plane * p.in_plane_stride + in_row0 * 8,
-                   (uint32_t)RA * 16, bar_af + 8 * slot);
+      uint32_t a_it = 0, b_it = 0;  // running ring counters
+      bool first = true;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, first = false) {
+        const TileInfo ti = locate_item(p, item);
+        const __half* wbase = p.w + (size_t)ti.nblk * p.total_steps * (step_bytes / 2);
+        const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
+        auto load_a_chunk = [&](int kc) {
+          const uint32_t slot = a_it % p.a_slots;
+          mbar_wait(bar_ae + 8 * slot, ((a_it / p.a_slots) & 1) ^ 1);
+          mbar_expect_tx(bar_af + 8 * slot, slot_bytes);
+          for (int q = 0; q < planes_per_chunk; ++q) {
+            const int plane = kc * planes_per_chunk + q;
+            bulk_g2s(sA + slot_bytes * slot + (uint32_t)q * RA * 16, p.in + (size_t)plane * p.in_plane_stride + in_row0 * 8,
+                     (uint32_t)RA * 16, bar_af + 8 * slot);
+          }
+          ++a_it;
+        };
+        auto load_b = [&](int i) {  // i-th stage load of this item
+          const uint32_t st = b_it % p.nstages;
+          mbar_wait(bar_be + 8 * st, ((b_it / p.nstages) & 1) ^ 1);
+          const int first_step = i * p.sps;
+          const int nsteps = min(p.sps, p.total_steps - first_step);
+          const uint32_t bytes = step_bytes * nsteps;
+          mbar_expect_tx(bar_bf + 8 * st, bytes);
+          bulk_g2s(sB + stage_bytes * st, wbase + (size_t)first_step * (step_bytes / 2), bytes, bar_bf + 8 * st);
+          ++b_it;
+        };
+        const bool load_w = !p.b_resident || first;
+        // consumption order is (kc, tap); keep one A chunk of lookahead ahead of the B loads
+        load_a_chunk(0);
+        int next_b = 0;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          if (kc + 1 < p.nkc) load_a_chunk(kc + 1);
+          const int last_step = (kc + 1) * p.taps - 1;  // last step that uses chunk kc
+          while (load_w && next_b < p.nloads && next_b * p.sps <= last_step) load_b(next_b++);
         }
-      };
-      auto load_b = [&](int i) {  // i-th stage load
-        const int st = i % p.nstages;
-        mbar_wait(bar_be + 8 * st, ((i / p.nstages) & 1) ^ 1);
-        const int first = i * p.sps;
-        const int nsteps = min(p.sps, p.total_steps - first);
-        const uint32_t bytes = step_bytes * nsteps;
-        mbar_expect_tx(bar_bf + 8 * st, bytes);
-        bulk_g2s(sB + stage_bytes * st, wbase + (size_t)first * (step_bytes / 2), bytes, bar_bf + 8 * st);
-      };
-      // consumption order is (kc, tap); keep one A chunk of lookahead ahead of the B loads
-      load_a_chunk(0);
-      int next_b = 0;
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        if (kc + 1 < p.nkc) load_a_chunk(kc + 1);
-        const int last_step = (kc + 1) * p.taps - 1;  // last step that uses chunk kc
-        while (next_b < p.nloads && next_b * p.sps <= last_step) load_b(next_b++);
       }
     }
   } else if (warp == 1) {
@@ -297,53 +322,85 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) umma_conv_kernel(const __grid_
       // ---------------- MMA issuer ----------------
       const uint32_t a_lbo = (uint32_t)RA * 16, b_lbo = (uint32_t)p.nb * 16;
       const int k16_per_chunk = p.kc / 16;
-      int step = 0;
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        const int slot = kc % p.a_slots;
-        mbar_wait(bar_af + 8 * slot, (kc / p.a_slots) & 1);
-        const uint32_t a_slot = sA + slot_bytes * slot;
-        for (int tap = 0; tap < p.taps; ++tap, ++step) {
-          const int load = step / p.sps, si = step - load * p.sps;
-          const int st = load % p.nstages;
-          if (si == 0) mbar_wait(bar_bf + 8 * st, (load / p.nstages) & 1);
-          tc_fence_after();
-          const int row_off = p.halo_lo + p.tap_shift[tap];
-          const uint32_t b_stage = sB + stage_bytes * st + step_bytes * si;
-          for (int a = 0; a < p.mt; ++a) {
-            for (int k = 0; k < k16_per_chunk; ++k) {
-              const uint64_t ad = make_desc(a_slot + (uint32_t)(2 * k) * RA * 16 + (uint32_t)(a * 128 + row_off) * 16, a_lbo, 128u);
-              const uint64_t bd = make_desc(b_stage + (uint32_t)(2 * k) * p.nb * 16, b_lbo, 128u);
-              tc_mma_f16(tmem_base + (uint32_t)(a * p.nb), ad, bd, p.idesc, (step > 0 || k > 0) ? 1u : 0u);
+      uint32_t a_it = 0, b_it = 0, it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * acc_cols;
+        int step = 0;
+        for (int kc = 0; kc < p.nkc; ++kc, ++a_it) {
+          const uint32_t slot = a_it % p.a_slots;
+          mbar_wait(bar_af + 8 * slot, (a_it / p.a_slots) & 1);
+          const uint32_t a_slot = sA + slot_bytes * slot;
+          for (int tap = 0; tap < p.taps; ++tap, ++step) {
+            const int load = step / p.sps, si = step - load * p.sps;
+            uint32_t st;
+            if (p.b_resident) {
+              st = 0;
+              if (it == 0 && si == 0 && load == 0) mbar_wait(bar_bf, 0);
+            } else {
+              st = (b_it + load) % p.nstages;
+              if (si == 0) mbar_wait(bar_bf + 8 * st, ((b_it + load) / p.nstages) & 1);
             }
+            tc_fence_after();
+            const int row_off = p.halo_lo + p.tap_shift[tap];
+            const uint32_t b_stage = p.b_resident ? sB + step_bytes * step : sB + stage_bytes * st + step_bytes * si;
+            for (int a = 0; a < p.mt; ++a) {
+              for (int k = 0; k < k16_per_chunk; ++k) {
+                const uint64_t ad = make_desc(a_slot + (uint32_t)(2 * k) * RA * 16 + (uint32_t)(a * 128 + row_off) * 16, a_lbo, 128u);
+                const uint64_t bd = make_desc(b_stage + (uint32_t)(2 * k) * p.nb * 16, b_lbo, 128u);
+                tc_mma_f16(tmem_acc + (uint32_t)(a * p.nb), ad, bd, p.idesc, (step > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if (!p.b_resident && (si == p.sps - 1 || step == p.total_steps - 1)) tc_commit(bar_be + 8 * st);
           }
-          if (si == p.sps - 1 || step == p.total_steps - 1) tc_commit(bar_be + 8 * st);
+          tc_commit(bar_ae + 8 * slot);
         }
-        tc_commit(bar_ae + 8 * slot);
+        if (!p.b_resident) b_it += p.nloads;
+        tc_commit(bar_accf + 8 * buf);
       }
-      tc_commit(bar_acc);
     }
   } else {
     // ---------------- epilogue (8 warps) ----------------
-    const int wq = warp & 3;          // TMEM lane quarter this warp may access
+    const int wq = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // two warps per quarter split the work items
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const float* bias = p.bias + (size_t)nblk * p.nb;
-    const float* bias_u = p.bias_utt ? p.bias_utt + (size_t)b * gridDim.y * p.nb + (size_t)nblk * p.nb : nullptr;
+    const int etid = threadIdx.x - 64;
     const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE;
     const int nch = wide ? 32 : 16;
     const int items_per_acc = p.nb / nch;
-    const int n_items = p.mt * items_per_acc;
-    for (int it = half; it < n_items; it += 2) {
-      const int a = it / items_per_acc;
-      const int c0 = (it - a * items_per_acc) * nch;
-      const int t = t0 + a * 128 + wq * 32 + lane;
-      const bool valid = t < len;
-      const long long orow = (long long)p.pstart_out[b] + (long long)t * p.out_mul + p.out_off;
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
-      if (wide) epilogue_item<32, false>(p, taddr, valid, orow, nblk * p.nb + c0, bias + c0, bias_u ? bias_u + c0 : nullptr);
-      else if (p.accum_mode == UACC_NONE) epilogue_item<16, false>(p, taddr, valid, orow, nblk * p.nb + c0, bias + c0, bias_u ? bias_u + c0 : nullptr);
-      else epilogue_item<16, true>(p, taddr, valid, orow, nblk * p.nb + c0, bias + c0, bias_u ? bias_u + c0 : nullptr);
+    const int n_sub = p.mt * items_per_acc;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      const TileInfo ti = locate_item(p, item);
+      float* bias = bias_s + buf * p.nb;
+      // bias of this item (the set used two items ago has been fully consumed: its acc_empty arrivals
+      // happen after the last read)
+      for (int i = etid; i < p.nb; i += NUM_EPI_WARPS * 32) {
+        float v = p.bias[(size_t)ti.nblk * p.nb + i];
+        if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.n_nblk * p.nb + (size_t)ti.nblk * p.nb + i];
+        bias[i] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");
+      mbar_wait(bar_accf + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * acc_cols;
+      for (int sub = half; sub < n_sub; sub += 2) {
+        const int a = sub / items_per_acc;
+        const int c0 = (sub - a * items_per_acc) * nch;
+        const int t = ti.t0 + a * 128 + wq * 32 + lane;
+        const bool valid = t < ti.len;
+        const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off;
+        const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
+        if (wide) epilogue_item<32, false>(p, taddr, valid, orow, ti.nblk * p.nb + c0, bias + c0);
+        else if (p.accum_mode == UACC_NONE) epilogue_item<16, false>(p, taddr, valid, orow, ti.nblk * p.nb + c0, bias + c0);
+        else epilogue_item<16, true>(p, taddr, valid, orow, ti.nblk * p.nb + c0, bias + c0);
+      }
+      // release the accumulator set
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * buf) : "memory");
     }
   }
   tc_fence_before();
@@ -415,7 +472,7 @@ uint16_t f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
 
 size_t layer_smem(int planes_per_chunk, int ra, int a_slots, size_t stage_bytes, int nstages) {
   size_t a = (size_t(planes_per_chunk) * ra * 16 * a_slots + 127) & ~size_t(127);
-  return a + stage_bytes * nstages + 256;
+  return a + stage_bytes * nstages + 256 + 1024;  // barriers + bias
 }
 
 // wsel(co, ci, tap) returns the weight of output channel co, input channel ci, tap index `tap`
@@ -448,37 +505,51 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
   if (L.halo_lo > GAP || L.halo_hi > GAP) fail(SBV2_ERR_UNSUPPORTED, "conv halo exceeds the packing gap");
   L.total_steps = taps * L.nkc;
   const size_t step_bytes = size_t(L.nb) * L.kc * 2;
-  L.sps = int(std::max<size_t>(1, (16 * 1024) / step_bytes));
-  L.sps = std::min(L.sps, L.total_steps);
-  L.nloads = (L.total_steps + L.sps - 1) / L.sps;
-  const size_t stage_bytes = step_bytes * L.sps;
-  // accumulators per CTA: keep MT*NB <= 256 TMEM columns so that two CTAs can share an SM
-  int mt = std::max(1, std::min(mt_pref, 256 / L.nb));
-  if (mt == 3) mt = 2;
+  const size_t w_bytes = step_bytes * L.total_steps;
+  // accumulators per CTA: two sets of MT*NB <= 256 TMEM columns (double-buffered across work items)
+  int mt = 1;
+  while (mt * 2 <= std::min(mt_pref, 256 / L.nb)) mt *= 2;
   const int ppc = L.kc / 8;
+  const size_t budget = size_t(SMEM_LIMIT) - 2048;
   bool placed = false;
   for (; mt >= 1 && !placed; mt >>= 1) {
     const int ra = 128 * mt + L.halo_lo + L.halo_hi;
-    // first try to fit two CTAs per SM, then one
-    for (size_t budget : {size_t(SMEM_TWO_CTAS), size_t(SMEM_LIMIT)}) {
-      for (int slots = std::min(MAX_ASLOTS, L.nkc); slots >= std::min(2, L.nkc) && !placed; --slots) {
-        for (int ns = std::min(MAX_STAGES, L.nloads); ns >= std::min(2, L.nloads) && !placed; --ns) {
-          size_t s = layer_smem(ppc, ra, slots, stage_bytes, ns);
-          if (s <= budget) {
-            L.mt = mt;
-            L.a_slots = slots;
-            L.nstages = ns;
-            L.smem = s;
-            placed = true;
-          }
+    const size_t slot = size_t(ppc) * ra * 16;
+    // weights resident for the whole kernel when they fit next to a double-buffered activation tile
+    const int min_slots = std::max(2, std::min(L.nkc + 1, MAX_ASLOTS));
+    if (L.n_nblk == 1 && w_bytes + slot * std::min(2 * L.nkc, MAX_ASLOTS) <= budget && w_bytes <= 100 * 1024) {
+      L.b_resident = 1;
+      L.sps = L.total_steps;
+      L.nloads = 1;
+      L.nstages = 1;
+      L.mt = mt;
+      L.a_slots = std::min(2 * L.nkc, MAX_ASLOTS);
+      while (L.a_slots < MAX_ASLOTS && w_bytes + slot * (L.a_slots + 1) <= budget && L.a_slots < 3 * L.nkc) ++L.a_slots;
+      L.smem = ((slot * L.a_slots + 127) & ~size_t(127)) + w_bytes + 2048;
+      placed = true;
+      break;
+    }
+    L.b_resident = 0;
+    L.sps = int(std::max<size_t>(1, (16 * 1024) / step_bytes));
+    L.sps = std::min(L.sps, L.total_steps);
+    L.nloads = (L.total_steps + L.sps - 1) / L.sps;
+    const size_t stage_bytes = step_bytes * L.sps;
+    for (int ns = std::min(MAX_STAGES, std::max(2, L.nloads)); ns >= 2 && !placed; --ns) {
+      for (int slots = MAX_ASLOTS; slots >= min_slots && !placed; --slots) {
+        size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + 2048;
+        if (sm <= budget + 2048) {
+          L.mt = mt;
+          L.a_slots = slots;
+          L.nstages = ns;
+          L.smem = sm;
+          placed = true;
         }
       }
-      if (placed) break;
     }
     if (mt == 1) break;
   }
   if (!placed) fail(SBV2_ERR_UNSUPPORTED, "conv tile does not fit in shared memory");
-  L.tmem_cols = pow2_at_least(L.mt * L.nb);
+  L.tmem_cols = pow2_at_least(2 * L.mt * L.nb);
   L.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(L.nb >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
   // pack weights: [nblk][kc][tap][KC/8][NB][8]
   std::vector<uint16_t> pk(size_t(L.n_nblk) * L.total_steps * L.nb * L.kc);
@@ -496,7 +567,7 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
   return L;
 }
 
-int mt_slot(int mt) { return mt == 1 ? 0 : (mt == 2 ? 1 : 2); }
+int mt_slot(int mt) { return mt == 1 ? 0 : (mt == 2 ? 1 : (mt == 4 ? 2 : (mt == 8 ? 3 : 4))); }
 
 void set_smem_attr() {
   static bool done = false;
@@ -550,6 +621,8 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.n_utt = n_utt;
   a.cin = L.cin;
   a.nb = L.nb;
+  a.n_nblk = L.n_nblk;
+  a.b_resident = L.b_resident;
   a.taps = L.taps;
   a.kc = L.kc;
   a.nkc = L.nkc;
@@ -571,7 +644,14 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.tmem_cols = L.tmem_cols;
   a.idesc = L.idesc;
   if (gi.n_tiles[slot] <= 0) return;
-  dim3 grid(gi.n_tiles[slot], L.n_nblk);
+  a.n_items = gi.n_tiles[slot] * L.n_nblk;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid(std::min(a.n_items, num_sms));
   umma_conv_kernel<<<grid, NUM_THREADS, L.smem, ctx.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
@@ -589,8 +669,8 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
   const int B = int(ylen.size());
   BatchGeom bg;
   bg.g.resize(muls.size());
-  // ints: per geom: pstart[B], len[B], prefix x3 [(B+1)*3]; then ystart[B], wstart[B]
-  const size_t per = size_t(2) * B + size_t(3) * (B + 1);
+  // ints: per geom: pstart[B], len[B], prefix x5 [(B+1)*5]; then ystart[B], wstart[B]
+  const size_t per = size_t(2) * B + size_t(5) * (B + 1);
   const size_t total = per * muls.size() + size_t(2) * B;
   // the pinned blob of the previous run may still be in flight on the stream
   CUDA_CHECK(cudaStreamSynchronize(owner->stream));
@@ -614,7 +694,7 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
       r += l + GAP;
     }
     G.rows_tot = r + TAIL_ROWS;
-    for (int slot = 0; slot < 3; ++slot) {
+    for (int slot = 0; slot < 5; ++slot) {
       int tm = 128 << slot;
       int* pf = hp + 2 * B + slot * (B + 1);
       int acc = 0;
@@ -641,7 +721,7 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
     const int* dp = d + per * s;
     G.d_pstart = dp;
     G.d_len = dp + B;
-    for (int slot = 0; slot < 3; ++slot) G.d_prefix[slot] = dp + 2 * B + slot * (B + 1);
+    for (int slot = 0; slot < 5; ++slot) G.d_prefix[slot] = dp + 2 * B + slot * (B + 1);
   }
   bg.d_ystart = d + per * muls.size();
   bg.d_wstart = bg.d_ystart + B;

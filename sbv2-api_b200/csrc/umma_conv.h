@@ -13,7 +13,7 @@ struct sbv2_model;
 namespace sbv2 {
 
 constexpr int UMMA_GAP = 32;         // zero rows around each utterance (>= largest halo: 5*(11-1)/2 = 25)
-constexpr int UMMA_TAIL_ROWS = 640;  // slack rows after the last utterance (a tile may over-read)
+constexpr int UMMA_TAIL_ROWS = 2304;  // slack rows after the last utterance (a tile may over-read)
 constexpr int UMMA_MAX_TAPS = 16;
 
 struct HostConv {
@@ -37,6 +37,7 @@ struct ConvLayer {
   float* bias = nullptr; // [cout]
   int cin = 0, cout = 0, nb = 0, n_nblk = 1, taps = 1, kc = 64, nkc = 1, mt = 1, sps = 1, nstages = 2, nloads = 1, total_steps = 1;
   int a_slots = 1;
+  int b_resident = 0;  // all weight steps stay in shared memory for the whole (persistent) kernel
   int tap_shift[UMMA_MAX_TAPS] = {0};
   int halo_lo = 0, halo_hi = 0;
   size_t smem = 0;
@@ -56,8 +57,8 @@ struct Geom {
   std::vector<int> pstart, len;
   const int* d_pstart = nullptr;
   const int* d_len = nullptr;
-  const int* d_prefix[3] = {nullptr, nullptr, nullptr};  // tiles of 128 * {1, 2, 4} rows
-  int n_tiles[3] = {0, 0, 0};
+  const int* d_prefix[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // tiles of 128 * {1, 2, 4, 8, 16} rows
+  int n_tiles[5] = {0, 0, 0, 0, 0};
   int max_len = 0;
 };
 struct BatchGeom {

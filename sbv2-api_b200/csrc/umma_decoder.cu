@@ -83,7 +83,7 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
     const HostConv& U = w.ups[s];
     if (U.d0 != C) fail(SBV2_ERR_UNSUPPORTED, "decoder upsample channel mismatch");
     std::vector<ConvLayer> phases;
-    for (int r = 0; r < w.up_u[s]; ++r) phases.push_back(make_up_phase_layer(owner, U, w.up_u[s], r, 4));
+    for (int r = 0; r < w.up_u[s]; ++r) phases.push_back(make_up_phase_layer(owner, U, w.up_u[s], r, 16));
     D->ups.push_back(phases);
     D->up_u.push_back(w.up_u[s]);
     C = U.d1;
@@ -92,8 +92,8 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
       size_t rb = size_t(s) * w.per + j;
       std::vector<ConvLayer> l1, l2;
       for (size_t l = 0; l < w.res_c1[rb].size(); ++l) {
-        l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 4));
-        l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 4));
+        l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 16));
+        l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 16));
       }
       D->c1.push_back(l1);
       D->c2.push_back(l2);
