@@ -1,0 +1,352 @@
+// DeBERTa-v2 glue kernels: embedding gather, wide LayerNorm with planar fp16 copy, disentangled
+// attention (HF modeling_deberta_v2.py:137-345 restated), output scatter.
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "kernels.h"
+
+namespace sbv2 {
+namespace {
+
+__global__ void embed_rows_kernel(float* h, const float* table, const int* ids, int C, int n_vocab, int64_t rows) {
+  int64_t row = blockIdx.x;
+  if (row >= rows) return;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+  const float4* src = reinterpret_cast<const float4*>(table + (size_t)id * C);
+  float4* dst = reinterpret_cast<float4*>(h + (size_t)row * C);
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+// one warp per row; lane handles planes lane, lane+32, ... (NPL of them)
+template <int NPL>
+__global__ void ln_planar_wide_kernel(float* h, __half* hp, __half* hp2, const float* y32, const float* gamma, const float* beta,
+                                      float eps, int C, PlanarSegs s) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= s.len[b]) return;
+  const int planes = C / 8;
+  const size_t row = (size_t)s.start[b] + t;
+  const size_t prow = (size_t)(s.pstart[b] + t) * 8;
+  float v[NPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int pl = lane + 32 * q;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+    if (pl < planes) {
+      const float4 x0 = *reinterpret_cast<const float4*>(h + row * C + pl * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(h + row * C + pl * 8 + 4);
+      v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x0.z; v[q][3] = x0.w;
+      v[q][4] = x1.x; v[q][5] = x1.y; v[q][6] = x1.z; v[q][7] = x1.w;
+      if (y32) {
+        const float4 y0 = *reinterpret_cast<const float4*>(y32 + (size_t)pl * s.plane_stride + prow);
+        const float4 y1 = *reinterpret_cast<const float4*>(y32 + (size_t)pl * s.plane_stride + prow + 4);
+        v[q][0] += y0.x; v[q][1] += y0.y; v[q][2] += y0.z; v[q][3] += y0.w;
+        v[q][4] += y1.x; v[q][5] += y1.y; v[q][6] += y1.z; v[q][7] += y1.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[q][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    if (lane + 32 * q < planes) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[q][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int pl = lane + 32 * q;
+    if (pl >= planes) continue;
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = (v[q][e] - mean) * rstd * gamma[pl * 8 + e] + beta[pl * 8 + e];
+    *reinterpret_cast<float4*>(h + row * C + pl * 8) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(h + row * C + pl * 8 + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(r[2 * e], r[2 * e + 1]);
+    if (hp) *reinterpret_cast<uint4*>(hp + (size_t)pl * s.plane_stride + prow) = o;
+    if (hp2) *reinterpret_cast<uint4*>(hp2 + (size_t)pl * s.plane_stride + prow) = o;
+  }
+}
+
+__global__ void scatter_rows_kernel(float* out, const float* h, int C, int S, PlanarSegs s) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  float4* dst = reinterpret_cast<float4*>(out + ((size_t)b * S + t) * C);
+  if (t < s.len[b]) {
+    const float4* src = reinterpret_cast<const float4*>(h + (size_t)(s.start[b] + t) * C);
+    for (int i = threadIdx.x; i < C / 4; i += blockDim.x) dst[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < C / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// disentangled attention: 64 queries x 64 keys per step, D = 64, fp32 math on fp16 q|k|v.
+// score[i][j] = (Q_i.K_j + Q_i.posK[idx(i-j)] + K_j.posQ[idx(i-j)]) / sqrt(3 D)
+// For one (query tile, key tile) pair the needed position rows form one contiguous range of at
+// most 127 rows (idx is monotone in i-j), so both bias terms are small tile GEMMs followed by a gather.
+// ---------------------------------------------------------------------------------------------
+constexpr int BQ = 64, BK = 64, BD = 64, BP = 128;
+
+__global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, const __half* qkv, const float* pos_k, const float* pos_q,
+                                                                const int* bucket_idx, int max_rel, int heads, PlanarSegs s) {
+  extern __shared__ float sm[];
+  float* Qt = sm;                     // [BD][BQ+1]   (scaled)
+  float* Kt = Qt + BD * (BQ + 1);     // [BD][BK+1]
+  float* Vs = Kt + BD * (BK + 1);     // [BK][BD]
+  float* Ps = Vs + BK * BD;           // [BQ][BK+1]
+  float* Pt = Ps + BQ * (BK + 1);     // [BD][BP+1]   position rows (transposed), posK then posQ
+  float* C2P = Pt + BD * (BP + 1);    // [BQ][BP+1]
+  float* P2C = C2P + BQ * (BP + 1);   // [BK][BP+1]
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int len = s.len[b];
+  const int q0 = blockIdx.x * BQ;
+  if (q0 >= len) return;
+  const long long pbase = s.pstart[b];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  constexpr int DP = BD / 8;
+  const int HD = heads * BD;
+  const float scale = 1.0f / sqrtf(3.0f * BD);
+  const int q_plane0 = h * DP, k_plane0 = heads * DP + h * DP, v_plane0 = 2 * heads * DP + h * DP;
+
+  for (int i = tid; i < BQ * DP; i += 256) {
+    const int r = i % BQ, pl = i / BQ;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    if (q0 + r < len) {
+      const uint4 u = *reinterpret_cast<const uint4*>(qkv + (size_t)(q_plane0 + pl) * s.plane_stride + (pbase + q0 + r) * 8);
+      const __half2* uh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 y = __half22float2(uh[e]);
+        f[2 * e] = y.x * scale;
+        f[2 * e + 1] = y.y * scale;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Qt[(pl * 8 + e) * (BQ + 1) + r] = f[e];
+  }
+
+  float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -CUDART_INF_F;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[i][c] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < len; k0 += BK) {
+    __syncthreads();
+    // K, V tiles
+    for (int i = tid; i < BK * DP; i += 256) {
+      const int r = i % BK, pl = i / BK;
+      float kf[8], vf[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kf[e] = vf[e] = 0.f;
+      if (k0 + r < len) {
+        const uint4 uk = *reinterpret_cast<const uint4*>(qkv + (size_t)(k_plane0 + pl) * s.plane_stride + (pbase + k0 + r) * 8);
+        const uint4 uv = *reinterpret_cast<const uint4*>(qkv + (size_t)(v_plane0 + pl) * s.plane_stride + (pbase + k0 + r) * 8);
+        const __half2* kh = reinterpret_cast<const __half2*>(&uk);
+        const __half2* vh = reinterpret_cast<const __half2*>(&uv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __half22float2(kh[e]), c = __half22float2(vh[e]);
+          kf[2 * e] = a.x; kf[2 * e + 1] = a.y;
+          vf[2 * e] = c.x; vf[2 * e + 1] = c.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        Kt[(pl * 8 + e) * (BK + 1) + r] = kf[e];
+        Vs[r * BD + pl * 8 + e] = vf[e];
+      }
+    }
+    // position range of this tile pair: delta = i - j in [q0-k0-63, q0-k0+63]
+    const int dmin = max(q0 - k0 - (BK - 1), -max_rel), dmax = min(q0 - k0 + (BQ - 1), max_rel);
+    const int pmin = bucket_idx[dmin + max_rel], pmax = bucket_idx[dmax + max_rel];
+    const int np = pmax - pmin + 1;  // <= 127
+    for (int phase = 0; phase < 2; ++phase) {
+      const float* pos = phase == 0 ? pos_k : pos_q;
+      __syncthreads();  // Pt free (and K/V/Q tiles visible on the first pass)
+      for (int i = tid; i < np * BD; i += 256) {
+        const int pr = i / BD, d = i % BD;
+        Pt[d * (BP + 1) + pr] = pos[(size_t)(pmin + pr) * HD + h * BD + d];
+      }
+      __syncthreads();
+      // [64 x np] = X[64 x 64] . Pt[64 x np]; thread: rows ty*4.., cols tx*8..
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+      const float* X = phase == 0 ? Qt : Kt;
+      for (int d = 0; d < BD; ++d) {
+        float xa[4], pb[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xa[i] = X[d * (BQ + 1) + ty * 4 + i];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pb[c] = Pt[d * (BP + 1) + tx * 8 + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(xa[i], pb[c], acc[i][c]);
+      }
+      float* dst = phase == 0 ? C2P : P2C;
+      const float mul = phase == 0 ? 1.0f : scale;  // Q is pre-scaled, K is not
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dst[(ty * 4 + i) * (BP + 1) + tx * 8 + c] = acc[i][c] * mul;
+    }
+    __syncthreads();
+    float sc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
+    for (int d = 0; d < BD; ++d) {
+      float qa[4], kb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = Qt[d * (BQ + 1) + ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kb[j] = Kt[d * (BK + 1) + tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sc[i][j] = fmaf(qa[i], kb[j], sc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int qi = q0 + ty * 4 + i;
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kj = k0 + tx * 4 + j;
+        int delta = qi - kj;
+        delta = delta < -max_rel ? -max_rel : (delta > max_rel ? max_rel : delta);
+        int pi = bucket_idx[delta + max_rel] - pmin;
+        pi = pi < 0 ? 0 : (pi >= np ? np - 1 : pi);
+        sc[i][j] += C2P[(ty * 4 + i) * (BP + 1) + pi] + P2C[(tx * 4 + j) * (BP + 1) + pi];
+        if (kj >= len) sc[i][j] = -CUDART_INF_F;
+        mx = fmaxf(mx, sc[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float m_new = fmaxf(m_run[i], mx);
+      const float corr = (m_run[i] == -CUDART_INF_F) ? 0.f : expf(m_run[i] - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pv = (sc[i][j] == -CUDART_INF_F) ? 0.f : expf(sc[i][j] - m_new);
+        Ps[(ty * 4 + i) * (BK + 1) + tx * 4 + j] = pv;
+        psum += pv;
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
+      l_run[i] = l_run[i] * corr + psum;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[i][c] *= corr;
+    }
+    __syncthreads();
+    for (int j = 0; j < BK; ++j) {
+      float pv[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = Ps[(ty * 4 + i) * (BK + 1) + j];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vv[c] = Vs[j * BD + tx * 4 + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[i][c] = fmaf(pv[i], vv[c], o[i][c]);
+    }
+  }
+  __syncthreads();
+  float* Os = Kt;  // [BQ][BD] fits in BD*(BK+1)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float inv = 1.0f / l_run[i];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Os[(ty * 4 + i) * BD + tx * 4 + c] = o[i][c] * inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < BQ * DP; i += 256) {
+    const int r = i % BQ, pl = i / BQ;
+    if (q0 + r >= len) continue;
+    uint4 u;
+    __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(Os[r * BD + pl * 8 + 2 * e], Os[r * BD + pl * 8 + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(out + (size_t)(h * DP + pl) * s.plane_stride + (pbase + q0 + r) * 8) = u;
+  }
+}
+
+}  // namespace
+
+#define POST_LAUNCH(ctx)            \
+  do {                              \
+    CUDA_CHECK(cudaGetLastError()); \
+    (ctx).count();                  \
+  } while (0)
+
+void launch_embed_rows(const LaunchCtx& ctx, float* h, const float* table, const int* ids, int C, int n_vocab, int64_t rows) {
+  if (rows <= 0) return;
+  embed_rows_kernel<<<(unsigned)rows, 128, 0, ctx.stream>>>(h, table, ids, C, n_vocab, rows);
+  POST_LAUNCH(ctx);
+}
+
+void launch_ln_planar_wide(const LaunchCtx& ctx, float* h, __half* hp, __half* hp2, const float* y32, const float* gamma,
+                           const float* beta, float eps, int C, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (C % 8 != 0 || C > 1024) fail(SBV2_ERR_UNSUPPORTED, "ln_planar_wide: C must be a multiple of 8 and <= 1024");
+  dim3 grid((s.max_len + 7) / 8, s.n);
+  const int planes = C / 8;
+  if (planes <= 32) ln_planar_wide_kernel<1><<<grid, 256, 0, ctx.stream>>>(h, hp, hp2, y32, gamma, beta, eps, C, s);
+  else if (planes <= 64) ln_planar_wide_kernel<2><<<grid, 256, 0, ctx.stream>>>(h, hp, hp2, y32, gamma, beta, eps, C, s);
+  else ln_planar_wide_kernel<4><<<grid, 256, 0, ctx.stream>>>(h, hp, hp2, y32, gamma, beta, eps, C, s);
+  POST_LAUNCH(ctx);
+}
+
+void launch_scatter_rows(const LaunchCtx& ctx, float* out, const float* h, int C, int S, const PlanarSegs& s) {
+  if (s.n <= 0 || S <= 0) return;
+  dim3 grid(S, s.n);
+  scatter_rows_kernel<<<grid, 128, 0, ctx.stream>>>(out, h, C, S, s);
+  POST_LAUNCH(ctx);
+}
+
+void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k, const float* pos_q,
+                              const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (head_dim != BD) fail(SBV2_ERR_UNSUPPORTED, "deberta attention: head_dim must be 64");
+  size_t smem = sizeof(float) * (size_t)(BD * (BQ + 1) + BD * (BK + 1) + BK * BD + BQ * (BK + 1) + BD * (BP + 1) + BQ * (BP + 1) + BK * (BP + 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((s.max_len + BQ - 1) / BQ, heads, s.n);
+  deberta_attention_kernel<<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k, pos_q, bucket_idx, max_rel, heads, s);
+  POST_LAUNCH(ctx);
+}
+
+}  // namespace sbv2

@@ -1,6 +1,307 @@
+// DeBERTa-v2 feature encoder (deberta.onnx) as a static kernel plan.
+// Replaces the `ort::Session::run` of crates/sbv2_core/src/bert.rs:11-16.  The graph is
+// HF DebertaV2ForMaskedLM up to hidden_states[-3] (scripts/convert/convert_deberta.py:27-35): only
+// encoder layers 0..L-3 are live; the MLM head and the last two layers are never computed.
+// GEMMs / the k=3 ConvLayer run on the tcgen05 kernel (fp16 operands, fp32 accumulate), the residual
+// stream and LayerNorms are fp32, the disentangled attention is an fp32 CUDA-core kernel.
+#include <algorithm>
+#include <cmath>
+#include <sstream>
+
 #include "model.h"
+#include "umma_conv.h"
+
 namespace sbv2 {
-sbv2_model* create_bert_model(const OnnxModel&, int) { fail(SBV2_ERR_UNSUPPORTED, "bert not built yet"); }
-void bert_predict(sbv2_model*, const int64_t*, const int64_t*, int, int64_t, float*) { fail(SBV2_ERR_UNSUPPORTED, "bert not built yet"); }
-int bert_hidden(const sbv2_model*) { return 0; }
+namespace {
+
+struct BertLayer {
+  ConvLayer qkv, o, f1, f2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  float *pos_k = nullptr, *pos_q = nullptr;  // [2*span, hidden] projections of LN(rel_embeddings)
+};
+
+struct BertModel : sbv2_model {
+  int hidden = 0, heads = 0, inter = 0, vocab = 0, n_layers_total = 0, n_run = 0, span = 0, max_rel = 511;
+  float eps = 1e-7f;
+  float* word_emb = nullptr;
+  float *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<BertLayer> layers;
+  bool has_conv = false;
+  ConvLayer conv;
+  float *conv_g = nullptr, *conv_b = nullptr;
+  int* bucket_idx = nullptr;  // device [2*max_rel+1]
+  DBuf ids, h, embp, hp, qkvp, ctxp, f1p, y32, meta, outd;
+  PinnedBuf pin_meta, pin_io;
+};
+
+std::string find_prefix(const OnnxModel& m) {
+  for (const char* p : {"deberta.", "", "model.deberta.", "bert."})
+    if (m.find(std::string(p) + "embeddings.word_embeddings.weight")) return p;
+  fail(SBV2_ERR_UNSUPPORTED, "not a DeBERTa-v2 graph (embeddings.word_embeddings.weight missing)");
+}
+
+// HF make_log_bucket_position in float32, as torch evaluates it
+int log_bucket(int rel, int bucket_size, int max_position) {
+  const int mid = bucket_size / 2;
+  const int sign = (rel > 0) - (rel < 0);
+  const int abs_pos = (rel < mid && rel > -mid) ? mid - 1 : std::abs(rel);
+  if (abs_pos <= mid) return rel;
+  const float log_pos = std::ceil(std::log(float(abs_pos) / float(mid)) / std::log(float(max_position - 1) / float(mid)) * float(mid - 1)) + float(mid);
+  return int(log_pos) * sign;
+}
+
+}  // namespace
+
+sbv2_model* create_bert_model(const OnnxModel& m, int device) {
+  std::unique_ptr<BertModel> M(new BertModel());
+  M->device = device;
+  M->is_bert = true;
+  CUDA_CHECK(cudaSetDevice(device));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+  M->metadata = m.metadata;
+  const std::string P = find_prefix(m);
+  auto get = [&](const std::string& n) -> const OnnxTensor& {
+    const OnnxTensor* t = m.find(P + n);
+    if (!t) fail(SBV2_ERR_UNSUPPORTED, "DeBERTa graph lacks initializer '" + P + n + "'");
+    return *t;
+  };
+  auto f32 = [&](const std::string& n) { return m.as_f32(get(n)); };
+  auto vec = [&](const std::string& n, int expect) {
+    auto v = f32(n);
+    if (int(v.size()) != expect) fail(SBV2_ERR_UNSUPPORTED, "initializer '" + n + "' has unexpected size");
+    return M->upload_f32(v);
+  };
+  const OnnxTensor& we = get("embeddings.word_embeddings.weight");
+  if (we.dims.size() != 2) fail(SBV2_ERR_UNSUPPORTED, "word embeddings must be 2-D");
+  M->vocab = int(we.dims[0]);
+  M->hidden = int(we.dims[1]);
+  if (m.find(P + "embeddings.position_embeddings.weight")) fail(SBV2_ERR_UNSUPPORTED, "position_biased_input=True is not supported");
+  if (M->hidden % 64 != 0 || M->hidden > 1024) fail(SBV2_ERR_UNSUPPORTED, "hidden size must be a multiple of 64 and <= 1024");
+  M->heads = M->hidden / 64;
+  M->word_emb = M->upload_f32(m.as_f32(we));
+  M->emb_g = vec("embeddings.LayerNorm.weight", M->hidden);
+  M->emb_b = vec("embeddings.LayerNorm.bias", M->hidden);
+  int L = 0;
+  while (m.find(P + "encoder.layer." + std::to_string(L) + ".attention.self.query_proj.weight")) ++L;
+  if (L < 3) fail(SBV2_ERR_UNSUPPORTED, "DeBERTa graph needs at least 3 encoder layers (output is hidden_states[-3])");
+  M->n_layers_total = L;
+  M->n_run = L - 2;
+  const OnnxTensor& rel = get("encoder.rel_embeddings.weight");
+  if (rel.dims.size() != 2 || rel.dims[1] != M->hidden || rel.dims[0] % 2 != 0) fail(SBV2_ERR_UNSUPPORTED, "unexpected rel_embeddings shape");
+  M->span = int(rel.dims[0] / 2);
+  LaunchCtx ctx = M->ctx();
+  // LN(rel_embeddings) once (norm_rel_ebd = layer_norm)
+  float* rel_raw = M->upload_f32(m.as_f32(rel));
+  float* rel_ln = nullptr;
+  {
+    float* g = vec("encoder.LayerNorm.weight", M->hidden);
+    float* b = vec("encoder.LayerNorm.bias", M->hidden);
+    CUDA_CHECK(cudaMalloc(&rel_ln, size_t(2) * M->span * M->hidden * 4));
+    M->owned_device.push_back(rel_ln);
+    launch_layernorm(ctx, rel_ln, rel_raw, nullptr, nullptr, g, b, M->eps, ACT_NONE, M->hidden, 2 * M->span);
+  }
+  // one segment of 2*span rows for the load-time projections
+  int two[2] = {0, 2 * M->span};
+  int* d_two = static_cast<int*>(M->upload_bytes(two, 8));
+  Segs pseg;
+  pseg.start = d_two;
+  pseg.len = d_two + 1;
+  pseg.n = 1;
+  pseg.max_len = 2 * M->span;
+  auto host_linear = [&](const std::string& n) {
+    HostConv hc;
+    const OnnxTensor& t = get(n + ".weight");
+    if (t.dims.size() < 2) fail(SBV2_ERR_UNSUPPORTED, n + ".weight must be a matrix");
+    hc.d0 = int(t.dims[0]);
+    hc.d1 = int(t.dims[1]);
+    hc.k = t.dims.size() > 2 ? int(t.dims[2]) : 1;
+    hc.w = m.as_f32(t);
+    hc.b = f32(n + ".bias");
+    return hc;
+  };
+  DBuf wt;
+  wt.stream = M->stream;
+  const int H = M->hidden;
+  for (int l = 0; l < M->n_run; ++l) {
+    const std::string lp = "encoder.layer." + std::to_string(l);
+    BertLayer B;
+    HostConv q = host_linear(lp + ".attention.self.query_proj"), k = host_linear(lp + ".attention.self.key_proj"),
+             v = host_linear(lp + ".attention.self.value_proj");
+    if (q.d0 != H || q.d1 != H) fail(SBV2_ERR_UNSUPPORTED, "unexpected attention projection shape");
+    // position projections (share_att_key): pos_k = key_proj(rel_ln), pos_q = query_proj(rel_ln); fp32, once per model
+    for (int which = 0; which < 2; ++which) {
+      const HostConv& hc = which == 0 ? k : q;
+      std::vector<float> t(size_t(H) * H);
+      for (int co = 0; co < H; ++co)
+        for (int ci = 0; ci < H; ++ci) t[size_t(ci) * H + co] = hc.w[size_t(co) * H + ci];
+      wt.ensure(t.size() * 4 + size_t(H) * 4);
+      CUDA_CHECK(cudaMemcpyAsync(wt.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, M->stream));
+      CUDA_CHECK(cudaMemcpyAsync(wt.as<float>() + t.size(), hc.b.data(), size_t(H) * 4, cudaMemcpyHostToDevice, M->stream));
+      float* dst = nullptr;
+      CUDA_CHECK(cudaMalloc(&dst, size_t(2) * M->span * H * 4));
+      M->owned_device.push_back(dst);
+      ConvArgs a;
+      a.in = rel_ln;
+      a.in_ld = H;
+      a.w = wt.as<float>();
+      a.bias = wt.as<float>() + t.size();
+      a.out = dst;
+      a.out_ld = H;
+      a.cin = H;
+      a.cout = H;
+      a.seg = pseg;
+      launch_conv(ctx, a);
+      CUDA_CHECK(cudaStreamSynchronize(M->stream));  // `t` and wt are reused
+      (which == 0 ? B.pos_k : B.pos_q) = dst;
+    }
+    HostConv qkv;
+    qkv.d0 = 3 * H;
+    qkv.d1 = H;
+    for (const HostConv* hc : {&q, &k, &v}) {
+      qkv.w.insert(qkv.w.end(), hc->w.begin(), hc->w.end());
+      qkv.b.insert(qkv.b.end(), hc->b.begin(), hc->b.end());
+    }
+    B.qkv = make_conv1d_layer(M.get(), qkv, 1, 1);
+    B.o = make_conv1d_layer(M.get(), host_linear(lp + ".attention.output.dense"), 1, 1);
+    HostConv f1 = host_linear(lp + ".intermediate.dense");
+    M->inter = f1.d0;
+    B.f1 = make_conv1d_layer(M.get(), f1, 1, 1);
+    B.f2 = make_conv1d_layer(M.get(), host_linear(lp + ".output.dense"), 1, 1);
+    B.ln1_g = vec(lp + ".attention.output.LayerNorm.weight", H);
+    B.ln1_b = vec(lp + ".attention.output.LayerNorm.bias", H);
+    B.ln2_g = vec(lp + ".output.LayerNorm.weight", H);
+    B.ln2_b = vec(lp + ".output.LayerNorm.bias", H);
+    M->layers.push_back(B);
+  }
+  if (m.find(P + "encoder.conv.conv.weight")) {
+    HostConv c = host_linear("encoder.conv.conv");
+    if (c.k % 2 == 0) fail(SBV2_ERR_UNSUPPORTED, "even ConvLayer kernel size");
+    M->conv = make_conv1d_layer(M.get(), c, 1, 1);
+    M->conv_g = vec("encoder.conv.LayerNorm.weight", H);
+    M->conv_b = vec("encoder.conv.LayerNorm.bias", H);
+    M->has_conv = true;
+  }
+  // bucket index table: clamp(bucket(delta) + span, 0, 2*span-1), delta in [-max_rel, max_rel]
+  {
+    std::vector<int> tab(size_t(2) * M->max_rel + 1);
+    for (int d = -M->max_rel; d <= M->max_rel; ++d) {
+      int bkt = log_bucket(d, M->span, 2 * M->span) + M->span;  // position_buckets = span, max_position = 2*span
+      tab[size_t(d + M->max_rel)] = std::min(std::max(bkt, 0), 2 * M->span - 1);
+    }
+    M->bucket_idx = static_cast<int*>(M->upload_bytes(tab.data(), tab.size() * 4));
+  }
+  for (DBuf* b : {&M->ids, &M->h, &M->embp, &M->hp, &M->qkvp, &M->ctxp, &M->f1p, &M->y32, &M->meta, &M->outd}) b->stream = M->stream;
+  std::ostringstream js;
+  js << "{\"kind\":\"deberta-v2\",\"hidden_size\":" << H << ",\"num_attention_heads\":" << M->heads << ",\"intermediate_size\":" << M->inter
+     << ",\"vocab_size\":" << M->vocab << ",\"num_hidden_layers\":" << L << ",\"live_layers\":" << M->n_run
+     << ",\"position_buckets\":" << M->span << ",\"conv_layer\":" << (M->has_conv ? "true" : "false") << "}";
+  M->describe_json = js.str();
+  CUDA_CHECK(cudaStreamSynchronize(M->stream));
+  return M.release();
+}
+
+int bert_hidden(const sbv2_model* m) { return static_cast<const BertModel*>(m)->hidden; }
+
+void bert_predict(sbv2_model* mm, const int64_t* ids, const int64_t* mask, int batch, int64_t S, float* out) {
+  auto* Mp = static_cast<BertModel*>(mm);
+  BertModel& M = *Mp;
+  SBV2_REQUIRE(batch > 0 && S > 0, "empty input");
+  SBV2_REQUIRE(S <= M.max_rel + 1, "sequence longer than 512 tokens is not supported");
+  M.bind_device();
+  const int H = M.hidden;
+  // right-padded masks only: 1..1 0..0
+  std::vector<int> len(batch), start(batch);
+  int64_t n = 0;
+  int max_len = 0;
+  for (int b = 0; b < batch; ++b) {
+    int l = 0;
+    while (l < S && mask[b * S + l] != 0) ++l;
+    for (int64_t t = l; t < S; ++t)
+      if (mask[b * S + t] != 0) fail(SBV2_ERR_UNSUPPORTED, "attention_mask must be a prefix of ones (right padding)");
+    len[b] = l;
+    start[b] = int(n);
+    n += l;
+    max_len = std::max(max_len, l);
+  }
+  const size_t out_elems = size_t(batch) * S * H;
+  if (n == 0) {
+    memset(out, 0, out_elems * 4);
+    return;
+  }
+  LaunchCtx ctx = M.ctx();
+  // ids of the valid tokens, packed
+  M.pin_io.ensure(std::max(size_t(n) * 4, out_elems * 4));
+  int* hid = M.pin_io.as<int>();
+  for (int b = 0; b < batch; ++b)
+    for (int t = 0; t < len[b]; ++t) {
+      int64_t id = ids[b * S + t];
+      SBV2_REQUIRE(id >= 0 && id < M.vocab, "token id out of range");
+      hid[start[b] + t] = int(id);
+    }
+  M.ids.ensure(size_t(n) * 4);
+  CUDA_CHECK(cudaMemcpyAsync(M.ids.p, hid, size_t(n) * 4, cudaMemcpyHostToDevice, M.stream));
+  std::vector<int> muls(1, 1);
+  // utterances with zero tokens still need a segment: build_geoms handles len 0
+  BatchGeom bg = build_geoms(&M, M.meta, M.pin_meta, start, len, muls);
+  const Geom& G = bg.g[0];
+  PlanarSegs ps;
+  ps.start = bg.d_ystart;
+  ps.pstart = G.d_pstart;
+  ps.len = G.d_len;
+  ps.n = batch;
+  ps.max_len = max_len;
+  ps.plane_stride = G.rows_tot * 8;
+  const size_t R = size_t(G.rows_tot);
+  M.h.ensure(size_t(n) * H * 4);
+  M.embp.ensure(R * H * 2);
+  M.hp.ensure(R * H * 2);
+  M.qkvp.ensure(R * 3 * H * 2);
+  M.ctxp.ensure(R * H * 2);
+  M.f1p.ensure(R * M.inter * 2);
+  M.y32.ensure(R * H * 4);
+  M.outd.ensure(out_elems * 4);
+  float* h = M.h.as<float>();
+  __half* embp = M.embp.as<__half>();
+  __half* hp = M.hp.as<__half>();
+  __half* qkvp = M.qkvp.as<__half>();
+  __half* ctxp = M.ctxp.as<__half>();
+  __half* f1p = M.f1p.as<__half>();
+  float* y32 = M.y32.as<float>();
+  if (M.has_conv) launch_zero_gaps(ctx, embp, H, G, batch);
+  launch_embed_rows(ctx, h, M.word_emb, M.ids.as<int>(), H, M.vocab, n);
+  launch_ln_planar_wide(ctx, h, embp, nullptr, nullptr, M.emb_g, M.emb_b, M.eps, H, ps);
+  auto umma = [&](const ConvLayer& L, const __half* in, __half* o, float* acc32, int act) {
+    ConvCall c;
+    c.in = in;
+    c.out = o;
+    c.accum = acc32;
+    c.accum_mode = acc32 ? UACC_SET : UACC_NONE;
+    c.act_out = act;
+    c.act_on_accum = acc32 != nullptr && act != ACT_NONE;
+    launch_umma(ctx, L, G, G, c, batch);
+  };
+  for (int l = 0; l < M.n_run; ++l) {
+    const BertLayer& B = M.layers[l];
+    const __half* in = l == 0 ? embp : hp;
+    umma(B.qkv, in, qkvp, nullptr, ACT_NONE);
+    launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+    umma(B.o, ctxp, nullptr, y32, ACT_NONE);
+    launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln1_g, B.ln1_b, M.eps, H, ps);
+    umma(B.f1, hp, f1p, nullptr, ACT_GELU);
+    umma(B.f2, f1p, nullptr, y32, ACT_NONE);
+    launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln2_g, B.ln2_b, M.eps, H, ps);
+    if (l == 0 && M.has_conv) {
+      // ConvLayer: LN(layer0_out + gelu(conv(embeddings)))
+      umma(M.conv, embp, nullptr, y32, ACT_GELU);
+      launch_ln_planar_wide(ctx, h, hp, nullptr, y32, M.conv_g, M.conv_b, M.eps, H, ps);
+    }
+  }
+  launch_scatter_rows(ctx, M.outd.as<float>(), h, H, int(S), ps);
+  M.debug["bert_h"] = DebugView{h, n, H, 4};
+  float* ho = M.pin_io.as<float>();
+  CUDA_CHECK(cudaMemcpyAsync(ho, M.outd.p, out_elems * 4, cudaMemcpyDeviceToHost, M.stream));
+  CUDA_CHECK(cudaStreamSynchronize(M.stream));
+  memcpy(out, ho, out_elems * 4);
+}
+
 }  // namespace sbv2

@@ -140,3 +140,20 @@ void launch_rel_attention_planar(const LaunchCtx& ctx, __half* ctx_out, const __
 // z[row, C/2:] -= m32 (planar fp32, C/2 channels)
 void launch_coupling_sub_planar(const LaunchCtx& ctx, float* z, const float* m32, int C, const PlanarSegs& s);
 }  // namespace sbv2
+
+// ---- DeBERTa glue (bert_kernels.cu) ----------------------------------------------------------------
+namespace sbv2 {
+// h = LN(h + y32) * gamma + beta for any C <= 1024 (multiple of 256 or <= 256); y32 planar fp32 or null;
+// also writes the planar fp16 copy hp (and hp2 if not null).
+void launch_ln_planar_wide(const LaunchCtx& ctx, float* h, __half* hp, __half* hp2, const float* y32, const float* gamma,
+                           const float* beta, float eps, int C, const PlanarSegs& s);
+// h[row, :] = table[ids[row], :]
+void launch_embed_rows(const LaunchCtx& ctx, float* h, const float* table, const int* ids, int C, int n_vocab, int64_t rows);
+// DeBERTa-v2 disentangled attention (c2p + p2c, shared keys) on planar fp16 q|k|v -> planar fp16 ctx.
+// pos_k/pos_q: fp32 [2*span, heads*64] projections of the normalised relative embeddings;
+// bucket_idx: int [2*max_rel+1] = clamp(bucket(delta) + span, 0, 2*span-1) for delta = -max_rel..max_rel.
+void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k, const float* pos_q,
+                              const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
+// out[b, t, :] = h[start[b] + t, :] for t < len[b], zeros elsewhere (out: [n, S, C] fp32)
+void launch_scatter_rows(const LaunchCtx& ctx, float* out, const float* h, int C, int S, const PlanarSegs& s);
+}  // namespace sbv2

@@ -17,7 +17,7 @@
 //   warp 0   : producer — bulk copies of activation chunks (ring of A slots) and of the packed
 //              weights (ring of B stages), completion on mbarriers
 //   warp 1   : TMEM alloc + single-thread tcgen05.mma issue, MT accumulators of 128 x NB fp32
-//   warps 2-9: epilogue — tcgen05.ld, bias, residual, MRF accumulation, activation, fp16 store
+//   warps 2-17: epilogue — tcgen05.ld, bias, residual, MRF accumulation, activation, fp16 store
 // Two CTAs fit on an SM for every decoder shape (<= 113 KB smem, <= 256 TMEM columns), so one CTA's
 // epilogue overlaps the other's MMA phase.
 #include <cuda_fp16.h>
@@ -39,8 +39,8 @@ constexpr int MAX_ASLOTS = 8;
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_TWO_CTAS = 113 * 1024;
-constexpr int NUM_THREADS = 320;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct UmmaConvArgs {
   const __half* in;
@@ -62,10 +62,12 @@ struct UmmaConvArgs {
   int halo_lo, halo_hi;
   int out_mul, out_off;
   int act_out;
-  int has_res, accum_mode;
+  float act_slope;             // max(v, slope*v): 1 none, 0 relu, 0.1 / 0.01 leaky relu
+  int has_res, accum_mode, act_on_accum;
   float accum_div;
   int tmem_cols;
   unsigned idesc;
+  long long* trace;  // debug: [grid][64 items][8 events] clock64 stamps, or null
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -120,6 +122,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
+
 // SWIZZLE_NONE, K-major shared-memory matrix descriptor (sm_100 "version 1")
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -131,14 +147,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == ACT_LRELU) return v > 0.f ? v : v * 0.1f;
-  if (act == ACT_LRELU01) return v > 0.f ? v : v * 0.01f;
-  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_LRELU) return fmaxf(v, v * 0.1f);
+  if (act == ACT_LRELU01) return fmaxf(v, v * 0.01f);
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
   return v;
 }
 
-// Epilogue of NCH (16 or 32) accumulator columns of one row.
-template <int NCH, bool ACC>
+// Epilogue of NCH (16 or 32) accumulator columns of one row.  Compile-time variants keep the
+// per-element code branch-free: activation is max(v, slope*v) (slope 1 = none, 0 = relu, 0.1 / 0.01 =
+// leaky relu); GELU (DeBERTa FFN only) is the one runtime branch, taken per plane.
+template <int NCH, bool ACC, bool RES>
 __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t taddr, bool valid, long long orow, int co0_global,
                                               const float* bias) {
   constexpr int NPL = NCH / 8;
@@ -146,27 +165,28 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
 #pragma unroll
   for (int q = 0; q < NCH / 16; ++q) tc_ld16(taddr + 16 * q, v + 16 * q);
   // issue the global loads this item needs while the TMEM load is in flight
-  uint4 r[NPL];
+  uint4 r[RES ? NPL : 1];
   float4 s[ACC ? 2 * NPL : 1];
-  long long eoff[NPL];
+  const long long eoff0 = ((long long)co0_global >> 3) * p.out_plane_stride + orow * 8;
 #pragma unroll
   for (int pl = 0; pl < NPL; ++pl) {
-    const long long plane = (long long)(co0_global + 8 * pl) >> 3;
-    eoff[pl] = plane * p.out_plane_stride + orow * 8;
-    if (valid && p.has_res) r[pl] = *reinterpret_cast<const uint4*>(p.residual + eoff[pl]);
+    const long long eoff = eoff0 + pl * p.out_plane_stride;
+    if (RES && valid) r[pl] = *reinterpret_cast<const uint4*>(p.residual + eoff);
     if (ACC && valid && p.accum_mode >= UACC_ADD) {
-      const float4* sp = reinterpret_cast<const float4*>(p.accum + eoff[pl]);
+      const float4* sp = reinterpret_cast<const float4*>(p.accum + eoff);
       s[2 * pl] = sp[0];
       s[2 * pl + 1] = sp[1];
     }
   }
   tc_wait_ld();
   if (!valid) return;
+  const float slope = p.act_slope;
+  const bool gelu = p.act_out == ACT_GELU;
 #pragma unroll
   for (int pl = 0; pl < NPL; ++pl) {
+    const long long eoff = eoff0 + pl * p.out_plane_stride;
     float f[8];
     const int co = 8 * pl;  // offset within this item
-#pragma unroll
     {
       const float4 b0 = *reinterpret_cast<const float4*>(bias + co), b1 = *reinterpret_cast<const float4*>(bias + co + 4);
       f[0] = __uint_as_float(v[co + 0]) + b0.x; f[1] = __uint_as_float(v[co + 1]) + b0.y;
@@ -174,36 +194,52 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
       f[4] = __uint_as_float(v[co + 4]) + b1.x; f[5] = __uint_as_float(v[co + 5]) + b1.y;
       f[6] = __uint_as_float(v[co + 6]) + b1.z; f[7] = __uint_as_float(v[co + 7]) + b1.w;
     }
-    if (p.has_res) {
+    if (RES) {
       const __half2* rh = reinterpret_cast<const __half2*>(&r[pl]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float2 y = __half22float2(rh[e]);
-        f[2 * e] += y.x >= 0.f ? y.x : y.x * 10.f;
-        f[2 * e + 1] += y.y >= 0.f ? y.y : y.y * 10.f;
+        const float2 y = __half22float2(rh[e]);
+        f[2 * e] += fminf(y.x, y.x * 10.f);  // inverse of lrelu(0.1): x = y >= 0 ? y : 10 y
+        f[2 * e + 1] += fminf(y.y, y.y * 10.f);
       }
     }
-    if (ACC && p.accum_mode != UACC_NONE) {
-      float4* sp = reinterpret_cast<float4*>(p.accum + eoff[pl]);
+    if (ACC) {
+      if (p.act_on_accum) {
+        if (gelu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752440f));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], f[e] * slope);
+        }
+      }
+      float4* sp = reinterpret_cast<float4*>(p.accum + eoff);
       if (p.accum_mode >= UACC_ADD) {
-        const float4 s0 = s[ACC ? 2 * pl : 0], s1 = s[ACC ? 2 * pl + 1 : 0];
+        const float4 s0 = s[2 * pl], s1 = s[2 * pl + 1];
         f[0] += s0.x; f[1] += s0.y; f[2] += s0.z; f[3] += s0.w;
         f[4] += s1.x; f[5] += s1.y; f[6] += s1.z; f[7] += s1.w;
       }
       if (p.accum_mode != UACC_FINAL) {
         sp[0] = make_float4(f[0], f[1], f[2], f[3]);
         sp[1] = make_float4(f[4], f[5], f[6], f[7]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = f[e] / p.accum_div;
+        continue;
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] / p.accum_div;
     }
-    if (p.out && (p.accum_mode == UACC_NONE || p.accum_mode == UACC_FINAL)) {
+    if (p.out) {
+      if (gelu && !(ACC && p.act_on_accum)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752440f));
+      } else if (!(ACC && p.act_on_accum)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], f[e] * slope);
+      }
       uint4 o;
       __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(act_apply(f[2 * e], p.act_out), act_apply(f[2 * e + 1], p.act_out));
-      *reinterpret_cast<uint4*>(p.out + eoff[pl]) = o;
+      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+      *reinterpret_cast<uint4*>(p.out + eoff) = o;
     }
   }
 }
@@ -216,6 +252,11 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
 struct TileInfo {
   int b, t0, len, nblk;
 };
+#define TRACE(ev, itv)                                                                         \
+  do {                                                                                         \
+    if (p.trace && (itv) < 64) p.trace[((size_t)blockIdx.x * 64 + (itv)) * 8 + (ev)] = clock64(); \
+  } while (0)
+
 __device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item) {
   TileInfo ti;
   const int tile = item / p.n_nblk;
@@ -234,7 +275,9 @@ __device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item)
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform so that role branches are uniform and the MMA
+  // descriptors stay in uniform registers (UTCHMMA takes UR operands; R2UR per MMA is slow)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int TM = 128 * p.mt;
   const int RA = TM + p.halo_lo + p.halo_hi;
   const int planes_per_chunk = p.kc / 8;
@@ -281,8 +324,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       // ---------------- producer ----------------
       uint32_t a_it = 0, b_it = 0;  // running ring counters
       bool first = true;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, first = false) {
+      uint32_t pit = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, first = false, ++pit) {
         const TileInfo ti = locate_item(p, item);
+        TRACE(0, pit);
         const __half* wbase = p.w + (size_t)ti.nblk * p.total_steps * (step_bytes / 2);
         const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
         auto load_a_chunk = [&](int kc) {
@@ -315,91 +360,130 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           const int last_step = (kc + 1) * p.taps - 1;  // last step that uses chunk kc
           while (load_w && next_b < p.nloads && next_b * p.sps <= last_step) load_b(next_b++);
         }
+        TRACE(1, pit);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t a_lbo = (uint32_t)RA * 16, b_lbo = (uint32_t)p.nb * 16;
+    {
+      // ---------------- MMA issuer (whole warp runs the control flow, one elected lane issues) ----------------
+      // Descriptors are built once; per MMA only the 14-bit start-address field advances (the issuing
+      // thread's instruction latency, not the tensor pipe, was the bottleneck with per-MMA rebuilds).
       const int k16_per_chunk = p.kc / 16;
-      uint32_t a_it = 0, b_it = 0, it = 0;
+      const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
+      const uint64_t a_desc0 = desc_hi | ((uint64_t)((uint32_t)RA & 0x3FFF) << 16);    // LBO = RA*16 B
+      const uint64_t b_desc0 = desc_hi | ((uint64_t)((uint32_t)p.nb & 0x3FFF) << 16);  // LBO = NB*16 B
+      const uint32_t a_kstep = 2u * (uint32_t)RA, b_kstep = 2u * (uint32_t)p.nb;       // two planes per K=16 step (16-B units)
+      uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0, it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
         tc_fence_after();
+        if (lane == 0) TRACE(2, it);
         const uint32_t tmem_acc = tmem_base + buf * acc_cols;
-        int step = 0;
-        for (int kc = 0; kc < p.nkc; ++kc, ++a_it) {
-          const uint32_t slot = a_it % p.a_slots;
-          mbar_wait(bar_af + 8 * slot, (a_it / p.a_slots) & 1);
-          const uint32_t a_slot = sA + slot_bytes * slot;
+        int step = 0, si = 0;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          mbar_wait(bar_af + 8 * a_slot_i, a_par);
+          if (kc == 0 && lane == 0) TRACE(3, it);
+          const uint64_t a_chunk = a_desc0 + ((sA + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
           for (int tap = 0; tap < p.taps; ++tap, ++step) {
-            const int load = step / p.sps, si = step - load * p.sps;
-            uint32_t st;
+            uint32_t b_addr;
             if (p.b_resident) {
-              st = 0;
-              if (it == 0 && si == 0 && load == 0) mbar_wait(bar_bf, 0);
+              if (it == 0 && step == 0) mbar_wait(bar_bf, 0);
+              b_addr = sB + step_bytes * step;
             } else {
-              st = (b_it + load) % p.nstages;
-              if (si == 0) mbar_wait(bar_bf + 8 * st, ((b_it + load) / p.nstages) & 1);
+              if (si == 0) mbar_wait(bar_bf + 8 * b_st, b_par);
+              b_addr = sB + stage_bytes * b_st + step_bytes * si;
             }
             tc_fence_after();
-            const int row_off = p.halo_lo + p.tap_shift[tap];
-            const uint32_t b_stage = p.b_resident ? sB + step_bytes * step : sB + stage_bytes * st + step_bytes * si;
-            for (int a = 0; a < p.mt; ++a) {
-              for (int k = 0; k < k16_per_chunk; ++k) {
-                const uint64_t ad = make_desc(a_slot + (uint32_t)(2 * k) * RA * 16 + (uint32_t)(a * 128 + row_off) * 16, a_lbo, 128u);
-                const uint64_t bd = make_desc(b_stage + (uint32_t)(2 * k) * p.nb * 16, b_lbo, 128u);
-                tc_mma_f16(tmem_acc + (uint32_t)(a * p.nb), ad, bd, p.idesc, (step > 0 || k > 0) ? 1u : 0u);
+            const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[tap];
+            const uint64_t b_d = b_desc0 + (b_addr >> 4);
+            const uint32_t accf = step > 0 ? 1u : 0u;
+            if (elect_one_sync()) {
+              for (int a = 0; a < p.mt; ++a) {
+                const uint64_t ad = a_tap + (uint32_t)(a * 128);
+                const uint32_t tacc = tmem_acc + (uint32_t)(a * p.nb);
+                tc_mma_f16(tacc, ad, b_d, p.idesc, accf);
+                for (int k = 1; k < k16_per_chunk; ++k) tc_mma_f16(tacc, ad + k * a_kstep, b_d + k * b_kstep, p.idesc, 1u);
               }
             }
-            if (!p.b_resident && (si == p.sps - 1 || step == p.total_steps - 1)) tc_commit(bar_be + 8 * st);
+            __syncwarp();
+            if (!p.b_resident) {
+              ++si;
+              if (si == p.sps || step == p.total_steps - 1) {
+                if (elect_one_sync()) tc_commit(bar_be + 8 * b_st);
+                __syncwarp();
+                si = 0;
+                if (++b_st == (uint32_t)p.nstages) {
+                  b_st = 0;
+                  b_par ^= 1;
+                }
+              }
+            }
           }
-          tc_commit(bar_ae + 8 * slot);
+          if (elect_one_sync()) tc_commit(bar_ae + 8 * a_slot_i);
+          __syncwarp();
+          if (++a_slot_i == (uint32_t)p.a_slots) {
+            a_slot_i = 0;
+            a_par ^= 1;
+          }
         }
-        if (!p.b_resident) b_it += p.nloads;
-        tc_commit(bar_accf + 8 * buf);
+        if (elect_one_sync()) tc_commit(bar_accf + 8 * buf);
+        __syncwarp();
+        if (lane == 0) TRACE(4, it);
       }
     }
   } else {
-    // ---------------- epilogue (8 warps) ----------------
+    // ---------------- epilogue warps ----------------
     const int wq = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // two warps per quarter split the work items
+    const int part = (warp - 2) >> 2;  // NUM_EPI_WARPS/4 warps per quarter split the work items
     const int etid = threadIdx.x - 64;
     const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE;
     const int nch = wide ? 32 : 16;
     const int items_per_acc = p.nb / nch;
     const int n_sub = p.mt * items_per_acc;
+    const bool bias_per_item = p.n_nblk > 1 || p.bias_utt != nullptr;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
       const TileInfo ti = locate_item(p, item);
-      float* bias = bias_s + buf * p.nb;
-      // bias of this item (the set used two items ago has been fully consumed: its acc_empty arrivals
-      // happen after the last read)
-      for (int i = etid; i < p.nb; i += NUM_EPI_WARPS * 32) {
-        float v = p.bias[(size_t)ti.nblk * p.nb + i];
-        if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.n_nblk * p.nb + (size_t)ti.nblk * p.nb + i];
-        bias[i] = v;
+      float* bias = bias_s + (bias_per_item ? buf * p.nb : 0);
+      if (bias_per_item || it == 0) {
+        // (per item: the set used two items ago has been fully consumed — its acc_empty arrivals
+        // happen after the last read)
+        for (int i = etid; i < p.nb; i += NUM_EPI_WARPS * 32) {
+          float v = p.bias[(size_t)ti.nblk * p.nb + i];
+          if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.n_nblk * p.nb + (size_t)ti.nblk * p.nb + i];
+          bias[i] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");
       mbar_wait(bar_accf + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) TRACE(5, it);
       const uint32_t tmem_acc = tmem_base + buf * acc_cols;
-      for (int sub = half; sub < n_sub; sub += 2) {
+      for (int sub = part; sub < n_sub; sub += NUM_EPI_WARPS / 4) {
         const int a = sub / items_per_acc;
         const int c0 = (sub - a * items_per_acc) * nch;
         const int t = ti.t0 + a * 128 + wq * 32 + lane;
         const bool valid = t < ti.len;
         const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off;
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
-        if (wide) epilogue_item<32, false>(p, taddr, valid, orow, ti.nblk * p.nb + c0, bias + c0);
-        else if (p.accum_mode == UACC_NONE) epilogue_item<16, false>(p, taddr, valid, orow, ti.nblk * p.nb + c0, bias + c0);
-        else epilogue_item<16, true>(p, taddr, valid, orow, ti.nblk * p.nb + c0, bias + c0);
+        const int cg = ti.nblk * p.nb + c0;
+        if (p.accum_mode != UACC_NONE) {
+          if (p.has_res) epilogue_item<16, true, true>(p, taddr, valid, orow, cg, bias + c0);
+          else epilogue_item<16, true, false>(p, taddr, valid, orow, cg, bias + c0);
+        } else if (wide) {
+          if (p.has_res) epilogue_item<32, false, true>(p, taddr, valid, orow, cg, bias + c0);
+          else epilogue_item<32, false, false>(p, taddr, valid, orow, cg, bias + c0);
+        } else {
+          if (p.has_res) epilogue_item<16, false, true>(p, taddr, valid, orow, cg, bias + c0);
+          else epilogue_item<16, false, false>(p, taddr, valid, orow, cg, bias + c0);
+        }
       }
       // release the accumulator set
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 64) TRACE(6, it);
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * buf) : "memory");
     }
   }
@@ -510,7 +594,8 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
   int mt = 1;
   while (mt * 2 <= std::min(mt_pref, 256 / L.nb)) mt *= 2;
   const int ppc = L.kc / 8;
-  const size_t budget = size_t(SMEM_LIMIT) - 2048;
+  const size_t kMisc = 4096;  // barriers (256 B) + two bias sets
+  const size_t budget = size_t(SMEM_LIMIT) - kMisc;
   bool placed = false;
   for (; mt >= 1 && !placed; mt >>= 1) {
     const int ra = 128 * mt + L.halo_lo + L.halo_hi;
@@ -525,7 +610,7 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
       L.mt = mt;
       L.a_slots = std::min(2 * L.nkc, MAX_ASLOTS);
       while (L.a_slots < MAX_ASLOTS && w_bytes + slot * (L.a_slots + 1) <= budget && L.a_slots < 3 * L.nkc) ++L.a_slots;
-      L.smem = ((slot * L.a_slots + 127) & ~size_t(127)) + w_bytes + 2048;
+      L.smem = ((slot * L.a_slots + 127) & ~size_t(127)) + w_bytes + kMisc;
       placed = true;
       break;
     }
@@ -536,8 +621,8 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
     const size_t stage_bytes = step_bytes * L.sps;
     for (int ns = std::min(MAX_STAGES, std::max(2, L.nloads)); ns >= 2 && !placed; --ns) {
       for (int slots = MAX_ASLOTS; slots >= min_slots && !placed; --slots) {
-        size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + 2048;
-        if (sm <= budget + 2048) {
+        size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + kMisc;
+        if (sm <= size_t(SMEM_LIMIT)) {
           L.mt = mt;
           L.a_slots = slots;
           L.nstages = ns;
@@ -601,6 +686,8 @@ ConvLayer make_up_phase_layer(sbv2_model* owner, const HostConv& c, int u, int r
                     [=](int co, int ci, int tap) { return w[(size_t(ci) * cout + co) * k + rr + u * tap]; }, mt_pref);
 }
 
+long long* g_trace = nullptr;  // debug hook, see sbv2_debug_conv_trace
+
 void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt) {
   set_smem_attr();
   UmmaConvArgs a;
@@ -638,11 +725,14 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.out_mul = c.out_mul;
   a.out_off = c.out_off;
   a.act_out = c.act_out;
+  a.act_slope = c.act_out == ACT_LRELU ? 0.1f : (c.act_out == ACT_LRELU01 ? 0.01f : (c.act_out == ACT_RELU ? 0.f : 1.f));
   a.has_res = c.residual ? 1 : 0;
   a.accum_mode = c.accum_mode;
+  a.act_on_accum = c.act_on_accum ? 1 : 0;
   a.accum_div = c.accum_div;
   a.tmem_cols = L.tmem_cols;
   a.idesc = L.idesc;
+  a.trace = g_trace;
   if (gi.n_tiles[slot] <= 0) return;
   a.n_items = gi.n_tiles[slot] * L.n_nblk;
   static int num_sms = 0;

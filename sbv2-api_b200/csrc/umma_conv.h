@@ -79,7 +79,8 @@ struct ConvCall {
   float* accum = nullptr;         // planar fp32 (geometry of out)
   int accum_mode = UACC_NONE;
   float accum_div = 1.f;
-  int act_out = ACT_NONE;         // ACT_NONE / ACT_RELU / ACT_LRELU / ACT_LRELU01
+  int act_out = ACT_NONE;         // ACT_NONE / ACT_RELU / ACT_LRELU / ACT_LRELU01 / ACT_GELU
+  bool act_on_accum = false;      // apply act_out before the fp32 accumulate/store instead of on the fp16 output
   const float* bias_utt = nullptr;
   int out_mul = 1, out_off = 0;
 };

@@ -317,3 +317,74 @@ extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const
     CUDA_CHECK(cudaStreamSynchronize(owner.stream));
   });
 }
+
+// ---- test hook: per-role clock64 trace of one conv launch (performance debugging) ----------------------------
+namespace sbv2 {
+extern long long* g_trace;
+}
+extern "C" int sbv2_debug_conv_trace(int64_t T, int cin, int cout, int k, int dil, int mt_pref, int with_residual, int accum_mode,
+                                     long long* out_trace /*[n_blocks*64*8]*/, int n_blocks, float* out_ms, int* out_cfg /*[8]*/) {
+  using namespace sbv2;
+  return guarded([&] {
+    sbv2_model owner;
+    owner.device = 0;
+    CUDA_CHECK(cudaSetDevice(0));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&owner.stream, cudaStreamNonBlocking));
+    LaunchCtx ctx = owner.ctx();
+    HostConv hc;
+    hc.d0 = cout;
+    hc.d1 = cin;
+    hc.k = k;
+    hc.w.assign(size_t(cout) * cin * k, 0.01f);
+    hc.b.assign(cout, 0.1f);
+    ConvLayer L = make_conv1d_layer(&owner, hc, dil, mt_pref);
+    if (out_cfg) {
+      int cfg[8] = {L.mt, L.nb, L.a_slots, L.nstages, L.sps, L.b_resident, int(L.smem), L.nkc};
+      memcpy(out_cfg, cfg, sizeof(cfg));
+    }
+    DBuf meta, xin, xout, acc, tr;
+    PinnedBuf pin;
+    for (DBuf* b : {&meta, &xin, &xout, &acc, &tr}) b->stream = owner.stream;
+    std::vector<int> ystart{0}, ylen{int(T)}, muls{1};
+    BatchGeom bg = build_geoms(&owner, meta, pin, ystart, ylen, muls);
+    const Geom& G = bg.g[0];
+    xin.ensure(size_t(G.rows_tot) * cin * 2);
+    xout.ensure(size_t(G.rows_tot) * cout * 2);
+    acc.ensure(size_t(G.rows_tot) * cout * 4);
+    CUDA_CHECK(cudaMemsetAsync(xin.p, 0, size_t(G.rows_tot) * cin * 2, owner.stream));
+    CUDA_CHECK(cudaMemsetAsync(xout.p, 0, size_t(G.rows_tot) * cout * 2, owner.stream));
+    CUDA_CHECK(cudaMemsetAsync(acc.p, 0, size_t(G.rows_tot) * cout * 4, owner.stream));
+    const size_t tr_elems = size_t(148) * 64 * 8;
+    tr.ensure(tr_elems * 8);
+    CUDA_CHECK(cudaMemsetAsync(tr.p, 0, tr_elems * 8, owner.stream));
+    ConvCall c;
+    c.in = xin.as<__half>();
+    c.out = xout.as<__half>();
+    c.act_out = ACT_LRELU;
+    if (with_residual) c.residual = xin.as<__half>();
+    if (accum_mode) {
+      c.accum = acc.as<float>();
+      c.accum_mode = accum_mode;
+      c.accum_div = 3.f;
+      if (accum_mode != UACC_FINAL) c.out = nullptr;
+    }
+    for (int i = 0; i < 2; ++i) launch_umma(ctx, L, G, G, c, 1);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, owner.stream));
+    for (int i = 0; i < 5; ++i) launch_umma(ctx, L, G, G, c, 1);
+    CUDA_CHECK(cudaEventRecord(e1, owner.stream));
+    g_trace = tr.as<long long>();
+    launch_umma(ctx, L, G, G, c, 1);
+    g_trace = nullptr;
+    CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (out_ms) *out_ms = ms / 5.f;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (out_trace && n_blocks > 0)
+      CUDA_CHECK(cudaMemcpy(out_trace, tr.p, size_t(std::min(n_blocks, 148)) * 64 * 8 * 8, cudaMemcpyDeviceToHost));
+  });
+}

@@ -1,0 +1,100 @@
+// Micro-benchmark (debug hook): issue rate of tcgen05.mma.cta_group::1.kind::f16 M=128 for
+// different N and shared-memory layouts, no loads — isolates the tensor-pipe / smem-operand cost
+// from the rest of the conv kernel.
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int layout, int shift_rows, int iters, int nacc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t sA = smem_u32(smem), sB = sA + 96 * 1024;
+    const uint32_t idesc = (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+    uint64_t ad, bd;
+    const int RA = 306;
+    if (layout == 0) {  // no swizzle, plane-major: LBO = RA*16, SBO = 128
+      const uint64_t hi = (uint64_t)(0x4000u | 8u) << 32;
+      ad = hi | ((uint64_t)RA << 16) | ((sA >> 4) + shift_rows);
+      bd = hi | ((uint64_t)n << 16) | (sB >> 4);
+    } else {  // 128B swizzle, K-major: SBO = 1024, layout type 2
+      const uint64_t hi = ((uint64_t)(0x4000u | (1024u >> 4)) << 32) | ((uint64_t)2 << 61);
+      ad = hi | ((sA >> 4) + shift_rows * 8);  // shift by rows*128B
+      bd = hi | (sB >> 4);
+    }
+    // descriptors for 4 K-steps precomputed; the loop body is 8 back-to-back MMAs with no address math
+    uint64_t a4[4], b4[4];
+    for (int q = 0; q < 4; ++q) {
+      a4[q] = ad + (layout == 0 ? (uint64_t)(q * 2 * RA) : (uint64_t)(q * 2));
+      b4[q] = bd + (layout == 0 ? (uint64_t)(q * 2 * n) : (uint64_t)(q * 2));
+    }
+    const uint32_t acc0 = tmem, acc1 = tmem + (nacc > 1 ? n : 0);
+#define MMA(ACC, A, B, EN)                                                                                          \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(ACC), \
+               "l"(A), "l"(B), "r"(idesc), "r"(EN)                                                                   \
+               : "memory")
+    long long t0 = clock64();
+    MMA(acc0, a4[0], b4[0], 0u);
+    MMA(acc1, a4[0], b4[0], 0u);
+    for (int i = 0; i < iters; i += 8) {
+      MMA(acc0, a4[0], b4[0], 1u);
+      MMA(acc0, a4[1], b4[1], 1u);
+      MMA(acc0, a4[2], b4[2], 1u);
+      MMA(acc0, a4[3], b4[3], 1u);
+      MMA(acc1, a4[0], b4[0], 1u);
+      MMA(acc1, a4[1], b4[1], 1u);
+      MMA(acc1, a4[2], b4[2], 1u);
+      MMA(acc1, a4[3], b4[3], 1u);
+    }
+    long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile(
+        "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n" ::"r"(
+            smem_u32(&bar))
+        : "memory");
+    long long t2 = clock64();
+    if (blockIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace
+
+extern "C" int sbv2_debug_mma_rate(int n, int layout, int shift_rows, int iters, int nacc, int blocks, long long* out2) {
+  return sbv2::guarded([&] {
+    CUDA_CHECK(cudaSetDevice(0));
+    CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, 16));
+    mma_rate_kernel<<<blocks, 128, 200 * 1024>>>(n, layout, shift_rows, iters, nacc, d);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+  });
+}

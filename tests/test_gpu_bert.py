@@ -1,0 +1,95 @@
+"""GPU parity of the DeBERTa-v2 feature encoder (bert::predict, crates/sbv2_core/src/bert.rs:6-24)
+against the HF model the reference exports (oracle/deberta.py).  GEMM operands are fp16 (fp32
+accumulate, fp32 residual stream): tolerance 3e-2 max-abs on activations of magnitude ~4 and a
+relative Frobenius error below 5e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util  # noqa: F401  (sys.path)
+from oracle import deberta as od
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def S(lib_built):
+    import sbv2_b200
+    if sbv2_b200.device_count() < 1:
+        pytest.fail("GPU tests selected but no B200 is visible")
+    return sbv2_b200
+
+
+@pytest.fixture(scope="module")
+def tiny(S):
+    from sbv2_b200 import assets
+    cfg = od.tiny_config()
+    hf = od.build_model(cfg, seed=1)
+    model = S.Model(assets.deberta_onnx(od.state_dict_numpy(hf)), bert=True)
+    return cfg, hf, model
+
+
+def close(got, ref):
+    err = np.abs(got - ref).max()
+    rel = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30)
+    assert err <= 3e-2 and rel <= 5e-3, f"max-abs {err:.3e}, rel-fro {rel:.3e} (|ref| max {np.abs(ref).max():.2f})"
+
+
+def test_describe_and_live_layers(tiny):
+    cfg, hf, model = tiny
+    d = model.describe()
+    assert d["kind"] == "deberta-v2" and d["hidden_size"] == cfg.hidden_size
+    assert d["num_hidden_layers"] == cfg.num_hidden_layers and d["live_layers"] == cfg.num_hidden_layers - 2
+    assert model.hidden_size() == cfg.hidden_size
+
+
+@pytest.mark.parametrize("s", [1, 7, 64, 129, 200, 300])
+def test_predict_matches_hf(tiny, s):
+    """cfg 1 uses T_tok = 7; s > 129 exercises the log-bucket region of the relative positions."""
+    cfg, hf, model = tiny
+    g = torch.Generator().manual_seed(100 + s)
+    ids = torch.randint(3, cfg.vocab_size, (1, s), generator=g)
+    ref = od.predict(hf, ids, torch.ones_like(ids))[0].numpy()
+    got = model.predict(ids[0].numpy(), np.ones(s, np.int64))
+    assert got.shape == (s, cfg.hidden_size)
+    close(got, ref)
+
+
+def test_golden_fixture(tiny):
+    cfg, hf, model = tiny
+    g = np.load(os.path.join(GOLDEN, "deberta_tiny_s7.npz"))
+    got = model.predict(g["ids"][0], np.ones(7, np.int64))
+    close(got, g["out"])
+
+
+def test_batch_with_right_padding_equals_singles(tiny):
+    cfg, hf, model = tiny
+    g = torch.Generator().manual_seed(5)
+    S_, lens = 40, [40, 17, 1, 33]
+    ids = torch.randint(3, cfg.vocab_size, (len(lens), S_), generator=g).numpy()
+    mask = np.zeros_like(ids)
+    for b, l in enumerate(lens):
+        mask[b, :l] = 1
+    out = model.predict_batch(ids, mask)
+    assert out.shape == (len(lens), S_, cfg.hidden_size)
+    for b, l in enumerate(lens):
+        single = model.predict(ids[b, :l], np.ones(l, np.int64))
+        assert np.array_equal(out[b, :l], single)       # bit-identical to the batch-1 call
+        assert not out[b, l:].any()                     # padded positions are zeros
+        ref = od.predict(hf, torch.from_numpy(ids[b:b + 1, :l]), torch.ones(1, l, dtype=torch.long))[0].numpy()
+        close(single, ref)
+
+
+def test_error_paths(tiny, S):
+    cfg, hf, model = tiny
+    with pytest.raises(S.Sbv2Error):
+        model.predict([cfg.vocab_size + 5], [1])
+    with pytest.raises(S.Sbv2Error):
+        model.predict_batch(np.ones((1, 4), np.int64), np.array([[1, 0, 1, 1]]))  # hole in the mask
+    with pytest.raises(S.Sbv2Error):
+        model.synthesize(np.zeros((1024, 3), np.float32), [0, 1, 0], [0], [0, 6, 0], [0, 1, 0], np.zeros(256, np.float32),
+                         0.0, 1.0, 0.677, 0.8)
+    assert model.predict([5, 6, 7], [1, 1, 1]).shape == (3, cfg.hidden_size)
