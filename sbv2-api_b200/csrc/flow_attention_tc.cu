@@ -1,0 +1,391 @@
+// Window-relative multi-head attention of the transformer flow on tcgen05 tensor cores.
+//
+// One CTA = (utterance, head, 128-query tile).  Scores S = Q K^T are produced 128 keys at a time
+// into TMEM, the softmax runs on 128 threads (one query row each), probabilities go back to
+// shared memory as the fp16 A operand of O += P V, with V read as an MN-major B operand straight
+// from the planar activation layout.  The window terms are two extra tiny MMAs: Srel = Q Ek^T
+// (9 relative keys, padded to 16) before the loop and O += Prel Ev after it.
+// Softmax is exact two-pass (pass A: row max / sum; pass B: normalised probabilities), so the O
+// accumulator is never rescaled.  Replaces rel_attention_planar_kernel (fp32 CUDA cores) in the flow;
+// oracle: oracle/vits.py MultiHeadAttention.attention.
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "kernels.h"
+
+namespace sbv2 {
+namespace {
+
+constexpr int QT = 128, KT = 128, D = 96, DP = D / 8, RP = 16;  // RP: relative positions padded to 16
+constexpr uint32_t TILE_BYTES = DP * KT * 16;                   // one Q / K / V tile: 24 KB
+constexpr uint32_t P_BYTES = (KT / 8) * QT * 16;                // 32 KB
+constexpr uint32_t PREL_BYTES = (RP / 8) * QT * 16;             // 4 KB
+constexpr uint32_t REL_BYTES = DP * RP * 16;                    // 3 KB
+constexpr int TM_O = 0, TM_SREL = 96, TM_S = 128, TM_COLS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
+// no-swizzle descriptor: start (16-B units), LBO, SBO in bytes
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+constexpr uint32_t idesc_f16(int n, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// threads 0..127: softmax / epilogue (thread = query row, warp w owns TMEM lanes 32w..32w+31)
+// warp 4: control (bulk loads + MMA issue)
+__global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, const __half* qkv, const __half* rel_k_p,
+                                                                    const __half* rel_v_p, int heads, int window, PlanarSegs s) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int len = s.len[b];
+  const int q0 = blockIdx.x * QT;
+  if (q0 >= len) return;  // uniform per CTA
+  const long long pbase = s.pstart[b];
+  const int n_kt = (len + KT - 1) / KT;
+
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK0 = sQ + TILE_BYTES;             // K tiles [2]
+  const uint32_t sV0 = sK0 + 2 * TILE_BYTES;        // V tiles [2]
+  const uint32_t sP = sV0 + 2 * TILE_BYTES;         // P tile
+  const uint32_t sPrel = sP + P_BYTES;
+  const uint32_t sEk = sPrel + PREL_BYTES;
+  const uint32_t sEv = sEk + REL_BYTES;
+  const uint32_t sBar = sEv + REL_BYTES;
+  // barriers
+  const uint32_t bar_q = sBar, bar_kv = sBar + 8 /*[2]*/, bar_kvfree = sBar + 24 /*[2]*/, bar_s = sBar + 40, bar_sfree = sBar + 48,
+                 bar_p = sBar + 56, bar_pfree = sBar + 64, bar_done = sBar + 72;
+  const uint32_t tmem_slot = sBar + 80;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ));
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_kv + 8, 1);
+    mbar_init(bar_kvfree, 1);
+    mbar_init(bar_kvfree + 8, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_sfree, 128);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_pfree, 1);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero Prel (own row) before anything is accumulated into it
+  if (threadIdx.x < 128) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + (sPrel - sQ) + threadIdx.x * 16) = z;
+    *reinterpret_cast<uint4*>(smem + (sPrel - sQ) + QT * 16 + threadIdx.x * 16) = z;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  const int q_plane0 = h * DP, k_plane0 = heads * DP + h * DP, v_plane0 = 2 * heads * DP + h * DP;
+  const int n_tiles_total = 2 * n_kt;  // pass A tiles then pass B tiles
+
+  if (warp == 4) {
+    // ---------------- control warp ----------------
+    auto load_tile = [&](int i) {  // i-th tile of the (pass A, pass B) sequence
+      const int buf = i & 1;
+      const int kt = i < n_kt ? i : i - n_kt;
+      const bool with_v = i >= n_kt;
+      const long long row0 = pbase + (long long)kt * KT;
+      if (elect_one_sync()) {
+        mbar_wait(bar_kvfree + 8 * buf, ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar_kv + 8 * buf, with_v ? 2 * TILE_BYTES : TILE_BYTES);
+        for (int pl = 0; pl < DP; ++pl) {
+          bulk_g2s(sK0 + buf * TILE_BYTES + pl * KT * 16, qkv + (size_t)(k_plane0 + pl) * s.plane_stride + row0 * 8, KT * 16, bar_kv + 8 * buf);
+          if (with_v)
+            bulk_g2s(sV0 + buf * TILE_BYTES + pl * KT * 16, qkv + (size_t)(v_plane0 + pl) * s.plane_stride + row0 * 8, KT * 16,
+                     bar_kv + 8 * buf);
+        }
+      }
+      __syncwarp();
+    };
+    if (elect_one_sync()) {
+      mbar_expect_tx(bar_q, TILE_BYTES + 2 * REL_BYTES);
+      for (int pl = 0; pl < DP; ++pl)
+        bulk_g2s(sQ + pl * QT * 16, qkv + (size_t)(q_plane0 + pl) * s.plane_stride + (pbase + q0) * 8, QT * 16, bar_q);
+      bulk_g2s(sEk, rel_k_p, REL_BYTES, bar_q);
+      bulk_g2s(sEv, rel_v_p, REL_BYTES, bar_q);
+    }
+    __syncwarp();
+    load_tile(0);
+    mbar_wait(bar_q, 0);
+    tc_fence_after();
+    // K-major operands: LBO = rows*16 (next 8-channel plane), SBO = 128
+    const uint64_t dq = make_desc(sQ, QT * 16, 128);
+    const uint64_t dek = make_desc(sEk, RP * 16, 128);
+    const uint64_t dp = make_desc(sP, QT * 16, 128);
+    const uint64_t dprel = make_desc(sPrel, QT * 16, 128);
+    // MN-major B operands (V, Ev): SBO = next 8-column plane, LBO = next 8 K rows (128 B)
+    const uint64_t dev = make_desc(sEv, 128, RP * 16);
+    constexpr uint32_t ID_S = idesc_f16(KT, 0), ID_REL = idesc_f16(RP, 0), ID_O = idesc_f16(D, 1);
+    // Srel = Q Ek^T
+    if (elect_one_sync()) {
+      for (int k = 0; k < D / 16; ++k)
+        tc_mma_f16(tmem + TM_SREL, dq + (uint64_t)(k * 2 * QT), dek + (uint64_t)(k * 2 * RP), ID_REL, k > 0 ? 1u : 0u);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_tiles_total; ++i) {
+      const int buf = i & 1;
+      const bool pass_b = i >= n_kt;
+      if (i + 1 < n_tiles_total) load_tile(i + 1);
+      mbar_wait(bar_kv + 8 * buf, (i >> 1) & 1);
+      mbar_wait(bar_sfree, (i & 1) ^ 1);  // softmax threads have read the previous S
+      tc_fence_after();
+      const uint64_t dk = make_desc(sK0 + buf * TILE_BYTES, KT * 16, 128);
+      if (elect_one_sync()) {
+        for (int k = 0; k < D / 16; ++k)
+          tc_mma_f16(tmem + TM_S, dq + (uint64_t)(k * 2 * QT), dk + (uint64_t)(k * 2 * KT), ID_S, k > 0 ? 1u : 0u);
+        tc_commit(bar_s);
+        if (!pass_b) tc_commit(bar_kvfree + 8 * buf);  // pass A: K tile is free once S is done
+      }
+      __syncwarp();
+      if (pass_b) {
+        const int j = i - n_kt;
+        mbar_wait(bar_p, j & 1);  // P tile written (and visible to the async proxy)
+        tc_fence_after();
+        const uint64_t dv = make_desc(sV0 + buf * TILE_BYTES, 128, KT * 16);
+        if (elect_one_sync()) {
+          for (int k = 0; k < KT / 16; ++k)
+            tc_mma_f16(tmem + TM_O, dp + (uint64_t)(k * 2 * QT), dv + (uint64_t)(k * 16), ID_O, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(bar_pfree);
+          tc_commit(bar_kvfree + 8 * buf);
+        }
+        __syncwarp();
+      }
+    }
+    // window value term: O += Prel Ev   (Prel complete: the last bar_p wait covered it)
+    if (elect_one_sync()) {
+      tc_mma_f16(tmem + TM_O, dprel, dev, ID_O, 1u);
+      tc_commit(bar_done);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- softmax / epilogue threads ----------------
+    const int qi = q0 + (int)threadIdx.x;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c_scale = 1.4426950408889634f / sqrtf((float)D);  // log2(e) / sqrt(d)
+    // relative-key logits of this row
+    float srel[9];
+    {
+      // Srel is committed together with the first S tile (same MMA queue, in order): wait for S first
+      mbar_wait(bar_s, 0);
+      tc_fence_after();
+      uint32_t v[16];
+      tc_ld16(lane_addr + TM_SREL, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int r = 0; r < 9; ++r) srel[r] = r <= 2 * window ? __uint_as_float(v[r]) * c_scale : 0.f;
+    }
+    float m2 = -CUDART_INF_F, l = 0.f, inv_l = 0.f;
+    uint8_t* prow = smem + (sP - sQ) + threadIdx.x * 16;
+    uint8_t* prel_row = smem + (sPrel - sQ) + threadIdx.x * 16;
+    for (int i = 0; i < n_tiles_total; ++i) {
+      const bool pass_b = i >= n_kt;
+      const int kt = pass_b ? i - n_kt : i;
+      const int k0 = kt * KT;
+      if (i > 0) {
+        mbar_wait(bar_s, i & 1);
+        tc_fence_after();
+      }
+      if (pass_b && kt > 0) mbar_wait(bar_pfree, (kt - 1) & 1);  // previous P tile consumed by the MMA
+      if (i == n_kt) inv_l = 1.0f / l;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_S + c * 32, v);
+        tc_wait_ld();
+        const int kc0 = k0 + c * 32;
+        float sc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sc[e] = __uint_as_float(v[e]) * c_scale;
+        const int d0 = kc0 - qi;  // rel of element 0
+        if (d0 <= window && d0 + 31 >= -window) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int rel = d0 + e;
+#pragma unroll
+            for (int r = 0; r < 9; ++r)
+              if (rel == r - 4 && r <= 2 * window) sc[e] += srel[r + (window - 4)];
+          }
+        }
+        if (kc0 + 32 > len) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (kc0 + e >= len) sc[e] = -CUDART_INF_F;
+        }
+        if (!pass_b) {
+          float mx = sc[0];
+#pragma unroll
+          for (int e = 1; e < 32; ++e) mx = fmaxf(mx, sc[e]);
+          const float m_new = fmaxf(m2, mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sum += exp2f(sc[e] - m_new);
+          l = l * exp2f(m2 - m_new) + sum;
+          m2 = m_new;
+        } else {
+          float pv[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) pv[e] = exp2f(sc[e] - m2) * inv_l;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(pv[q * 8 + 2 * e], pv[q * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(prow + (size_t)(c * 4 + q) * QT * 16) = u;
+          }
+          if (d0 <= window && d0 + 31 >= -window) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int r = d0 + e + window;  // 0..2*window inside the band
+              if (r >= 0 && r <= 2 * window) {
+                __half hv = __float2half_rn(pv[e]);
+                *reinterpret_cast<__half*>(prel_row + (size_t)(r >> 3) * QT * 16 + (r & 7) * 2) = hv;
+              }
+            }
+          }
+        }
+      }
+      // S fully read
+      tc_fence_before();
+      mbar_arrive(bar_sfree);
+      if (pass_b) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P / Prel writes -> visible to the MMA's async proxy
+        mbar_arrive(bar_p);
+      }
+    }
+    // epilogue: O -> fp16 planar ctx
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_O + c * 32, v);
+      tc_wait_ld();
+      if (qi < len) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+          *reinterpret_cast<uint4*>(out + (size_t)(h * DP + c * 4 + q) * s.plane_stride + (pbase + qi) * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+// rel_k_p / rel_v_p: fp16 [D/8][16][8] packings of emb_rel_k / emb_rel_v ([2w+1, D], rows >= 2w+1 zero)
+void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* rel_k_p, const __half* rel_v_p,
+                              int heads, int head_dim, int window, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (head_dim != D || window != 4) fail(SBV2_ERR_UNSUPPORTED, "tensor-core attention: head_dim must be 96 and window 4");
+  const size_t smem = 5 * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(flow_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((s.max_len + QT - 1) / QT, heads, s.n);
+  flow_attention_tc_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+}  // namespace sbv2

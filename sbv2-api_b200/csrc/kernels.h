@@ -137,6 +137,9 @@ void launch_ln_planar(const LaunchCtx& ctx, float* h, __half* hp, const float* y
 // window-relative attention on planar fp16 q|k|v (3*H*D channels) -> planar fp16 ctx (H*D channels)
 void launch_rel_attention_planar(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* rel_k, const float* rel_v,
                                  int heads, int head_dim, int window, const PlanarSegs& s);
+// same on tcgen05 tensor cores (head_dim 96, window 4); rel_k_p / rel_v_p: fp16 [D/8][16][8] packings
+void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* rel_k_p, const __half* rel_v_p,
+                              int heads, int head_dim, int window, const PlanarSegs& s);
 // z[row, C/2:] -= m32 (planar fp32, C/2 channels)
 void launch_coupling_sub_planar(const LaunchCtx& ctx, float* z, const float* m32, int C, const PlanarSegs& s);
 }  // namespace sbv2

@@ -75,6 +75,8 @@ struct CouplingW {
 
 struct FlowTCLayer {
   ConvLayer qkv, o, f1, f2;
+  __half* rel_k_p = nullptr;  // fp16 [D/8][16][8] packing of emb_rel_k for the tensor-core attention
+  __half* rel_v_p = nullptr;
 };
 struct FlowTC {
   ConvLayer pre, post;
@@ -116,6 +118,8 @@ struct SynthModel : sbv2_model {
   bool use_umma = true;
   std::vector<FlowTC> flow_tc;  // tensor-core transformer flow (fp16 operands, fp32 residual stream)
   bool use_tc_flow = true;
+  bool use_tc_attn = true;
+  void* fl_qkvp_ptr = nullptr;  // last qkv buffer that was cleared (tails must be finite for the TC attention)
   std::vector<std::vector<HostConv>> flow_host;  // consumed at create: per coupling [pre, post, (qkv, o, f1, f2) x L]
   DBuf fl_x0p, fl_hp, fl_qkvp, fl_ctxp, fl_f1p, fl_y32, fl_m32, fl_meta;
   PinnedBuf fl_pin;
@@ -713,6 +717,29 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
     }
     for (DBuf* b : {&M->fl_x0p, &M->fl_hp, &M->fl_qkvp, &M->fl_ctxp, &M->fl_f1p, &M->fl_y32, &M->fl_m32, &M->fl_meta}) b->stream = M->stream;
   }
+  if (M->use_tc_flow) {
+    const char* aenv = getenv("SBV2_B200_ATTN");
+    const EncoderW& E0 = M->flow[0].enc;
+    M->use_tc_attn = !(aenv && std::string(aenv) == "simt") && E0.head_dim == 96 && E0.window == 4;
+    if (M->use_tc_attn) {
+      for (size_t i = 0; i < M->flow_tc.size(); ++i)
+        for (size_t l = 0; l < M->flow_tc[i].layers.size(); ++l) {
+          const EncLayerW& Lw = M->flow[i].enc.layers[l];
+          const int R = 2 * E0.window + 1, D = E0.head_dim;
+          std::vector<float> hk(size_t(R) * D), hv(size_t(R) * D);
+          CUDA_CHECK(cudaMemcpy(hk.data(), Lw.rel_k, hk.size() * 4, cudaMemcpyDeviceToHost));
+          CUDA_CHECK(cudaMemcpy(hv.data(), Lw.rel_v, hv.size() * 4, cudaMemcpyDeviceToHost));
+          auto pack = [&](const std::vector<float>& src) {
+            std::vector<__half> pk(size_t(D / 8) * 16 * 8, __float2half(0.f));
+            for (int r = 0; r < R; ++r)
+              for (int d = 0; d < D; ++d) pk[(size_t(d / 8) * 16 + r) * 8 + d % 8] = __float2half_rn(src[size_t(r) * D + d]);
+            return static_cast<__half*>(M->upload_bytes(pk.data(), pk.size() * 2));
+          };
+          M->flow_tc[i].layers[l].rel_k_p = pack(hk);
+          M->flow_tc[i].layers[l].rel_v_p = pack(hv);
+        }
+    }
+  }
   M->flow_host.clear();
   CUDA_CHECK(cudaStreamSynchronize(M->stream));
   return M.release();
@@ -1206,6 +1233,11 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     M.fl_x0p.ensure(size_t(G.rows_tot) * (C / 2) * 2);
     M.fl_hp.ensure(size_t(G.rows_tot) * H * 2);
     M.fl_qkvp.ensure(size_t(G.rows_tot) * 3 * H * 2);
+    if (M.fl_qkvp.p != M.fl_qkvp_ptr) {
+      // rows past an utterance's end are read (and masked) by the attention: they must hold finite values
+      CUDA_CHECK(cudaMemsetAsync(M.fl_qkvp.p, 0, M.fl_qkvp.cap, M.stream));
+      M.fl_qkvp_ptr = M.fl_qkvp.p;
+    }
     M.fl_ctxp.ensure(size_t(G.rows_tot) * H * 2);
     M.fl_f1p.ensure(size_t(G.rows_tot) * filt * 2);
     M.fl_y32.ensure(size_t(G.rows_tot) * H * 4);
@@ -1246,7 +1278,8 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
           launch_flow_mix(ctx, hf, hp16, hf, nullptr, gg, H, H, ps);
         }
         umma(Lt.qkv, hp16, qkvp, nullptr, ACT_NONE);
-        launch_rel_attention_planar(ctx, ctxp, qkvp, Lw.rel_k, Lw.rel_v, E.heads, E.head_dim, E.window, ps);
+        if (M.use_tc_attn) launch_flow_attention_tc(ctx, ctxp, qkvp, Lt.rel_k_p, Lt.rel_v_p, E.heads, E.head_dim, E.window, ps);
+        else launch_rel_attention_planar(ctx, ctxp, qkvp, Lw.rel_k, Lw.rel_v, E.heads, E.head_dim, E.window, ps);
         umma(Lt.o, ctxp, nullptr, y32, ACT_NONE);
         launch_ln_planar(ctx, hf, hp16, y32, Lw.n1.g, Lw.n1.b, 1e-5f, H, ps);
         umma(Lt.f1, hp16, f1p, nullptr, ACT_RELU);
