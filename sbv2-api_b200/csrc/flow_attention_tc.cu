@@ -21,7 +21,8 @@ constexpr uint32_t TILE_BYTES = DP * KT * 16;                   // one Q / K / V
 constexpr uint32_t P_BYTES = (KT / 8) * QT * 16;                // 32 KB
 constexpr uint32_t PREL_BYTES = (RP / 8) * QT * 16;             // 4 KB
 constexpr uint32_t REL_BYTES = DP * RP * 16;                    // 3 KB
-constexpr int TM_O = 0, TM_SREL = 96, TM_S = 128, TM_COLS = 256;
+constexpr int TM_O = 0, TM_SREL = 96, TM_S = 128 /* two sets: +0, +128 */, TM_COLS = 512;
+constexpr int NSM_WARPS = 8;  // softmax warps: two per TMEM lane quarter, each takes half of the keys of a tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -108,9 +109,9 @@ constexpr uint32_t idesc_f16(int n, int b_mn_major) {
   return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// threads 0..127: softmax / epilogue (thread = query row, warp w owns TMEM lanes 32w..32w+31)
-// warp 4: control (bulk loads + MMA issue)
-__global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, const __half* qkv, const __half* rel_k_p,
+// warps 0..7: softmax / epilogue (query row = 32*(w&3)+lane, key half = w>>2)
+// warp 8: control (bulk loads + MMA issue)
+__global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, const __half* qkv, const __half* rel_k_p,
                                                                     const __half* rel_v_p, int heads, int window, PlanarSegs s) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -130,9 +131,10 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
   const uint32_t sEv = sEk + REL_BYTES;
   const uint32_t sBar = sEv + REL_BYTES;
   // barriers
-  const uint32_t bar_q = sBar, bar_kv = sBar + 8 /*[2]*/, bar_kvfree = sBar + 24 /*[2]*/, bar_s = sBar + 40, bar_sfree = sBar + 48,
-                 bar_p = sBar + 56, bar_pfree = sBar + 64, bar_done = sBar + 72;
-  const uint32_t tmem_slot = sBar + 80;
+  const uint32_t bar_q = sBar, bar_kv = sBar + 8 /*[2]*/, bar_kvfree = sBar + 24 /*[2]*/, bar_s = sBar + 40 /*[2]*/,
+                 bar_sfree = sBar + 56 /*[2]*/, bar_p = sBar + 72, bar_pfree = sBar + 80, bar_done = sBar + 88;
+  const uint32_t tmem_slot = sBar + 96;
+  float* ml_x = reinterpret_cast<float*>(smem + (sBar - sQ) + 128);  // [2 halves][128 rows][2] (m, l) exchange
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ));
 
   if (threadIdx.x == 0) {
@@ -142,13 +144,15 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
     mbar_init(bar_kvfree, 1);
     mbar_init(bar_kvfree + 8, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_sfree, 128);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_s + 8, 1);
+    mbar_init(bar_sfree, 32 * NSM_WARPS);
+    mbar_init(bar_sfree + 8, 32 * NSM_WARPS);
+    mbar_init(bar_p, 32 * NSM_WARPS);
     mbar_init(bar_pfree, 1);
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == NSM_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
   const int q_plane0 = h * DP, k_plane0 = heads * DP + h * DP, v_plane0 = 2 * heads * DP + h * DP;
   const int n_tiles_total = 2 * n_kt;  // pass A tiles then pass B tiles
 
-  if (warp == 4) {
+  if (warp == NSM_WARPS) {
     // ---------------- control warp ----------------
     auto load_tile = [&](int i) {  // i-th tile of the (pass A, pass B) sequence
       const int buf = i & 1;
@@ -195,6 +199,7 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
     }
     __syncwarp();
     load_tile(0);
+    if (n_tiles_total > 1) load_tile(1);
     mbar_wait(bar_q, 0);
     tc_fence_after();
     // K-major operands: LBO = rows*16 (next 8-channel plane), SBO = 128
@@ -211,22 +216,25 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
         tc_mma_f16(tmem + TM_SREL, dq + (uint64_t)(k * 2 * QT), dek + (uint64_t)(k * 2 * RP), ID_REL, k > 0 ? 1u : 0u);
     }
     __syncwarp();
-    for (int i = 0; i < n_tiles_total; ++i) {
+    auto issue_s = [&](int i) {  // S(i) = Q K_i^T into accumulator set i & 1
       const int buf = i & 1;
-      const bool pass_b = i >= n_kt;
-      if (i + 1 < n_tiles_total) load_tile(i + 1);
       mbar_wait(bar_kv + 8 * buf, (i >> 1) & 1);
-      mbar_wait(bar_sfree, (i & 1) ^ 1);  // softmax threads have read the previous S
+      mbar_wait(bar_sfree + 8 * buf, ((i >> 1) & 1) ^ 1);  // softmax threads have read S(i-2)
       tc_fence_after();
       const uint64_t dk = make_desc(sK0 + buf * TILE_BYTES, KT * 16, 128);
       if (elect_one_sync()) {
         for (int k = 0; k < D / 16; ++k)
-          tc_mma_f16(tmem + TM_S, dq + (uint64_t)(k * 2 * QT), dk + (uint64_t)(k * 2 * KT), ID_S, k > 0 ? 1u : 0u);
-        tc_commit(bar_s);
-        if (!pass_b) tc_commit(bar_kvfree + 8 * buf);  // pass A: K tile is free once S is done
+          tc_mma_f16(tmem + TM_S + buf * KT, dq + (uint64_t)(k * 2 * QT), dk + (uint64_t)(k * 2 * KT), ID_S, k > 0 ? 1u : 0u);
+        tc_commit(bar_s + 8 * buf);
+        if (i < n_kt) tc_commit(bar_kvfree + 8 * buf);  // pass A: the K tile is free once S is done
       }
       __syncwarp();
-      if (pass_b) {
+    };
+    issue_s(0);
+    for (int i = 0; i < n_tiles_total; ++i) {
+      const int buf = i & 1;
+      if (i + 1 < n_tiles_total) issue_s(i + 1);  // overlaps the softmax of tile i
+      if (i >= n_kt) {
         const int j = i - n_kt;
         mbar_wait(bar_p, j & 1);  // P tile written (and visible to the async proxy)
         tc_fence_after();
@@ -239,6 +247,7 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
         }
         __syncwarp();
       }
+      if (i + 2 < n_tiles_total) load_tile(i + 2);
     }
     // window value term: O += Prel Ev   (Prel complete: the last bar_p wait covered it)
     if (elect_one_sync()) {
@@ -248,51 +257,66 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
     __syncwarp();
   } else {
     // ---------------- softmax / epilogue threads ----------------
-    const int qi = q0 + (int)threadIdx.x;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int qi = q0 + row;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const float c_scale = 1.4426950408889634f / sqrtf((float)D);  // log2(e) / sqrt(d)
     // relative-key logits of this row
     float srel[9];
     {
-      // Srel is committed together with the first S tile (same MMA queue, in order): wait for S first
+      // Srel is issued before S(0) on the same in-order MMA queue: S(0) complete implies Srel complete
       mbar_wait(bar_s, 0);
       tc_fence_after();
       uint32_t v[16];
       tc_ld16(lane_addr + TM_SREL, v);
       tc_wait_ld();
 #pragma unroll
-      for (int r = 0; r < 9; ++r) srel[r] = r <= 2 * window ? __uint_as_float(v[r]) * c_scale : 0.f;
+      for (int r = 0; r < 9; ++r) srel[r] = __uint_as_float(v[r]) * c_scale;
     }
     float m2 = -CUDART_INF_F, l = 0.f, inv_l = 0.f;
-    uint8_t* prow = smem + (sP - sQ) + threadIdx.x * 16;
-    uint8_t* prel_row = smem + (sPrel - sQ) + threadIdx.x * 16;
+    uint8_t* prow = smem + (sP - sQ) + row * 16;
+    uint8_t* prel_row = smem + (sPrel - sQ) + row * 16;
     for (int i = 0; i < n_tiles_total; ++i) {
       const bool pass_b = i >= n_kt;
       const int kt = pass_b ? i - n_kt : i;
       const int k0 = kt * KT;
+      const int buf = i & 1;
       if (i > 0) {
-        mbar_wait(bar_s, i & 1);
+        mbar_wait(bar_s + 8 * buf, (i >> 1) & 1);
         tc_fence_after();
       }
+      if (i == n_kt) {
+        // combine the two key-halves of each row: (m, l) -> final max and 1 / sum
+        ml_x[(half * QT + row) * 2] = m2;
+        ml_x[(half * QT + row) * 2 + 1] = l;
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * NSM_WARPS) : "memory");
+        const float mo = ml_x[((half ^ 1) * QT + row) * 2], lo = ml_x[((half ^ 1) * QT + row) * 2 + 1];
+        const float mf = fmaxf(m2, mo);
+        const float lf = (m2 == -CUDART_INF_F ? 0.f : l * exp2f(m2 - mf)) + (mo == -CUDART_INF_F ? 0.f : lo * exp2f(mo - mf));
+        m2 = mf;
+        inv_l = 1.0f / lf;
+      }
       if (pass_b && kt > 0) mbar_wait(bar_pfree, (kt - 1) & 1);  // previous P tile consumed by the MMA
-      if (i == n_kt) inv_l = 1.0f / l;
 #pragma unroll 1
-      for (int c = 0; c < KT / 32; ++c) {
+      for (int cc = 0; cc < KT / 64; ++cc) {
+        const int c = half * (KT / 64) + cc;
         uint32_t v[32];
-        tc_ld32(lane_addr + TM_S + c * 32, v);
+        tc_ld32(lane_addr + TM_S + buf * KT + c * 32, v);
         tc_wait_ld();
         const int kc0 = k0 + c * 32;
         float sc[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) sc[e] = __uint_as_float(v[e]) * c_scale;
         const int d0 = kc0 - qi;  // rel of element 0
-        if (d0 <= window && d0 + 31 >= -window) {
+        const bool band = d0 <= 4 && d0 + 31 >= -4;
+        if (band) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int rel = d0 + e;
 #pragma unroll
             for (int r = 0; r < 9; ++r)
-              if (rel == r - 4 && r <= 2 * window) sc[e] += srel[r + (window - 4)];
+              if (rel == r - 4) sc[e] += srel[r];
           }
         }
         if (kc0 + 32 > len) {
@@ -305,11 +329,13 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
 #pragma unroll
           for (int e = 1; e < 32; ++e) mx = fmaxf(mx, sc[e]);
           const float m_new = fmaxf(m2, mx);
-          float sum = 0.f;
+          if (m_new != -CUDART_INF_F) {
+            float sum = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) sum += exp2f(sc[e] - m_new);
-          l = l * exp2f(m2 - m_new) + sum;
-          m2 = m_new;
+            for (int e = 0; e < 32; ++e) sum += exp2f(sc[e] - m_new);
+            l = (m2 == -CUDART_INF_F ? 0.f : l * exp2f(m2 - m_new)) + sum;
+            m2 = m_new;
+          }
         } else {
           float pv[32];
 #pragma unroll
@@ -322,11 +348,11 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
             for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(pv[q * 8 + 2 * e], pv[q * 8 + 2 * e + 1]);
             *reinterpret_cast<uint4*>(prow + (size_t)(c * 4 + q) * QT * 16) = u;
           }
-          if (d0 <= window && d0 + 31 >= -window) {
+          if (band) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int r = d0 + e + window;  // 0..2*window inside the band
-              if (r >= 0 && r <= 2 * window) {
+              const int r = d0 + e + 4;  // 0..8 inside the band
+              if (r >= 0 && r <= 8) {
                 __half hv = __float2half_rn(pv[e]);
                 *reinterpret_cast<__half*>(prel_row + (size_t)(r >> 3) * QT * 16 + (r & 7) * 2) = hv;
               }
@@ -334,19 +360,19 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
           }
         }
       }
-      // S fully read
+      // this thread's part of S is read
       tc_fence_before();
-      mbar_arrive(bar_sfree);
+      mbar_arrive(bar_sfree + 8 * buf);
       if (pass_b) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P / Prel writes -> visible to the MMA's async proxy
         mbar_arrive(bar_p);
       }
     }
-    // epilogue: O -> fp16 planar ctx
+    // epilogue: O -> fp16 planar ctx (half 0: columns 0..63, half 1: 64..95)
     mbar_wait(bar_done, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = half * 2; c < (half == 0 ? 2 : D / 32); ++c) {
       uint32_t v[32];
       tc_ld32(lane_addr + TM_O + c * 32, v);
       tc_wait_ld();
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(160, 1) flow_attention_tc_kernel(__half* out, 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NSM_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
   }
 }
@@ -376,14 +402,14 @@ void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __hal
                               int heads, int head_dim, int window, const PlanarSegs& s) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != D || window != 4) fail(SBV2_ERR_UNSUPPORTED, "tensor-core attention: head_dim must be 96 and window 4");
-  const size_t smem = 5 * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 128;
+  const size_t smem = 5 * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 128 + 2 * QT * 2 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(flow_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid((s.max_len + QT - 1) / QT, heads, s.n);
-  flow_attention_tc_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s);
+  flow_attention_tc_kernel<<<grid, 32 * (NSM_WARPS + 1), smem, ctx.stream>>>(ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -14,29 +14,61 @@ thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
+// Pinned result blocks are recycled: cudaMallocHost of a 45 MB waveform buffer costs ~10 ms, which
+// would otherwise sit inside every synthesize call.
+namespace {
+struct PinnedBlock {
+  void* p;
+  size_t cap;
+};
+std::vector<PinnedBlock> g_pinned_free;
+std::unordered_map<void*, size_t> g_pinned_cap;
+size_t g_pinned_cached = 0;
+constexpr size_t kPinnedCacheLimit = size_t(1) << 30;
+}  // namespace
+
 void* alloc_out(size_t bytes, bool pinned) {
   void* p = nullptr;
   if (bytes == 0) bytes = 1;
   if (pinned) {
-    cudaError_t e = cudaMallocHost(&p, bytes);
+    const size_t want = (bytes + ((size_t(1) << 20) - 1)) & ~((size_t(1) << 20) - 1);
+    {
+      std::lock_guard<std::mutex> lk(g_out_mu);
+      size_t best = g_pinned_free.size();
+      for (size_t i = 0; i < g_pinned_free.size(); ++i)
+        if (g_pinned_free[i].cap >= want && g_pinned_free[i].cap <= 2 * want &&
+            (best == g_pinned_free.size() || g_pinned_free[i].cap < g_pinned_free[best].cap))
+          best = i;
+      if (best != g_pinned_free.size()) {
+        p = g_pinned_free[best].p;
+        g_pinned_cached -= g_pinned_free[best].cap;
+        g_pinned_free.erase(g_pinned_free.begin() + long(best));
+        g_out[p] = true;
+        return p;
+      }
+    }
+    cudaError_t e = cudaMallocHost(&p, want);
     if (e != cudaSuccess) {
       cudaGetLastError();
+      p = nullptr;
       pinned = false;
+    } else {
+      std::lock_guard<std::mutex> lk(g_out_mu);
+      g_pinned_cap[p] = want;
+      g_out[p] = true;
+      return p;
     }
   }
-  if (!p) {
-    p = malloc(bytes);
-    pinned = false;
-    if (!p) throw std::bad_alloc();
-  }
+  p = malloc(bytes);
+  if (!p) throw std::bad_alloc();
   std::lock_guard<std::mutex> lk(g_out_mu);
-  g_out[p] = pinned;
+  g_out[p] = false;
   return p;
 }
 
 void free_out(void* p) {
   if (!p) return;
-  bool pinned = false, found = false;
+  bool pinned = false, found = false, release = false;
   {
     std::lock_guard<std::mutex> lk(g_out_mu);
     auto it = g_out.find(p);
@@ -44,11 +76,24 @@ void free_out(void* p) {
       pinned = it->second;
       found = true;
       g_out.erase(it);
+      if (pinned) {
+        const size_t cap = g_pinned_cap[p];
+        if (g_pinned_cached + cap <= kPinnedCacheLimit) {
+          g_pinned_free.push_back({p, cap});
+          g_pinned_cached += cap;
+        } else {
+          g_pinned_cap.erase(p);
+          release = true;
+        }
+      }
     }
   }
   if (!found) return;  // not ours: ignore rather than corrupt the heap
-  if (pinned) cudaFreeHost(p);
-  else free(p);
+  if (pinned) {
+    if (release) cudaFreeHost(p);
+  } else {
+    free(p);
+  }
 }
 
 }  // namespace sbv2

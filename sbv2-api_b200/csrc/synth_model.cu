@@ -96,6 +96,10 @@ struct HParams {
 
 }  // namespace
 
+}  // namespace sbv2
+struct BatchBuffers;
+namespace sbv2 {
+
 struct SynthModel : sbv2_model {
   HParams hp;
   // weights
@@ -127,14 +131,18 @@ struct SynthModel : sbv2_model {
   uint64_t seed = 0x5b2b200ULL, rng_offset = 0;
   // workspaces
   DBuf ws[32];
+  std::vector<BatchBuffers*> batch_pool;  // idle batch buffer sets
   DecoderHostWeights dec_host;  // original-layout decoder weights, consumed by umma_decoder_create
   PinnedBuf pin_in, pin_ylen;
-  ~SynthModel() override {
-    if (umma) umma_decoder_free(umma);
-  }
+  ~SynthModel() override;
 };
 
 }  // namespace sbv2
+
+// Device buffers of one batch; recycled through the model's pool (cudaMalloc/cudaFree per call costs ms).
+struct BatchBuffers {
+  sbv2::DBuf in, zp, ymeta, wave, dur, cum, f2p, ylen_dev;
+};
 
 // One uploaded batch: host bookkeeping + device inputs/outputs.
 struct sbv2_device_batch {
@@ -143,10 +151,11 @@ struct sbv2_device_batch {
   std::vector<int> xlen, xstart, ylen, ystart;
   std::vector<int64_t> zp_frames;
   bool has_noise_sdp = false, has_noise_zp = false, any_sdp = false;
-  sbv2::DBuf in;    // one blob, see synth_upload
-  sbv2::DBuf zp;    // caller-provided noise_zp blocks (channel-major)
-  sbv2::DBuf ymeta; // ystart, ylen, zp offsets
-  sbv2::DBuf wave, dur, cum, f2p, ylen_dev;
+  BatchBuffers* bufs = nullptr;  // borrowed from / returned to the owner's pool
+  sbv2_model* owner = nullptr;
+  sbv2::DBuf &in, &zp, &ymeta, &wave, &dur, &cum, &f2p, &ylen_dev;
+  explicit sbv2_device_batch(BatchBuffers* b, sbv2_model* o)
+      : bufs(b), owner(o), in(b->in), zp(b->zp), ymeta(b->ymeta), wave(b->wave), dur(b->dur), cum(b->cum), f2p(b->f2p), ylen_dev(b->ylen_dev) {}
   // offsets (bytes) into `in`
   size_t o_x = 0, o_tone = 0, o_lang = 0, o_sid = 0, o_sdp_ratio = 0, o_ls = 0, o_ns = 0, o_nsw = 0, o_xstart = 0, o_xlen = 0,
          o_bert_off = 0, o_nsdp_off = 0, o_style = 0, o_bert = 0, o_nsdp = 0, o_zp_off = 0, o_zp_ld = 0;
@@ -155,6 +164,25 @@ struct sbv2_device_batch {
 };
 
 namespace sbv2 {
+
+SynthModel::~SynthModel() {
+  if (umma) umma_decoder_free(umma);
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  for (BatchBuffers* b : batch_pool) delete b;
+}
+
+static BatchBuffers* borrow_buffers(SynthModel& M) {
+  BatchBuffers* b;
+  if (!M.batch_pool.empty()) {
+    b = M.batch_pool.back();
+    M.batch_pool.pop_back();
+  } else {
+    b = new BatchBuffers();
+  }
+  for (DBuf* d : {&b->in, &b->zp, &b->ymeta, &b->wave, &b->dur, &b->cum, &b->f2p, &b->ylen_dev}) d->stream = M.stream;
+  return b;
+}
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -760,7 +788,7 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
   SBV2_REQUIRE(utts && batch > 0, "empty batch");
   M->bind_device();
   const HParams& hp = M->hp;
-  std::unique_ptr<sbv2_device_batch> b(new sbv2_device_batch());
+  std::unique_ptr<sbv2_device_batch, void (*)(sbv2_device_batch*)> b(new sbv2_device_batch(borrow_buffers(*M), M), synth_batch_free);
   b->B = batch;
   b->xlen.resize(batch);
   b->xstart.resize(batch);
@@ -821,6 +849,7 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
   b->o_nsdp = take(size_t(nx) * 2 * 4);
   const size_t total = off;
 
+  CUDA_CHECK(cudaStreamSynchronize(M->stream));  // previous upload's copies out of the staging buffer are done
   M->pin_in.ensure(total);
   uint8_t* h = M->pin_in.as<uint8_t>();
   int32_t* hx = reinterpret_cast<int32_t*>(h + b->o_x);
@@ -856,12 +885,20 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
     hboff[i] = int64_t(s) * hp.bert_dim;
     hnoff[i] = int64_t(s) * 2;
     memcpy(hstyle + size_t(i) * hp.style_dim, u.style_vec, size_t(hp.style_dim) * 4);
-    memcpy(hbert + size_t(s) * hp.bert_dim, u.bert, size_t(n) * hp.bert_dim * 4);
     if (u.noise_sdp) memcpy(hnsdp + size_t(s) * 2, u.noise_sdp, size_t(n) * 2 * 4);
   }
   b->in.stream = M->stream;
   b->in.ensure(total);
-  CUDA_CHECK(cudaMemcpyAsync(b->in.p, h, total, cudaMemcpyHostToDevice, M->stream));
+  // small tables first, then the BERT features utterance by utterance so that the DMA of one
+  // utterance overlaps the staging memcpy of the next
+  CUDA_CHECK(cudaMemcpyAsync(b->in.p, h, b->o_bert, cudaMemcpyHostToDevice, M->stream));
+  CUDA_CHECK(cudaMemcpyAsync(b->in.as<uint8_t>() + b->o_nsdp, h + b->o_nsdp, size_t(nx) * 2 * 4, cudaMemcpyHostToDevice, M->stream));
+  for (int i = 0; i < batch; ++i) {
+    const size_t off_f = size_t(b->xstart[i]) * hp.bert_dim, cnt = size_t(b->xlen[i]) * hp.bert_dim * 4;
+    memcpy(hbert + off_f, utts[i].bert, cnt);
+    CUDA_CHECK(cudaMemcpyAsync(b->in.as<uint8_t>() + b->o_bert + off_f * 4, reinterpret_cast<uint8_t*>(hbert) + off_f * 4, cnt,
+                               cudaMemcpyHostToDevice, M->stream));
+  }
   if (b->has_noise_zp) {
     size_t tot = 0;
     for (int i = 0; i < batch; ++i) tot += size_t(b->zp_frames[i]) * hp.inter;
@@ -874,8 +911,8 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
       o += n;
     }
   }
-  // the pinned staging buffer is reused by the next upload: wait for the copy
-  CUDA_CHECK(cudaStreamSynchronize(M->stream));
+  // no sync here: the copies overlap with the caller's next steps; the staging buffer is protected by
+  // the synchronisation at the top of the next upload
   return b.release();
 }
 
@@ -1373,7 +1410,15 @@ void synth_download(sbv2_model* mm, sbv2_device_batch* b, float** out_samples, i
   if (out_f2p) *out_f2p = hf2p;
 }
 
-void synth_batch_free(sbv2_device_batch* b) { delete b; }
+void synth_batch_free(sbv2_device_batch* b) {
+  if (!b) return;
+  if (b->bufs) {
+    auto* M = static_cast<SynthModel*>(b->owner);
+    if (M && M->batch_pool.size() < 4) M->batch_pool.push_back(b->bufs);
+    else delete b->bufs;  // DBuf destructors free the device memory
+  }
+  delete b;
+}
 
 // HiFi-GAN decoder alone (config 3)
 void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, const int64_t* sid, int batch, float** out_samples,
@@ -1384,7 +1429,8 @@ void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, con
   SBV2_REQUIRE(z && t_y && sid && batch > 0, "empty batch");
   M.bind_device();
   const HParams& hp = M.hp;
-  sbv2_device_batch b;
+  std::unique_ptr<sbv2_device_batch, void (*)(sbv2_device_batch*)> bp(new sbv2_device_batch(borrow_buffers(M), &M), synth_batch_free);
+  sbv2_device_batch& b = *bp;
   b.B = batch;
   b.decode_only = true;
   b.ylen.resize(batch);
@@ -1406,6 +1452,7 @@ void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, con
   size_t meta_ints = size_t(2) * batch + 2;
   size_t o_meta = 0, o_off = align_up(meta_ints * 4, 256), o_sid = align_up(o_off + size_t(batch) * 8, 256),
          o_z = align_up(o_sid + size_t(batch) * 8, 256), total = o_z + size_t(ny) * C * 4;
+  CUDA_CHECK(cudaStreamSynchronize(M.stream));
   M.pin_in.ensure(total);
   uint8_t* hbuf = M.pin_in.as<uint8_t>();
   int* hmeta = reinterpret_cast<int*>(hbuf + o_meta);

@@ -48,6 +48,9 @@ struct UmmaConvArgs {
   __half* out;
   long long out_plane_stride;
   const __half* residual;      // geometry of `out`; stored post-lrelu(0.1)
+  const __half* residual2;     // further post-lrelu terms added the same way (MRF: other resblocks' outputs)
+  const __half* residual3;
+  float out_div;               // result divided by this before the activation (MRF mean), 1 = off
   float* accum;                // fp32 planar, geometry of `out`
   const __half* w;             // packed [nblk][kc][tap][KC/8][NB][8]
   const float* bias;           // [n_nblk*NB]
@@ -157,7 +160,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // Epilogue of NCH (16 or 32) accumulator columns of one row.  Compile-time variants keep the
 // per-element code branch-free: activation is max(v, slope*v) (slope 1 = none, 0 = relu, 0.1 / 0.01 =
 // leaky relu); GELU (DeBERTa FFN only) is the one runtime branch, taken per plane.
-template <int NCH, bool ACC, bool RES>
+template <int NCH, bool ACC, int RES>
 __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t taddr, bool valid, long long orow, int co0_global,
                                               const float* bias) {
   constexpr int NPL = NCH / 8;
@@ -166,12 +169,17 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
   for (int q = 0; q < NCH / 16; ++q) tc_ld16(taddr + 16 * q, v + 16 * q);
   // issue the global loads this item needs while the TMEM load is in flight
   uint4 r[RES ? NPL : 1];
+  uint4 r2[RES == 3 ? NPL : 1], r3[RES == 3 ? NPL : 1];
   float4 s[ACC ? 2 * NPL : 1];
   const long long eoff0 = ((long long)co0_global >> 3) * p.out_plane_stride + orow * 8;
 #pragma unroll
   for (int pl = 0; pl < NPL; ++pl) {
     const long long eoff = eoff0 + pl * p.out_plane_stride;
     if (RES && valid) r[pl] = *reinterpret_cast<const uint4*>(p.residual + eoff);
+    if (RES == 3 && valid) {
+      r2[pl] = *reinterpret_cast<const uint4*>(p.residual2 + eoff);
+      r3[pl] = *reinterpret_cast<const uint4*>(p.residual3 + eoff);
+    }
     if (ACC && valid && p.accum_mode >= UACC_ADD) {
       const float4* sp = reinterpret_cast<const float4*>(p.accum + eoff);
       s[2 * pl] = sp[0];
@@ -201,6 +209,19 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
         const float2 y = __half22float2(rh[e]);
         f[2 * e] += fminf(y.x, y.x * 10.f);  // inverse of lrelu(0.1): x = y >= 0 ? y : 10 y
         f[2 * e + 1] += fminf(y.y, y.y * 10.f);
+      }
+    }
+    if (RES == 3) {
+      const __half2* ra = reinterpret_cast<const __half2*>(&r2[pl]);
+      const __half2* rb = reinterpret_cast<const __half2*>(&r3[pl]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 ya = __half22float2(ra[e]), yb = __half22float2(rb[e]);
+        // (r0 + r1) + r2 as the graph sums the resblocks, then / n
+        const float s0 = fminf(ya.x, ya.x * 10.f) + fminf(yb.x, yb.x * 10.f);
+        const float s1 = fminf(ya.y, ya.y * 10.f) + fminf(yb.y, yb.y * 10.f);
+        f[2 * e] = (s0 + f[2 * e]) / p.out_div;
+        f[2 * e + 1] = (s1 + f[2 * e + 1]) / p.out_div;
       }
     }
     if (ACC) {
@@ -437,7 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     const int wq = warp & 3;           // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;  // NUM_EPI_WARPS/4 warps per quarter split the work items
     const int etid = threadIdx.x - 64;
-    const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE;
+    const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE && p.has_res != 3;
     const int nch = wide ? 32 : 16;
     const int items_per_acc = p.nb / nch;
     const int n_sub = p.mt * items_per_acc;
@@ -470,14 +491,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
         const int cg = ti.nblk * p.nb + c0;
         if (p.accum_mode != UACC_NONE) {
-          if (p.has_res) epilogue_item<16, true, true>(p, taddr, valid, orow, cg, bias + c0);
-          else epilogue_item<16, true, false>(p, taddr, valid, orow, cg, bias + c0);
+          if (p.has_res) epilogue_item<16, true, 1>(p, taddr, valid, orow, cg, bias + c0);
+          else epilogue_item<16, true, 0>(p, taddr, valid, orow, cg, bias + c0);
+        } else if (p.has_res == 3) {
+          epilogue_item<16, false, 3>(p, taddr, valid, orow, cg, bias + c0);
         } else if (wide) {
-          if (p.has_res) epilogue_item<32, false, true>(p, taddr, valid, orow, cg, bias + c0);
-          else epilogue_item<32, false, false>(p, taddr, valid, orow, cg, bias + c0);
+          if (p.has_res) epilogue_item<32, false, 1>(p, taddr, valid, orow, cg, bias + c0);
+          else epilogue_item<32, false, 0>(p, taddr, valid, orow, cg, bias + c0);
         } else {
-          if (p.has_res) epilogue_item<16, false, true>(p, taddr, valid, orow, cg, bias + c0);
-          else epilogue_item<16, false, false>(p, taddr, valid, orow, cg, bias + c0);
+          if (p.has_res) epilogue_item<16, false, 1>(p, taddr, valid, orow, cg, bias + c0);
+          else epilogue_item<16, false, 0>(p, taddr, valid, orow, cg, bias + c0);
         }
       }
       // release the accumulator set
@@ -726,7 +749,10 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.out_off = c.out_off;
   a.act_out = c.act_out;
   a.act_slope = c.act_out == ACT_LRELU ? 0.1f : (c.act_out == ACT_LRELU01 ? 0.01f : (c.act_out == ACT_RELU ? 0.f : 1.f));
-  a.has_res = c.residual ? 1 : 0;
+  a.has_res = c.residual ? (c.residual2 ? 3 : 1) : 0;
+  a.residual2 = c.residual2;
+  a.residual3 = c.residual3;
+  a.out_div = c.out_div;
   a.accum_mode = c.accum_mode;
   a.act_on_accum = c.act_on_accum ? 1 : 0;
   a.accum_div = c.accum_div;

@@ -76,6 +76,9 @@ struct ConvCall {
   const __half* in = nullptr;
   __half* out = nullptr;          // planar fp16 (optional)
   const __half* residual = nullptr;  // planar fp16 stored post-lrelu(0.1): x = y >= 0 ? y : 10 y is added
+  const __half* residual2 = nullptr;  // MRF: two more post-lrelu terms (both or neither), summed first, then
+  const __half* residual3 = nullptr;  //      (r2 + r3 + v) / out_div before the activation
+  float out_div = 1.f;
   float* accum = nullptr;         // planar fp32 (geometry of out)
   int accum_mode = UACC_NONE;
   float accum_div = 1.f;

@@ -58,7 +58,7 @@ struct UmmaDecoder {
   std::vector<int> up_u, stage_c;
   std::vector<std::vector<ConvLayer>> c1, c2;  // [resblock][layer]
   float* post_w = nullptr;
-  DBuf zp, xs, xu, t1, r, sum, meta, gcond;
+  DBuf zp, xs, xu, t1, r, rj0, rj1, sum, meta, gcond;
   PinnedBuf pin_meta;
 };
 
@@ -103,7 +103,7 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
   D->post_k = w.post.k;
   if (D->post_c != C || D->post_c % 8 != 0) fail(SBV2_ERR_UNSUPPORTED, "decoder conv_post channel mismatch");
   D->post_w = owner->upload_f32(w.post.w);
-  for (DBuf* b : {&D->zp, &D->xs, &D->xu, &D->t1, &D->r, &D->sum, &D->meta, &D->gcond}) b->stream = owner->stream;
+  for (DBuf* b : {&D->zp, &D->xs, &D->xu, &D->t1, &D->r, &D->rj0, &D->rj1, &D->sum, &D->meta, &D->gcond}) b->stream = owner->stream;
   return D.release();
 }
 
@@ -123,7 +123,14 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
   D->xu.ensure(max_half * 2);
   D->t1.ensure(max_half * 2);
   D->r.ensure(max_half * 2);
-  D->sum.ensure(max_half * 4);
+  const bool mrf3 = D->per == 3;  // MRF mean folded into the last conv's epilogue (fp16 r0, r1) instead of an fp32 sum buffer
+  if (mrf3) {
+    D->rj0.ensure(max_half * 2);
+    D->rj1.ensure(max_half * 2);
+  } else {
+    D->sum.ensure(max_half * 4);
+  }
+  __half* rj[2] = {D->rj0.as<__half>(), D->rj1.as<__half>()};
   D->gcond.ensure(size_t(B) * D->c0 * 4);
   __half* zp = D->zp.as<__half>();
   __half* xs = D->xs.as<__half>();
@@ -212,13 +219,26 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
         if (l + 1 < nl) {
           c.out = r;
           c.act_out = ACT_LRELU;
+        } else if (mrf3) {
+          if (j + 1 < D->per) {
+            c.out = rj[j];
+            c.act_out = ACT_LRELU;
+          } else {
+            c.residual2 = rj[0];
+            c.residual3 = rj[1];
+            c.out_div = float(D->per);
+            launch_zero_gaps(ctx, xs, C, Go, B);
+            c.out = xs;
+            c.act_out = last_stage ? ACT_LRELU01 : ACT_LRELU;
+          }
+        } else if (D->per == 1) {
+          launch_zero_gaps(ctx, xs, C, Go, B);
+          c.out = xs;
+          c.act_out = last_stage ? ACT_LRELU01 : ACT_LRELU;
         } else {
           c.accum = sum;
           c.accum_div = float(D->per);
-          if (D->per == 1) {
-            c.accum_mode = UACC_FINAL;  // (0 + v)/1 — needs sum zero: use SET semantics via out only
-          }
-          if (j == 0 && D->per > 1) c.accum_mode = UACC_SET;
+          if (j == 0) c.accum_mode = UACC_SET;
           else if (j + 1 < D->per) c.accum_mode = UACC_ADD;
           else c.accum_mode = UACC_FINAL;
           if (c.accum_mode == UACC_FINAL) {

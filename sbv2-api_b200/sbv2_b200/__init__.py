@@ -127,14 +127,40 @@ def _i64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
-def _take(ptr, n: int, dtype) -> np.ndarray:
-    """Copy n elements out of a library-allocated buffer and release it."""
+class _Owned:
+    """Keeps a library-allocated buffer alive for the numpy views cut from it (zero-copy results)."""
+
+    def __init__(self, ptr):
+        self.ptr = C.cast(ptr, C.c_void_p)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib.sbv2_free(self.ptr)
+        except Exception:
+            pass
+
+
+def _take(ptr, n: int, dtype, copy: bool = True) -> np.ndarray:
+    """n elements of a library-allocated buffer: copied out (buffer released) or as a zero-copy
+    view that releases the buffer when it is garbage collected."""
     if n == 0:
         lib.sbv2_free(C.cast(ptr, C.c_void_p))
         return np.zeros(0, dtype=dtype)
-    arr = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
-    lib.sbv2_free(C.cast(ptr, C.c_void_p))
-    return arr.astype(dtype, copy=False)
+    if copy:
+        arr = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+        lib.sbv2_free(C.cast(ptr, C.c_void_p))
+        return arr.astype(dtype, copy=False)
+    owner = _Owned(ptr)
+    buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(owner.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+    _OWNERS[id(buf)] = owner  # tie the owner's lifetime to the ctypes buffer the views reference
+    import weakref
+    weakref.finalize(buf, _OWNERS.pop, id(buf), None)
+    return arr
+
+
+_OWNERS = {}
 
 
 def device_count() -> int:
@@ -339,7 +365,7 @@ class Model:
         pd, pf2 = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
         _check(lib.sbv2_synthesize_batch(self._h, arr, B, C.byref(p), _pi64(ns), C.byref(pd) if want_alignment else None,
                                          C.byref(pf2) if want_alignment else None))
-        flat = _take(p, int(ns.sum()), np.float32)
+        flat = _take(p, int(ns.sum()), np.float32, copy=False)
         offs = np.concatenate([[0], np.cumsum(ns)])
         audios = [flat[offs[i]:offs[i + 1]] for i in range(B)]
         if not want_alignment:
