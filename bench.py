@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="reduced model (tests only; not a benchmark configuration)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -126,7 +127,7 @@ def main():
     import torch
     from oracle import vits as ov
 
-    hp = ov.HParams()
+    hp = ov.tiny_hparams() if args.tiny else ov.HParams()
     workload = f"cfg4 shard: full JP-Extra pipeline, {args.batch} synthetic ~8 s utterances per GPU per step " \
                f"(T_x odd U{{201..281}}, BERT features given, sdp_ratio 0, transformer flow L=6)"
 

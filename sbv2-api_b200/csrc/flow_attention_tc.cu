@@ -22,6 +22,7 @@ constexpr uint32_t P_BYTES = (KT / 8) * QT * 16;                // 32 KB
 constexpr uint32_t PREL_BYTES = (RP / 8) * QT * 16;             // 4 KB
 constexpr uint32_t REL_BYTES = DP * RP * 16;                    // 3 KB
 constexpr int TM_O = 0, TM_SREL = 96, TM_S = 128 /* two sets: +0, +128 */, TM_COLS = 512;
+constexpr int NKV = 3;        // K/V tile buffers (prefetch depth)
 constexpr int NSM_WARPS = 8;  // softmax warps: two per TMEM lane quarter, each takes half of the keys of a tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,26 +124,26 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
   const int n_kt = (len + KT - 1) / KT;
 
   const uint32_t sQ = smem_u32(smem);
-  const uint32_t sK0 = sQ + TILE_BYTES;             // K tiles [2]
-  const uint32_t sV0 = sK0 + 2 * TILE_BYTES;        // V tiles [2]
-  const uint32_t sP = sV0 + 2 * TILE_BYTES;         // P tile
+  const uint32_t sK0 = sQ + TILE_BYTES;             // K tiles [NKV]
+  const uint32_t sV0 = sK0 + NKV * TILE_BYTES;      // V tiles [NKV]
+  const uint32_t sP = sV0 + NKV * TILE_BYTES;       // P tile
   const uint32_t sPrel = sP + P_BYTES;
   const uint32_t sEk = sPrel + PREL_BYTES;
   const uint32_t sEv = sEk + REL_BYTES;
   const uint32_t sBar = sEv + REL_BYTES;
   // barriers
-  const uint32_t bar_q = sBar, bar_kv = sBar + 8 /*[2]*/, bar_kvfree = sBar + 24 /*[2]*/, bar_s = sBar + 40 /*[2]*/,
-                 bar_sfree = sBar + 56 /*[2]*/, bar_p = sBar + 72, bar_pfree = sBar + 80, bar_done = sBar + 88;
-  const uint32_t tmem_slot = sBar + 96;
-  float* ml_x = reinterpret_cast<float*>(smem + (sBar - sQ) + 128);  // [2 halves][128 rows][2] (m, l) exchange
+  const uint32_t bar_q = sBar, bar_kv = sBar + 8 /*[4]*/, bar_kvfree = sBar + 40 /*[4]*/, bar_s = sBar + 72 /*[2]*/,
+                 bar_sfree = sBar + 88 /*[2]*/, bar_p = sBar + 104, bar_pfree = sBar + 112, bar_done = sBar + 120;
+  const uint32_t tmem_slot = sBar + 128;
+  float* ml_x = reinterpret_cast<float*>(smem + (sBar - sQ) + 256);  // [2 halves][128 rows][2] (m, l) exchange
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ));
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
-    mbar_init(bar_kv, 1);
-    mbar_init(bar_kv + 8, 1);
-    mbar_init(bar_kvfree, 1);
-    mbar_init(bar_kvfree + 8, 1);
+    for (int i = 0; i < NKV; ++i) {
+      mbar_init(bar_kv + 8 * i, 1);
+      mbar_init(bar_kvfree + 8 * i, 1);
+    }
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_sfree, 32 * NSM_WARPS);
@@ -173,20 +174,22 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
 
   if (warp == NSM_WARPS) {
     // ---------------- control warp ----------------
-    auto load_tile = [&](int i) {  // i-th tile of the (pass A, pass B) sequence
-      const int buf = i & 1;
+    auto load_tile = [&](int i) {  // i-th tile of the (pass A, pass B) sequence; lanes issue the plane copies in parallel
+      const int buf = i % NKV;
+      const uint32_t par = ((i / NKV) & 1) ^ 1;
       const int kt = i < n_kt ? i : i - n_kt;
       const bool with_v = i >= n_kt;
       const long long row0 = pbase + (long long)kt * KT;
-      if (elect_one_sync()) {
-        mbar_wait(bar_kvfree + 8 * buf, ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(bar_kv + 8 * buf, with_v ? 2 * TILE_BYTES : TILE_BYTES);
-        for (int pl = 0; pl < DP; ++pl) {
-          bulk_g2s(sK0 + buf * TILE_BYTES + pl * KT * 16, qkv + (size_t)(k_plane0 + pl) * s.plane_stride + row0 * 8, KT * 16, bar_kv + 8 * buf);
-          if (with_v)
-            bulk_g2s(sV0 + buf * TILE_BYTES + pl * KT * 16, qkv + (size_t)(v_plane0 + pl) * s.plane_stride + row0 * 8, KT * 16,
-                     bar_kv + 8 * buf);
-        }
+      mbar_wait(bar_kvfree + 8 * buf, par);
+      if (lane == 0) mbar_expect_tx(bar_kv + 8 * buf, with_v ? 2 * TILE_BYTES : TILE_BYTES);
+      __syncwarp();
+      if (lane < DP) {
+        bulk_g2s(sK0 + buf * TILE_BYTES + lane * KT * 16, qkv + (size_t)(k_plane0 + lane) * s.plane_stride + row0 * 8, KT * 16,
+                 bar_kv + 8 * buf);
+      } else if (lane < 2 * DP && with_v) {
+        const int pl = lane - DP;
+        bulk_g2s(sV0 + buf * TILE_BYTES + pl * KT * 16, qkv + (size_t)(v_plane0 + pl) * s.plane_stride + row0 * 8, KT * 16,
+                 bar_kv + 8 * buf);
       }
       __syncwarp();
     };
@@ -198,8 +201,7 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
       bulk_g2s(sEv, rel_v_p, REL_BYTES, bar_q);
     }
     __syncwarp();
-    load_tile(0);
-    if (n_tiles_total > 1) load_tile(1);
+    for (int i = 0; i < NKV && i < n_tiles_total; ++i) load_tile(i);
     mbar_wait(bar_q, 0);
     tc_fence_after();
     // K-major operands: LBO = rows*16 (next 8-channel plane), SBO = 128
@@ -217,37 +219,37 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
     }
     __syncwarp();
     auto issue_s = [&](int i) {  // S(i) = Q K_i^T into accumulator set i & 1
-      const int buf = i & 1;
-      mbar_wait(bar_kv + 8 * buf, (i >> 1) & 1);
-      mbar_wait(bar_sfree + 8 * buf, ((i >> 1) & 1) ^ 1);  // softmax threads have read S(i-2)
+      const int sb = i & 1, kb = i % NKV;
+      mbar_wait(bar_kv + 8 * kb, (i / NKV) & 1);
+      mbar_wait(bar_sfree + 8 * sb, ((i >> 1) & 1) ^ 1);  // softmax threads have read S(i-2)
       tc_fence_after();
-      const uint64_t dk = make_desc(sK0 + buf * TILE_BYTES, KT * 16, 128);
+      const uint64_t dk = make_desc(sK0 + kb * TILE_BYTES, KT * 16, 128);
       if (elect_one_sync()) {
         for (int k = 0; k < D / 16; ++k)
-          tc_mma_f16(tmem + TM_S + buf * KT, dq + (uint64_t)(k * 2 * QT), dk + (uint64_t)(k * 2 * KT), ID_S, k > 0 ? 1u : 0u);
-        tc_commit(bar_s + 8 * buf);
-        if (i < n_kt) tc_commit(bar_kvfree + 8 * buf);  // pass A: the K tile is free once S is done
+          tc_mma_f16(tmem + TM_S + sb * KT, dq + (uint64_t)(k * 2 * QT), dk + (uint64_t)(k * 2 * KT), ID_S, k > 0 ? 1u : 0u);
+        tc_commit(bar_s + 8 * sb);
+        if (i < n_kt) tc_commit(bar_kvfree + 8 * kb);  // pass A: the K tile is free once S is done
       }
       __syncwarp();
     };
     issue_s(0);
     for (int i = 0; i < n_tiles_total; ++i) {
-      const int buf = i & 1;
+      const int kb = i % NKV;
       if (i + 1 < n_tiles_total) issue_s(i + 1);  // overlaps the softmax of tile i
       if (i >= n_kt) {
         const int j = i - n_kt;
         mbar_wait(bar_p, j & 1);  // P tile written (and visible to the async proxy)
         tc_fence_after();
-        const uint64_t dv = make_desc(sV0 + buf * TILE_BYTES, 128, KT * 16);
+        const uint64_t dv = make_desc(sV0 + kb * TILE_BYTES, 128, KT * 16);
         if (elect_one_sync()) {
           for (int k = 0; k < KT / 16; ++k)
             tc_mma_f16(tmem + TM_O, dp + (uint64_t)(k * 2 * QT), dv + (uint64_t)(k * 16), ID_O, (j > 0 || k > 0) ? 1u : 0u);
           tc_commit(bar_pfree);
-          tc_commit(bar_kvfree + 8 * buf);
+          tc_commit(bar_kvfree + 8 * kb);
         }
         __syncwarp();
       }
-      if (i + 2 < n_tiles_total) load_tile(i + 2);
+      if (i + NKV < n_tiles_total) load_tile(i + NKV);
     }
     // window value term: O += Prel Ev   (Prel complete: the last bar_p wait covered it)
     if (elect_one_sync()) {
@@ -402,7 +404,7 @@ void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __hal
                               int heads, int head_dim, int window, const PlanarSegs& s) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != D || window != 4) fail(SBV2_ERR_UNSUPPORTED, "tensor-core attention: head_dim must be 96 and window 4");
-  const size_t smem = 5 * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 128 + 2 * QT * 2 * 4;
+  const size_t smem = (1 + 2 * NKV) * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 256 + 2 * QT * 2 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(flow_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
