@@ -23,6 +23,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ---------------------------------------------------------------------------------------------
 constexpr int CT = 64, CN = 64, CK = 16;
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) conv_kernel(ConvArgs a) {
   __shared__ float As[CK][CT + 4];
   __shared__ float Bs[CK][CN + 4];
@@ -47,50 +48,58 @@ __global__ void __launch_bounds__(256) conv_kernel(ConvArgs a) {
   const int b_r = tid >> 4;         // 0..15 ci row of the B tile
   const int b_c = (tid & 15) * 4;   // cout offset
 
-  for (int m = 0; m < a.taps; ++m) {
-    const int shift = a.off + m * a.dil;
-    const int tin = t0 + a_r + shift;
+  // fragment of step (m, c0) -> registers (global loads of the next step overlap the FMAs of this one)
+  auto load_frag = [&](int m, int c0, float (&av)[4], float (&bv)[4]) {
+    const int tin = t0 + a_r + a.off + m * a.dil;
     const bool row_ok = (t0 + a_r < len) && tin >= 0 && tin < len;
     const float* in_row = a.in + (size_t)(in_base + tin) * a.in_ld;
-    const float* wm = a.w + (size_t)m * a.cin * a.cout;
-    for (int c0 = 0; c0 < a.cin; c0 += CK) {
-      // A tile
-      float av[4];
+    const int ci = c0 + a_c;
+    if (VEC) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok && ci < a.cin) v = *reinterpret_cast<const float4*>(in_row + ci);
+      av[0] = apply_act(v.x, a.act_in); av[1] = apply_act(v.y, a.act_in);
+      av[2] = apply_act(v.z, a.act_in); av[3] = apply_act(v.w, a.act_in);
+    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int ci = c0 + a_c + q;
-        float v = 0.f;
-        if (row_ok && ci < a.cin) v = apply_act(in_row[ci], a.act_in);
-        av[q] = v;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) As[a_c + q][a_r] = av[q];
-      // B tile
-      {
-        int ci = c0 + b_r;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          int co = co0 + b_c + q;
-          float v = 0.f;
-          if (ci < a.cin && co < a.cout) v = wm[(size_t)ci * a.cout + co];
-          Bs[b_r][b_c + q] = v;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < CK; ++kk) {
-        float ar[4], br[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ar[i] = As[kk][ty * 4 + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) br[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-      }
-      __syncthreads();
+      for (int q = 0; q < 4; ++q) av[q] = (row_ok && ci + q < a.cin) ? apply_act(in_row[ci + q], a.act_in) : 0.f;
     }
+    const float* wrow = a.w + ((size_t)m * a.cin + (c0 + b_r)) * a.cout;
+    const int co = co0 + b_c;
+    if (VEC) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + b_r < a.cin && co < a.cout) v = *reinterpret_cast<const float4*>(wrow + co);
+      bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bv[q] = (c0 + b_r < a.cin && co + q < a.cout) ? wrow[co + q] : 0.f;
+    }
+  };
+
+  const int kchunks = (a.cin + CK - 1) / CK;
+  const int nsteps = a.taps * kchunks;
+  float av[4], bv[4];
+  load_frag(0, 0, av, bv);
+  for (int step = 0; step < nsteps; ++step) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) As[a_c + q][a_r] = av[q];
+    *reinterpret_cast<float4*>(&Bs[b_r][b_c]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+    if (step + 1 < nsteps) {
+      const int ns = step + 1;
+      const int m = ns / kchunks;
+      load_frag(m, (ns - m * kchunks) * CK, av, bv);
+    }
+#pragma unroll
+    for (int kk = 0; kk < CK; ++kk) {
+      const float4 ar = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 br = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float arr[4] = {ar.x, ar.y, ar.z, ar.w}, brr[4] = {br.x, br.y, br.z, br.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(arr[i], brr[j], acc[i][j]);
+    }
+    __syncthreads();
   }
 
 #pragma unroll
@@ -722,7 +731,10 @@ __global__ void dec_post_kernel(float* out, const float* x, const float* w, int 
 void launch_conv(const LaunchCtx& ctx, const ConvArgs& a) {
   if (a.seg.n <= 0 || a.seg.max_len <= 0) return;
   dim3 grid((a.seg.max_len + CT - 1) / CT, (a.cout + CN - 1) / CN, a.seg.n);
-  conv_kernel<<<grid, 256, 0, ctx.stream>>>(a);
+  const bool vec = a.cin % 4 == 0 && a.cout % 4 == 0 && a.in_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;
+  if (vec) conv_kernel<true><<<grid, 256, 0, ctx.stream>>>(a);
+  else conv_kernel<false><<<grid, 256, 0, ctx.stream>>>(a);
   POST_LAUNCH(ctx);
 }
 
