@@ -54,35 +54,44 @@ def make_batch(hp, batch: int, seed: int):
     return utts, raw
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+class ClockSampler:
+    """nvidia-smi in loop mode (-lms 100) for the duration of the timed region, as the profiling recipe does."""
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        time.sleep(0.15)
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.strip()]
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = [float(r[0]) for r in rows if r and num(r[0])]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and num(r[1])]
+        pw = [float(r[6]) for r in rows if len(r) > 6 and num(r[6])]
         reasons = []
         for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
-            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in rows):
                 reasons.append(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "samples": len(rows)}
 
 
 def cpu_oracle_rate(model, raw, n_utts: int, threads: int):
@@ -110,11 +119,13 @@ def cpu_oracle_rate(model, raw, n_utts: int, threads: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-replicas", type=int, default=2,
+                    help="model replicas per GPU driven by separate host threads in the e2e measurement (copies of one overlap compute of the other)")
     ap.add_argument("--tiny", action="store_true", help="reduced model (tests only; not a benchmark configuration)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -164,7 +175,6 @@ def main():
     oracle = ov.build_model(hp, seed=0)
     onnx = assets.synth_onnx(ov.state_dict_numpy(oracle), hp.upsample_rates, hp.resblock_dilation_sizes)
     model = S.Model(onnx, bert=False, device=local_rank)
-    del onnx
     model.seed(1234 + rank)
     utts, raw = make_batch(hp, args.batch, seed=100 + rank)
     stream = torch.cuda.ExternalStream(model.stream, device=local_rank)
@@ -208,16 +218,44 @@ def main():
     audio_s_step = samples / SR
 
     # ---- end to end through the C ABI with host buffers
+    # (a) one replica, one host thread: the latency-oriented number; (b) R replicas on this GPU, one host
+    # thread each (ctypes releases the GIL): H2D / D2H of one replica overlap the kernels of the other.
     for _ in range(2):
         model.synthesize_batch(utts)
     barrier()
     t0 = time.perf_counter()
-    e2e_audio = 0.0
-    for _ in range(args.steps):
+    single_audio = 0.0
+    n_single = max(2, args.steps // 2)
+    for _ in range(n_single):
         out = model.synthesize_batch(utts)
-        e2e_audio += sum(a.size for a in out) / SR
+        single_audio += sum(a.size for a in out) / SR
+    torch.cuda.synchronize()
+    e2e_single = single_audio / (time.perf_counter() - t0)
+    R = max(1, args.e2e_replicas)
+    replicas = [model] + [S.Model(onnx, bert=False, device=local_rank) for _ in range(R - 1)]
+    del onnx
+    for m in replicas[1:]:
+        m.seed(4321 + rank)
+        for _ in range(2):
+            m.synthesize_batch(utts)
+    per_thread = [0.0] * R
+    counts = [args.steps // R + (1 if i < args.steps % R else 0) for i in range(R)]
+
+    def worker(i):
+        for _ in range(counts[i]):
+            o = replicas[i].synthesize_batch(utts)
+            per_thread[i] += sum(a.size for a in o) / SR
+
+    barrier()
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(R)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
+    e2e_audio = sum(per_thread)
     barrier()
     h2d = sum(u["bert"].nbytes + 3 * 4 * u["x_tst"].size + u["style_vec"].nbytes + 8 * 4 for u in utts)
     d2h = int(samples * 4)
@@ -257,7 +295,8 @@ def main():
                        "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "region_ms_per_step_rank0": {"text": text_ms, "flow": flow_ms, "decoder": dec_ms}},
             "e2e": {"value": e2e_audio_total / (e2e_ms_max * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h, "replicas_per_gpu": R, "single_replica_rank0": e2e_single,
+                    "api": "sbv2_synthesize_batch (host buffers in, pinned host waveforms out)"},
             "gpu_launches": launches_total,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "umma_conv_kernel (HiFi-GAN decoder, timed region = whole decoder)",

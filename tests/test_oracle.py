@@ -91,3 +91,24 @@ def test_golden_fixture_reproduces(name):
     assert np.array_equal(inter["w_ceil"][0, 0].numpy().astype(np.int32), g["durations"])
     np.testing.assert_allclose(o[0, 0].numpy(), g["audio"], atol=2e-5)
     np.testing.assert_allclose(inter["logw"][0, 0].numpy(), g["logw"], atol=2e-5)
+
+
+def test_c_restatement_of_length_regulator_matches_numpy():
+    """oracle/length_regulator.c (plain C, integers) vs oracle/vits.py (numpy) vs float generate_path."""
+    import ctypes as C
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oracle_build_c", os.path.join(util.ROOT, "oracle", "build_c.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build())
+    lib.sbv2_oracle_durations.restype = C.c_int32
+    rng = np.random.default_rng(0)
+    for t_x in (1, 2, 23, 241, 1801):
+        for scale in (0.0, 0.3, 1.0, 2.5):
+            w = (np.exp(rng.standard_normal(t_x)) * scale).astype(np.float32)
+            d_ref, ty_ref, f_ref = ov.length_regulate_int(w)
+            d = np.zeros(t_x, np.int32)
+            ty = lib.sbv2_oracle_durations(w.ctypes.data_as(C.POINTER(C.c_float)), t_x, d.ctypes.data_as(C.POINTER(C.c_int32)))
+            f = np.zeros(ty, np.int32)
+            lib.sbv2_oracle_frame2ph(d.ctypes.data_as(C.POINTER(C.c_int32)), t_x, ty, f.ctypes.data_as(C.POINTER(C.c_int32)))
+            assert ty == ty_ref and np.array_equal(d, d_ref) and np.array_equal(f, f_ref)

@@ -1,0 +1,28 @@
+"""Sums ncu dram bytes + durations over the decoder's umma_conv launches of one bench step.
+Usage: python tools/decoder_traffic.py gpurun_out/traffic.csv  -> writes profiles/decoder_traffic.json"""
+import csv, json, os, sys
+lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
+per = {}
+order = []
+for row in csv.DictReader(lines):
+    kid = row["ID"]
+    if kid not in per:
+        per[kid] = {"name": row["Kernel Name"]}
+        order.append(kid)
+    v = float(row["Metric Value"].replace(",", ""))
+    u = row["Metric Unit"]
+    name = row["Metric Name"]
+    if name.startswith("dram__bytes"):
+        mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        per[kid][name] = v * mul
+    elif name == "gpu__time_duration.sum":
+        per[kid]["us"] = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+umma = [per[k] for k in order if "umma_conv" in per[k]["name"]]
+dec = umma[-113:]  # the decoder's convs are the last 113 tensor-core conv launches of a step
+rd = sum(k.get("dram__bytes_read.sum", 0) for k in dec)
+wr = sum(k.get("dram__bytes_write.sum", 0) for k in dec)
+us = sum(k.get("us", 0) for k in dec)
+out = {"launches": len(dec), "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr, "dram_bytes_per_step": rd + wr,
+       "kernel_time_us_under_ncu": us, "note": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum, cold-cache serialised replays; bench workload (32 x ~8 s)"}
+json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "decoder_traffic.json"), "w"), indent=1)
+print(out)
