@@ -61,7 +61,9 @@ struct UmmaConvArgs {
   const int* len;              // [n_utt] rows (input resolution)
   int n_utt;
   int cin, nb, n_nblk, n_items, taps, kc, nkc, mt, sps, nstages, nloads, total_steps, a_slots, b_resident;
-  int tap_shift[MAX_TAPS];
+  int n_groups;
+  int tap_shift[UMMA_MAX_GROUPS * MAX_TAPS];
+  int group_out_off[UMMA_MAX_GROUPS];
   int halo_lo, halo_hi;
   int out_mul, out_off;
   int act_out;
@@ -271,7 +273,7 @@ __device__ __forceinline__ void epilogue_item(const UmmaConvArgs& p, uint32_t ta
 // MMA thread alternates between two TMEM accumulator sets, and the epilogue warps drain set i while
 // the MMA thread fills set i^1 — loads, tensor work and stores of neighbouring tiles overlap.
 struct TileInfo {
-  int b, t0, len, nblk;
+  int b, t0, len, nblk, grp;
 };
 #define TRACE(ev, itv)                                                                         \
   do {                                                                                         \
@@ -280,8 +282,11 @@ struct TileInfo {
 
 __device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item) {
   TileInfo ti;
-  const int tile = item / p.n_nblk;
-  ti.nblk = item - tile * p.n_nblk;
+  const int per_tile = p.n_nblk * p.n_groups;
+  const int tile = item / per_tile;
+  const int rem = item - tile * per_tile;
+  ti.grp = rem / p.n_nblk;
+  ti.nblk = rem - ti.grp * p.n_nblk;
   int lo = 0, hi = p.n_utt;  // largest b with tile_prefix[b] <= tile
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, first = false, ++pit) {
         const TileInfo ti = locate_item(p, item);
         TRACE(0, pit);
-        const __half* wbase = p.w + (size_t)ti.nblk * p.total_steps * (step_bytes / 2);
+        const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
         auto load_a_chunk = [&](int kc) {
           const uint32_t slot = a_it % p.a_slots;
@@ -401,6 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         tc_fence_after();
         if (lane == 0) TRACE(2, it);
         const uint32_t tmem_acc = tmem_base + buf * acc_cols;
+        const int grp = (item % (p.n_nblk * p.n_groups)) / p.n_nblk;
         int step = 0, si = 0;
         for (int kc = 0; kc < p.nkc; ++kc) {
           mbar_wait(bar_af + 8 * a_slot_i, a_par);
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
               b_addr = sB + stage_bytes * b_st + step_bytes * si;
             }
             tc_fence_after();
-            const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[tap];
+            const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
             const uint64_t b_d = b_desc0 + (b_addr >> 4);
             const uint32_t accf = step > 0 ? 1u : 0u;
             if (elect_one_sync()) {
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const int c0 = (sub - a * items_per_acc) * nch;
         const int t = ti.t0 + a * 128 + wq * 32 + lane;
         const bool valid = t < ti.len;
-        const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off;
+        const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off + p.group_out_off[ti.grp];
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
         const int cg = ti.nblk * p.nb + c0;
         if (p.accum_mode != UACC_NONE) {
@@ -582,14 +588,18 @@ size_t layer_smem(int planes_per_chunk, int ra, int a_slots, size_t stage_bytes,
   return a + stage_bytes * nstages + 256 + 1024;  // barriers + bias
 }
 
-// wsel(co, ci, tap) returns the weight of output channel co, input channel ci, tap index `tap`
+// wsel(g, co, ci, tap) returns the weight of group g, output channel co, input channel ci, tap index `tap`;
+// shifts[g][tap] the input-row shift of that tap.
 template <class WSel>
-ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* shifts, const float* bias, WSel wsel, int mt_pref) {
+ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_groups, const int (*shifts)[MAX_TAPS], const int* group_out_off,
+                     const float* bias, WSel wsel, int mt_pref) {
   ConvLayer L;
   L.cin = cin;
   L.cout = cout;
   L.taps = taps;
+  L.n_groups = n_groups;
   if (taps > MAX_TAPS) fail(SBV2_ERR_UNSUPPORTED, "conv has too many taps for the tensor-core plan");
+  if (n_groups > UMMA_MAX_GROUPS) fail(SBV2_ERR_UNSUPPORTED, "too many polyphase groups");
   if (cin % 16 != 0 || cout % 16 != 0) fail(SBV2_ERR_UNSUPPORTED, "tensor-core conv needs channel counts divisible by 16");
   // N block: largest multiple of 16 that divides cout and is <= 256
   L.nb = 0;
@@ -602,10 +612,13 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
   L.kc = cin % 64 == 0 ? 64 : (cin % 48 == 0 ? 48 : (cin % 32 == 0 ? 32 : 16));
   L.nkc = cin / L.kc;
   int lo = 0, hi = 0;
-  for (int i = 0; i < taps; ++i) {
-    L.tap_shift[i] = shifts[i];
-    lo = std::min(lo, shifts[i]);
-    hi = std::max(hi, shifts[i]);
+  for (int g = 0; g < n_groups; ++g) {
+    L.group_out_off[g] = group_out_off ? group_out_off[g] : 0;
+    for (int i = 0; i < taps; ++i) {
+      L.tap_shift[g][i] = shifts[g][i];
+      lo = std::min(lo, shifts[g][i]);
+      hi = std::max(hi, shifts[g][i]);
+    }
   }
   L.halo_lo = -lo;
   L.halo_hi = hi;
@@ -625,7 +638,7 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
     const size_t slot = size_t(ppc) * ra * 16;
     // weights resident for the whole kernel when they fit next to a double-buffered activation tile
     const int min_slots = std::max(2, std::min(L.nkc + 1, MAX_ASLOTS));
-    if (L.n_nblk == 1 && w_bytes + slot * std::min(2 * L.nkc, MAX_ASLOTS) <= budget && w_bytes <= 100 * 1024) {
+    if (L.n_nblk == 1 && L.n_groups == 1 && w_bytes + slot * std::min(2 * L.nkc, MAX_ASLOTS) <= budget && w_bytes <= 100 * 1024) {
       L.b_resident = 1;
       L.sps = L.total_steps;
       L.nloads = 1;
@@ -659,15 +672,16 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, const int* 
   if (!placed) fail(SBV2_ERR_UNSUPPORTED, "conv tile does not fit in shared memory");
   L.tmem_cols = pow2_at_least(2 * L.mt * L.nb);
   L.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(L.nb >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-  // pack weights: [nblk][kc][tap][KC/8][NB][8]
-  std::vector<uint16_t> pk(size_t(L.n_nblk) * L.total_steps * L.nb * L.kc);
+  // pack weights: [group][nblk][kc][tap][KC/8][NB][8]
+  std::vector<uint16_t> pk(size_t(n_groups) * L.n_nblk * L.total_steps * L.nb * L.kc);
   size_t o = 0;
-  for (int nbk = 0; nbk < L.n_nblk; ++nbk)
-    for (int kc = 0; kc < L.nkc; ++kc)
-      for (int tap = 0; tap < taps; ++tap)
-        for (int pl = 0; pl < L.kc / 8; ++pl)
-          for (int n = 0; n < L.nb; ++n)
-            for (int e = 0; e < 8; ++e) pk[o++] = f2h(wsel(nbk * L.nb + n, kc * L.kc + pl * 8 + e, tap));
+  for (int g = 0; g < n_groups; ++g)
+    for (int nbk = 0; nbk < L.n_nblk; ++nbk)
+      for (int kc = 0; kc < L.nkc; ++kc)
+        for (int tap = 0; tap < taps; ++tap)
+          for (int pl = 0; pl < L.kc / 8; ++pl)
+            for (int n = 0; n < L.nb; ++n)
+              for (int e = 0; e < 8; ++e) pk[o++] = f2h(wsel(g, nbk * L.nb + n, kc * L.kc + pl * 8 + e, tap));
   L.w = static_cast<__half*>(owner->upload_bytes(pk.data(), pk.size() * 2));
   std::vector<float> bz(size_t(cout), 0.f);
   if (bias) std::copy(bias, bias + cout, bz.begin());
@@ -688,25 +702,34 @@ void set_smem_attr() {
 }  // namespace
 
 ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref) {
-  int shifts[MAX_TAPS];
+  int shifts[1][MAX_TAPS] = {{0}};
   if (c.k > MAX_TAPS) fail(SBV2_ERR_UNSUPPORTED, "kernel size too large");
   // "same" padding as the graph builds it: left (k-1)/2 * dil (FFN even kernels pad ((k-1)/2, k/2))
-  for (int j = 0; j < c.k; ++j) shifts[j] = (j - (c.k - 1) / 2) * dil;
+  for (int j = 0; j < c.k; ++j) shifts[0][j] = (j - (c.k - 1) / 2) * dil;
   const int cin = c.d1, k = c.k;
   const float* w = c.w.data();
-  return make_layer(owner, c.d1, c.d0, c.k, shifts, c.b.empty() ? nullptr : c.b.data(),
-                    [=](int co, int ci, int tap) { return w[(size_t(co) * cin + ci) * k + tap]; }, mt_pref);
+  return make_layer(owner, c.d1, c.d0, c.k, 1, shifts, nullptr, c.b.empty() ? nullptr : c.b.data(),
+                    [=](int, int co, int ci, int tap) { return w[(size_t(co) * cin + ci) * k + tap]; }, mt_pref);
 }
 
-ConvLayer make_up_phase_layer(sbv2_model* owner, const HostConv& c, int u, int r, int mt_pref) {
+ConvLayer make_upsample_layer(sbv2_model* owner, const HostConv& c, int u, int mt_pref) {
+  // out[u*q + r] = bias + sum_m sum_ci w[ci][co][rr + u*m] * in[q + cc - m],  s = r + pad, rr = s % u, cc = s / u
   const int k = c.k, pad = (k - u) / 2, taps = k / u;
-  const int s = r + pad, rr = s % u, cc = s / u;
-  int shifts[MAX_TAPS];
-  for (int m = 0; m < taps; ++m) shifts[m] = cc - m;
+  if (u > UMMA_MAX_GROUPS || taps > MAX_TAPS) fail(SBV2_ERR_UNSUPPORTED, "upsample rate / kernel not supported by the tensor-core plan");
+  int shifts[UMMA_MAX_GROUPS][MAX_TAPS] = {{0}};
+  int offs[UMMA_MAX_GROUPS] = {0};
+  int rrs[UMMA_MAX_GROUPS] = {0};
+  for (int r = 0; r < u; ++r) {
+    const int s = r + pad;
+    rrs[r] = s % u;
+    for (int m = 0; m < taps; ++m) shifts[r][m] = s / u - m;
+    offs[r] = r;
+  }
   const int cout = c.d1;
   const float* w = c.w.data();
-  return make_layer(owner, c.d0, c.d1, taps, shifts, c.b.empty() ? nullptr : c.b.data(),
-                    [=](int co, int ci, int tap) { return w[(size_t(ci) * cout + co) * k + rr + u * tap]; }, mt_pref);
+  std::vector<int> rr(rrs, rrs + UMMA_MAX_GROUPS);
+  return make_layer(owner, c.d0, c.d1, taps, u, shifts, offs, c.b.empty() ? nullptr : c.b.data(),
+                    [=](int g, int co, int ci, int tap) { return w[(size_t(ci) * cout + co) * k + rr[g] + u * tap]; }, mt_pref);
 }
 
 long long* g_trace = nullptr;  // debug hook, see sbv2_debug_conv_trace
@@ -742,7 +765,11 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.nloads = L.nloads;
   a.total_steps = L.total_steps;
   a.a_slots = L.a_slots;
-  for (int i = 0; i < MAX_TAPS; ++i) a.tap_shift[i] = L.tap_shift[i];
+  a.n_groups = L.n_groups;
+  for (int g = 0; g < UMMA_MAX_GROUPS; ++g) {
+    a.group_out_off[g] = L.group_out_off[g];
+    for (int i = 0; i < MAX_TAPS; ++i) a.tap_shift[g * MAX_TAPS + i] = L.tap_shift[g][i];
+  }
   a.halo_lo = L.halo_lo;
   a.halo_hi = L.halo_hi;
   a.out_mul = c.out_mul;
@@ -760,7 +787,7 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.idesc = L.idesc;
   a.trace = g_trace;
   if (gi.n_tiles[slot] <= 0) return;
-  a.n_items = gi.n_tiles[slot] * L.n_nblk;
+  a.n_items = gi.n_tiles[slot] * L.n_nblk * L.n_groups;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;

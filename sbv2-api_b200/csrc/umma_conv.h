@@ -15,6 +15,7 @@ namespace sbv2 {
 constexpr int UMMA_GAP = 32;         // zero rows around each utterance (>= largest halo: 5*(11-1)/2 = 25)
 constexpr int UMMA_TAIL_ROWS = 2304;  // slack rows after the last utterance (a tile may over-read)
 constexpr int UMMA_MAX_TAPS = 16;
+constexpr int UMMA_MAX_GROUPS = 8;    // polyphase groups of one launch (ConvTranspose phases)
 
 struct HostConv {
   std::vector<float> w, b;  // PyTorch layout: Conv1d [d0=Cout, d1=Cin, k]; ConvTranspose1d [d0=Cin, d1=Cout, k]
@@ -38,7 +39,11 @@ struct ConvLayer {
   int cin = 0, cout = 0, nb = 0, n_nblk = 1, taps = 1, kc = 64, nkc = 1, mt = 1, sps = 1, nstages = 2, nloads = 1, total_steps = 1;
   int a_slots = 1;
   int b_resident = 0;  // all weight steps stay in shared memory for the whole (persistent) kernel
-  int tap_shift[UMMA_MAX_TAPS] = {0};
+  // groups: independent weight sets sharing the input tile (the u phases of a ConvTranspose1d); group g uses
+  // row shifts tap_shift[g][*] and writes output rows t*out_mul + group_out_off[g]
+  int n_groups = 1;
+  int tap_shift[UMMA_MAX_GROUPS][UMMA_MAX_TAPS] = {{0}};
+  int group_out_off[UMMA_MAX_GROUPS] = {0};
   int halo_lo = 0, halo_hi = 0;
   size_t smem = 0;
   int tmem_cols = 32;
@@ -47,8 +52,9 @@ struct ConvLayer {
 
 // Conv1d weight [Cout][Cin][k], "same" padding, dilation dil.
 ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref);
-// phase r (= output index mod u) of ConvTranspose1d weight [Cin][Cout][k], stride u, pad (k-u)/2
-ConvLayer make_up_phase_layer(sbv2_model* owner, const HostConv& c, int u, int r, int mt_pref);
+// ConvTranspose1d weight [Cin][Cout][k], stride u, pad (k-u)/2 as u polyphase groups of k/u taps (one launch;
+// launch with ConvCall::out_mul = u)
+ConvLayer make_upsample_layer(sbv2_model* owner, const HostConv& c, int u, int mt_pref);
 
 // One time resolution of one packed batch.
 struct Geom {

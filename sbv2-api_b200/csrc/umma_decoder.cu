@@ -54,7 +54,7 @@ struct UmmaDecoder {
   ConvLayer pre;
   float* cond_w = nullptr;  // fp32 [1][gin][c0]
   float* cond_b = nullptr;
-  std::vector<std::vector<ConvLayer>> ups;  // [stage][phase]
+  std::vector<ConvLayer> ups;  // [stage], polyphase groups inside
   std::vector<int> up_u, stage_c;
   std::vector<std::vector<ConvLayer>> c1, c2;  // [resblock][layer]
   float* post_w = nullptr;
@@ -82,9 +82,7 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
   for (int s = 0; s < D->n_stages; ++s) {
     const HostConv& U = w.ups[s];
     if (U.d0 != C) fail(SBV2_ERR_UNSUPPORTED, "decoder upsample channel mismatch");
-    std::vector<ConvLayer> phases;
-    for (int r = 0; r < w.up_u[s]; ++r) phases.push_back(make_up_phase_layer(owner, U, w.up_u[s], r, 16));
-    D->ups.push_back(phases);
+    D->ups.push_back(make_upsample_layer(owner, U, w.up_u[s], 16));
     D->up_u.push_back(w.up_u[s]);
     C = U.d1;
     D->stage_c.push_back(C);
@@ -189,14 +187,13 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
     const int C = D->stage_c[s];
     const int u = D->up_u[s];
     launch_zero_gaps(ctx, xu, C, Go, B);
-    for (int ph = 0; ph < u; ++ph) {
+    {
       ConvCall c;
       c.in = xs;
       c.out = xu;
       c.act_out = ACT_LRELU;
       c.out_mul = u;
-      c.out_off = ph;
-      launch_umma(ctx, D->ups[s][ph], Gi, Go, c, B);
+      launch_umma(ctx, D->ups[s], Gi, Go, c, B);
     }
     launch_zero_gaps(ctx, t1, C, Go, B);
     launch_zero_gaps(ctx, r, C, Go, B);
