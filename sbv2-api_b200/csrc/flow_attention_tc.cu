@@ -101,6 +101,11 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
       : "r"(0xffffffffu));
   return pred;
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // no-swizzle descriptor: start (16-B units), LBO, SBO in bytes
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
@@ -110,10 +115,17 @@ constexpr uint32_t idesc_f16(int n, int b_mn_major) {
   return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// debug timeline (sbv2_debug_attn_trace): trace[(tile * 8 + event)] = clock64() of CTA (0, 0, 0)
+#define ATRACE(ev, i)                                                                                   \
+  do {                                                                                                   \
+    if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < 64) trace[(i) * 8 + (ev)] = clock64(); \
+  } while (0)
+
 // warps 0..7: softmax / epilogue (query row = 32*(w&3)+lane, key half = w>>2)
 // warp 8: control (bulk loads + MMA issue)
 __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, const __half* qkv, const __half* rel_k_p,
-                                                                    const __half* rel_v_p, int heads, int window, PlanarSegs s) {
+                                                                    const __half* rel_v_p, int heads, int window, PlanarSegs s,
+                                                                    long long* trace) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -221,8 +233,10 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
     auto issue_s = [&](int i) {  // S(i) = Q K_i^T into accumulator set i & 1
       const int sb = i & 1, kb = i % NKV;
       mbar_wait(bar_kv + 8 * kb, (i / NKV) & 1);
+      if (lane == 0) ATRACE(0, i);
       mbar_wait(bar_sfree + 8 * sb, ((i >> 1) & 1) ^ 1);  // softmax threads have read S(i-2)
       tc_fence_after();
+      if (lane == 0) ATRACE(1, i);
       const uint64_t dk = make_desc(sK0 + kb * TILE_BYTES, KT * 16, 128);
       if (elect_one_sync()) {
         for (int k = 0; k < D / 16; ++k)
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
         const int j = i - n_kt;
         mbar_wait(bar_p, j & 1);  // P tile written (and visible to the async proxy)
         tc_fence_after();
+        if (lane == 0) ATRACE(2, i);
         const uint64_t dv = make_desc(sV0 + kb * TILE_BYTES, 128, KT * 16);
         if (elect_one_sync()) {
           for (int k = 0; k < KT / 16; ++k)
@@ -250,6 +265,7 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
         __syncwarp();
       }
       if (i + NKV < n_tiles_total) load_tile(i + NKV);
+      if (lane == 0) ATRACE(3, i);
     }
     // window value term: O += Prel Ev   (Prel complete: the last bar_p wait covered it)
     if (elect_one_sync()) {
@@ -276,9 +292,34 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
 #pragma unroll
       for (int r = 0; r < 9; ++r) srel[r] = __uint_as_float(v[r]) * c_scale;
     }
-    float m2 = -CUDART_INF_F, l = 0.f, inv_l = 0.f;
+    float m2 = -CUDART_INF_F, l = 0.f, mb = 0.f;  // running max, running sum (pass A); mb = max + log2(sum) (pass B)
     uint8_t* prow = smem + (sP - sQ) + row * 16;
     uint8_t* prel_row = smem + (sPrel - sQ) + row * 16;
+    // pass A on 32 logits x[e] * c: running (max, sum) update
+    auto pass_a = [&](const float* x, float c) {
+      float mx = x[0];
+#pragma unroll
+      for (int e = 1; e < 32; ++e) mx = fmaxf(mx, x[e]);
+      const float m_new = fmaxf(m2, mx * c);  // finite: the caller skips chunks without a valid key
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) sum += ex2_approx(fmaf(x[e], c, -m_new));
+      l = fmaf(l, ex2_approx(m2 - m_new), sum);  // first chunk: 0 * 2^-inf = 0
+      m2 = m_new;
+    };
+    // pass B: p[e] = 2^(x[e] * c - mb), fp16 into the P tile (columns 32 * c32 ...)
+    auto pass_b_store = [&](const float* x, float c, int c32, float* pv) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) pv[e] = ex2_approx(fmaf(x[e], c, -mb));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(pv[q * 8 + 2 * e], pv[q * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(prow + (size_t)(c32 * 4 + q) * QT * 16) = u;
+      }
+    };
     for (int i = 0; i < n_tiles_total; ++i) {
       const bool pass_b = i >= n_kt;
       const int kt = pass_b ? i - n_kt : i;
@@ -288,81 +329,76 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
         mbar_wait(bar_s + 8 * buf, (i >> 1) & 1);
         tc_fence_after();
       }
+      if (threadIdx.x == 0) ATRACE(4, i);
       if (i == n_kt) {
-        // combine the two key-halves of each row: (m, l) -> final max and 1 / sum
+        // combine the two key-halves of each row: (m, l) -> final max and log2(sum)
         ml_x[(half * QT + row) * 2] = m2;
         ml_x[(half * QT + row) * 2 + 1] = l;
         asm volatile("bar.sync 1, %0;" ::"r"(32 * NSM_WARPS) : "memory");
         const float mo = ml_x[((half ^ 1) * QT + row) * 2], lo = ml_x[((half ^ 1) * QT + row) * 2 + 1];
-        const float mf = fmaxf(m2, mo);
-        const float lf = (m2 == -CUDART_INF_F ? 0.f : l * exp2f(m2 - mf)) + (mo == -CUDART_INF_F ? 0.f : lo * exp2f(mo - mf));
+        const float mf = fmaxf(m2, mo);  // finite: key 0 is always valid
+        const float lf = l * ex2_approx(m2 - mf) + lo * ex2_approx(mo - mf);
         m2 = mf;
-        inv_l = 1.0f / lf;
+        mb = mf + log2f(lf);
       }
       if (pass_b && kt > 0) mbar_wait(bar_pfree, (kt - 1) & 1);  // previous P tile consumed by the MMA
+      if (threadIdx.x == 0) ATRACE(5, i);
 #pragma unroll 1
       for (int cc = 0; cc < KT / 64; ++cc) {
         const int c = half * (KT / 64) + cc;
+        const int kc0 = k0 + c * 32;
+        if (kc0 >= len) {  // no valid key in this chunk (warp-uniform)
+          if (pass_b) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(prow + (size_t)(c * 4 + q) * QT * 16) = z;
+          }
+          continue;
+        }
         uint32_t v[32];
         tc_ld32(lane_addr + TM_S + buf * KT + c * 32, v);
         tc_wait_ld();
-        const int kc0 = k0 + c * 32;
-        float sc[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) sc[e] = __uint_as_float(v[e]) * c_scale;
-        const int d0 = kc0 - qi;  // rel of element 0
-        const bool band = d0 <= 4 && d0 + 31 >= -4;
-        if (band) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int rel = d0 + e;
-#pragma unroll
-            for (int r = 0; r < 9; ++r)
-              if (rel == r - 4) sc[e] += srel[r];
+        float* x = reinterpret_cast<float*>(v);
+        const int j0 = kc0 - qi + 4;  // index into srel of element 0: element e is relative position j0 + e - 4
+        const bool band = j0 <= 8 && j0 + 31 >= 0;
+        const bool tail = kc0 + 32 > len;
+        if (!__any_sync(0xffffffffu, band) && !tail) {
+          // fast path: plain scaled logits
+          if (!pass_b) {
+            pass_a(x, c_scale);
+          } else {
+            float pv[32];
+            pass_b_store(x, c_scale, c, pv);
           }
+          continue;
         }
-        if (kc0 + 32 > len) {
+        // slow path (a chunk that touches the diagonal band or the end of the utterance): build the logits first.
+        // Selects only — data-dependent branches here diverge per lane and cost tens of thousands of cycles.
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (kc0 + e >= len) sc[e] = -CUDART_INF_F;
+        for (int e = 0; e < 32; ++e) {
+          const int r = j0 + e;
+          float add = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 9; ++rr) add = (r == rr) ? srel[rr] : add;
+          x[e] = (kc0 + e < len) ? fmaf(x[e], c_scale, add) : -CUDART_INF_F;
         }
         if (!pass_b) {
-          float mx = sc[0];
-#pragma unroll
-          for (int e = 1; e < 32; ++e) mx = fmaxf(mx, sc[e]);
-          const float m_new = fmaxf(m2, mx);
-          if (m_new != -CUDART_INF_F) {
-            float sum = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) sum += exp2f(sc[e] - m_new);
-            l = (m2 == -CUDART_INF_F ? 0.f : l * exp2f(m2 - m_new)) + sum;
-            m2 = m_new;
-          }
+          pass_a(x, 1.0f);
         } else {
           float pv[32];
+          pass_b_store(x, 1.0f, c, pv);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) pv[e] = exp2f(sc[e] - m2) * inv_l;
+          for (int rr = 0; rr < 9; ++rr) {
+            const int e = rr - j0;
+            float val = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __half2* uh = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(pv[q * 8 + 2 * e], pv[q * 8 + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(prow + (size_t)(c * 4 + q) * QT * 16) = u;
-          }
-          if (band) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int r = d0 + e + 4;  // 0..8 inside the band
-              if (r >= 0 && r <= 8) {
-                __half hv = __float2half_rn(pv[e]);
-                *reinterpret_cast<__half*>(prel_row + (size_t)(r >> 3) * QT * 16 + (r & 7) * 2) = hv;
-              }
-            }
+            for (int ee = 0; ee < 32; ++ee) val = (e == ee) ? pv[ee] : val;
+            if (e >= 0 && e < 32) *reinterpret_cast<__half*>(prel_row + (size_t)(rr >> 3) * QT * 16 + (rr & 7) * 2) = __float2half_rn(val);
           }
         }
       }
       // this thread's part of S is read
+      if (threadIdx.x == 0) ATRACE(6, i);
       tc_fence_before();
       mbar_arrive(bar_sfree + 8 * buf);
       if (pass_b) {
@@ -401,7 +437,7 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
 
 // rel_k_p / rel_v_p: fp16 [D/8][16][8] packings of emb_rel_k / emb_rel_v ([2w+1, D], rows >= 2w+1 zero)
 void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* rel_k_p, const __half* rel_v_p,
-                              int heads, int head_dim, int window, const PlanarSegs& s) {
+                              int heads, int head_dim, int window, const PlanarSegs& s, long long* trace) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != D || window != 4) fail(SBV2_ERR_UNSUPPORTED, "tensor-core attention: head_dim must be 96 and window 4");
   const size_t smem = (1 + 2 * NKV) * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 256 + 2 * QT * 2 * 4;
@@ -411,9 +447,65 @@ void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __hal
     attr_set = true;
   }
   dim3 grid((s.max_len + QT - 1) / QT, heads, s.n);
-  flow_attention_tc_kernel<<<grid, 32 * (NSM_WARPS + 1), smem, ctx.stream>>>(ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s);
+  flow_attention_tc_kernel<<<grid, 32 * (NSM_WARPS + 1), smem, ctx.stream>>>(ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s, trace);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }
 
 }  // namespace sbv2
+
+// ---- test hook: timeline + timing of the attention kernel on a synthetic batch ------------------------------------
+#include "model.h"
+#include "umma_conv.h"
+extern "C" int sbv2_debug_attn_trace(int T, int n_utt, int heads, long long* out_trace /*[64*8]*/, float* out_ms) {
+  using namespace sbv2;
+  return guarded([&] {
+    sbv2_model owner;
+    owner.device = 0;
+    CUDA_CHECK(cudaSetDevice(0));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&owner.stream, cudaStreamNonBlocking));
+    LaunchCtx ctx = owner.ctx();
+    DBuf meta, qkv, out, tr, rel;
+    PinnedBuf pin;
+    for (DBuf* b : {&meta, &qkv, &out, &tr, &rel}) b->stream = owner.stream;
+    std::vector<int> ystart, ylen, muls{1};
+    for (int i = 0; i < n_utt; ++i) {
+      ystart.push_back(i * T);
+      ylen.push_back(T);
+    }
+    BatchGeom bg = build_geoms(&owner, meta, pin, ystart, ylen, muls);
+    const Geom& G = bg.g[0];
+    const int C = heads * D;
+    qkv.ensure(size_t(G.rows_tot) * 3 * C * 2);
+    out.ensure(size_t(G.rows_tot) * C * 2);
+    rel.ensure(2 * REL_BYTES);
+    tr.ensure(64 * 8 * 8);
+    CUDA_CHECK(cudaMemsetAsync(qkv.p, 0x11, size_t(G.rows_tot) * 3 * C * 2, owner.stream));  // small positive fp16 values
+    CUDA_CHECK(cudaMemsetAsync(rel.p, 0, 2 * REL_BYTES, owner.stream));
+    CUDA_CHECK(cudaMemsetAsync(tr.p, 0, 64 * 8 * 8, owner.stream));
+    PlanarSegs ps;
+    ps.start = bg.d_ystart;
+    ps.pstart = G.d_pstart;
+    ps.len = G.d_len;
+    ps.n = n_utt;
+    ps.max_len = T;
+    ps.plane_stride = G.rows_tot * 8;
+    const __half* rk = rel.as<__half>();
+    const __half* rv = rk + REL_BYTES / 2;
+    for (int i = 0; i < 2; ++i) launch_flow_attention_tc(ctx, out.as<__half>(), qkv.as<__half>(), rk, rv, heads, D, 4, ps, nullptr);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, owner.stream));
+    for (int i = 0; i < 5; ++i) launch_flow_attention_tc(ctx, out.as<__half>(), qkv.as<__half>(), rk, rv, heads, D, 4, ps, nullptr);
+    CUDA_CHECK(cudaEventRecord(e1, owner.stream));
+    launch_flow_attention_tc(ctx, out.as<__half>(), qkv.as<__half>(), rk, rv, heads, D, 4, ps, tr.as<long long>());
+    CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (out_ms) *out_ms = ms / 5.f;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (out_trace) CUDA_CHECK(cudaMemcpy(out_trace, tr.p, 64 * 8 * 8, cudaMemcpyDeviceToHost));
+  });
+}

@@ -139,7 +139,7 @@ void launch_rel_attention_planar(const LaunchCtx& ctx, __half* ctx_out, const __
                                  int heads, int head_dim, int window, const PlanarSegs& s);
 // same on tcgen05 tensor cores (head_dim 96, window 4); rel_k_p / rel_v_p: fp16 [D/8][16][8] packings
 void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* rel_k_p, const __half* rel_v_p,
-                              int heads, int head_dim, int window, const PlanarSegs& s);
+                              int heads, int head_dim, int window, const PlanarSegs& s, long long* trace = nullptr);
 // z[row, C/2:] -= m32 (planar fp32, C/2 channels)
 void launch_coupling_sub_planar(const LaunchCtx& ctx, float* z, const float* m32, int C, const PlanarSegs& s);
 }  // namespace sbv2

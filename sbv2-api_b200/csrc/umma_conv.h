@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <map>
 #include <vector>
 
 #include "common.h"
@@ -65,6 +66,8 @@ struct Geom {
   const int* d_len = nullptr;
   const int* d_prefix[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // tiles of 128 * {1, 2, 4, 8, 16} rows
   int n_tiles[5] = {0, 0, 0, 0, 0};
+  // tile tables for other tile heights (fused ResBlock pairs use 128*MT - 2*halo rows per tile)
+  std::map<int, std::pair<const int*, int>> extra;  // height -> (device prefix [n+1], number of tiles)
   int max_len = 0;
 };
 struct BatchGeom {
@@ -75,7 +78,7 @@ struct BatchGeom {
 struct DBuf;
 struct PinnedBuf;
 BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::vector<int>& ystart, const std::vector<int>& ylen,
-                      const std::vector<int>& muls);
+                      const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights = nullptr);
 
 enum UAccum { UACC_NONE = 0, UACC_SET = 1, UACC_ADD = 2, UACC_FINAL = 3 };
 struct ConvCall {
@@ -99,6 +102,32 @@ void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, i
 void launch_to_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
                       int n_utt, int act);
 void launch_from_planar(const LaunchCtx& ctx, float* out, const __half* in, int C, const int* d_start, const Geom& g, int n_utt);
+
+// A fused ResBlock1 pair (umma_pair.cu): out = conv2(lrelu(conv1(in) + b1)) + b2 + x, the intermediate stays on chip.
+struct PairLayer {
+  __half* w1 = nullptr;  // [kc][tap][KC/8][C][8]
+  __half* w2 = nullptr;
+  float* bias1 = nullptr;
+  float* bias2 = nullptr;
+  int c = 0, taps = 1, kc = 16, nkc = 1, mt = 1, t1rows = 128, t1pitch = 144, out_rows = 128, h1 = 0, h2 = 0;
+  int shift1[UMMA_MAX_TAPS] = {0};
+  int sps = 1, nstages = 1, nloads = 1, total_steps = 1, a_slots = 2, b_resident = 0;
+  size_t smem = 0;
+  int tmem_cols = 512;
+  unsigned idesc = 0;
+};
+struct PairCall {
+  const __half* in = nullptr;  // post-lrelu planar fp16; also the residual.  Must not alias out.
+  __half* out = nullptr;
+  const __half* residual2 = nullptr;  // as ConvCall
+  const __half* residual3 = nullptr;
+  float out_div = 1.f;
+  int act_out = ACT_LRELU;
+};
+// false when the pair does not fit the fused plan (channel count, taps, shared memory); c1 has dilation dil, c2 dilation 1
+bool make_pair_layer(sbv2_model* owner, const HostConv& c1, int dil, const HostConv& c2, PairLayer* out);
+// g.extra must hold the tile table for L.out_rows (build_geoms extra_heights)
+void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, const PairCall& c, int n_utt);
 
 struct UmmaDecoder;
 UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner);

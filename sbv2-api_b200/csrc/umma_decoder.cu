@@ -6,15 +6,15 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "model.h"
 #include "umma_conv.h"
 
 namespace sbv2 {
+extern long long* g_pair_trace;
 namespace {
-
-constexpr int GAP = UMMA_GAP;
 
 // decoder post: out[t] = tanh(sum_j sum_c w[c][j] * x[t+j-pad][c]); x planar fp16 already activated (lrelu 0.01)
 __global__ void post_planar_kernel(float* wave, const __half* x, long long plane_stride, const float* w, int C, int k, const int* pstart,
@@ -57,6 +57,9 @@ struct UmmaDecoder {
   std::vector<ConvLayer> ups;  // [stage], polyphase groups inside
   std::vector<int> up_u, stage_c;
   std::vector<std::vector<ConvLayer>> c1, c2;  // [resblock][layer]
+  std::vector<std::vector<PairLayer>> pairs;   // [resblock][layer]: fused conv1+conv2 (umma_pair.cu) where fused[rb][l]
+  std::vector<std::vector<char>> fused;
+  std::vector<std::vector<int>> pair_heights;  // [geometry level]: tile heights the fused pairs need
   float* post_w = nullptr;
   DBuf zp, xs, xu, t1, r, rj0, rj1, sum, meta, gcond;
   PinnedBuf pin_meta;
@@ -78,6 +81,11 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
     D->cond_w = owner->upload_f32(t);
     D->cond_b = owner->upload_f32(w.cond.b);
   }
+  // ResBlock pairs are fused for C <= 64: there the unfused convs are bound by HBM traffic, not by the tensor pipe
+  // (C = 128 would stream 2 x 360 KB of weights from L2 per 118 output rows).  SBV2_B200_PAIR_MAXC=0 disables fusion.
+  int pair_maxc = 64;
+  if (const char* e = getenv("SBV2_B200_PAIR_MAXC")) pair_maxc = atoi(e);
+  D->pair_heights.assign(size_t(D->n_stages) + 1, {});
   int C = D->c0;
   for (int s = 0; s < D->n_stages; ++s) {
     const HostConv& U = w.ups[s];
@@ -89,12 +97,27 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
     for (int j = 0; j < w.per; ++j) {
       size_t rb = size_t(s) * w.per + j;
       std::vector<ConvLayer> l1, l2;
+      std::vector<PairLayer> lp;
+      std::vector<char> lf;
       for (size_t l = 0; l < w.res_c1[rb].size(); ++l) {
-        l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 16));
-        l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 16));
+        PairLayer P;
+        const bool f = (w.per == 1 || w.per == 3) && C <= pair_maxc && make_pair_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], w.res_c2[rb][l], &P);
+        lf.push_back(f ? 1 : 0);
+        lp.push_back(P);
+        if (f) {
+          std::vector<int>& hs = D->pair_heights[s + 1];
+          if (std::find(hs.begin(), hs.end(), P.out_rows) == hs.end()) hs.push_back(P.out_rows);
+          l1.emplace_back();
+          l2.emplace_back();
+        } else {
+          l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 16));
+          l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 16));
+        }
       }
       D->c1.push_back(l1);
       D->c2.push_back(l2);
+      D->pairs.push_back(lp);
+      D->fused.push_back(lf);
     }
   }
   D->post_c = w.post.d1;
@@ -112,7 +135,7 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
   LaunchCtx ctx = owner->ctx();
   std::vector<int> muls(1, 1);
   for (int s = 0; s < D->n_stages; ++s) muls.push_back(muls.back() * D->up_u[s]);
-  BatchGeom bg = build_geoms(owner, D->meta, D->pin_meta, ystart, ylen, muls);
+  BatchGeom bg = build_geoms(owner, D->meta, D->pin_meta, ystart, ylen, muls, &D->pair_heights);
   // buffer sizes
   size_t max_half = size_t(bg.g[0].rows_tot) * D->c0;
   for (int s = 0; s < D->n_stages; ++s) max_half = std::max(max_half, size_t(bg.g[s + 1].rows_tot) * D->stage_c[s]);
@@ -203,49 +226,72 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
       const __half* cur = xu;
       const size_t nl = D->c1[rb].size();
       for (size_t l = 0; l < nl; ++l) {
-        {
-          ConvCall c;
-          c.in = cur;
-          c.out = t1;
-          c.act_out = ACT_LRELU;
-          launch_umma(ctx, D->c1[rb][l], Go, Go, c, B);
-        }
-        ConvCall c;
-        c.in = t1;
-        c.residual = cur;
-        if (l + 1 < nl) {
-          c.out = r;
-          c.act_out = ACT_LRELU;
-        } else if (mrf3) {
-          if (j + 1 < D->per) {
-            c.out = rj[j];
-            c.act_out = ACT_LRELU;
+        // destination of this pair: the stage output (last pair of the last ResBlock: MRF mean folded in), the
+        // ResBlock's output rj[j], or a scratch buffer that is not the pair's input
+        const bool fuse = D->fused[rb][l] != 0;
+        // unfused: conv1 -> mid, conv2 (+ residual) -> dst, where dst may be the input buffer (element-wise aliasing only)
+        __half* mid = cur == t1 ? r : t1;
+        __half* dst = fuse ? (cur == r ? t1 : r) : (mid == t1 ? r : t1);
+        int act = ACT_LRELU;
+        const __half *res2 = nullptr, *res3 = nullptr;
+        float out_div = 1.f;
+        float* accum = nullptr;
+        int accum_mode = UACC_NONE;
+        if (l + 1 == nl) {
+          const bool last_rb = j + 1 == D->per;
+          if (mrf3 && !last_rb) {
+            dst = rj[j];
+          } else if (mrf3 || D->per == 1) {
+            if (mrf3) {
+              res2 = rj[0];
+              res3 = rj[1];
+              out_div = float(D->per);
+            }
+            launch_zero_gaps(ctx, xs, C, Go, B);
+            dst = xs;
+            act = last_stage ? ACT_LRELU01 : ACT_LRELU;
           } else {
-            c.residual2 = rj[0];
-            c.residual3 = rj[1];
-            c.out_div = float(D->per);
-            launch_zero_gaps(ctx, xs, C, Go, B);
-            c.out = xs;
-            c.act_out = last_stage ? ACT_LRELU01 : ACT_LRELU;
-          }
-        } else if (D->per == 1) {
-          launch_zero_gaps(ctx, xs, C, Go, B);
-          c.out = xs;
-          c.act_out = last_stage ? ACT_LRELU01 : ACT_LRELU;
-        } else {
-          c.accum = sum;
-          c.accum_div = float(D->per);
-          if (j == 0) c.accum_mode = UACC_SET;
-          else if (j + 1 < D->per) c.accum_mode = UACC_ADD;
-          else c.accum_mode = UACC_FINAL;
-          if (c.accum_mode == UACC_FINAL) {
-            launch_zero_gaps(ctx, xs, C, Go, B);
-            c.out = xs;
-            c.act_out = last_stage ? ACT_LRELU01 : ACT_LRELU;
+            accum = sum;
+            accum_mode = j == 0 ? UACC_SET : (last_rb ? UACC_FINAL : UACC_ADD);
+            dst = nullptr;
+            if (last_rb) {
+              launch_zero_gaps(ctx, xs, C, Go, B);
+              dst = xs;
+              act = last_stage ? ACT_LRELU01 : ACT_LRELU;
+            }
           }
         }
-        launch_umma(ctx, D->c2[rb][l], Go, Go, c, B);
-        cur = r;
+        if (fuse) {
+          PairCall pc;
+          pc.in = cur;
+          pc.out = dst;
+          pc.residual2 = res2;
+          pc.residual3 = res3;
+          pc.out_div = out_div;
+          pc.act_out = act;
+          launch_umma_pair(ctx, D->pairs[rb][l], Go, pc, B);
+        } else {
+          {
+            ConvCall c;
+            c.in = cur;
+            c.out = mid;
+            c.act_out = ACT_LRELU;
+            launch_umma(ctx, D->c1[rb][l], Go, Go, c, B);
+          }
+          ConvCall c;
+          c.in = mid;
+          c.residual = cur;
+          c.residual2 = res2;
+          c.residual3 = res3;
+          c.out_div = out_div;
+          c.out = dst;
+          c.act_out = act;
+          c.accum = accum;
+          c.accum_mode = accum_mode;
+          c.accum_div = float(D->per);
+          launch_umma(ctx, D->c2[rb][l], Go, Go, c, B);
+        }
+        cur = dst;
       }
     }
   }
@@ -338,6 +384,7 @@ extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const
 // ---- test hook: per-role clock64 trace of one conv launch (performance debugging) ----------------------------
 namespace sbv2 {
 extern long long* g_trace;
+extern long long* g_pair_trace;
 }
 extern "C" int sbv2_debug_conv_trace(int64_t T, int cin, int cout, int k, int dil, int mt_pref, int with_residual, int accum_mode,
                                      long long* out_trace /*[n_blocks*64*8]*/, int n_blocks, float* out_ms, int* out_cfg /*[8]*/) {
@@ -403,5 +450,130 @@ extern "C" int sbv2_debug_conv_trace(int64_t T, int cin, int cout, int k, int di
     cudaEventDestroy(e1);
     if (out_trace && n_blocks > 0)
       CUDA_CHECK(cudaMemcpy(out_trace, tr.p, size_t(std::min(n_blocks, 148)) * 64 * 8 * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+// ---- test hook: one ResBlock pair through the fused kernel and through two unfused tensor-core convs ------------
+// x: packed [sum(lens), C] fp32 (pre-activation); outputs are the stored (post-lrelu) values, packed the same way.
+extern "C" int sbv2_debug_pair_compare(const float* x, const int* lens, int n_utt, int C, int k, int dil, const float* w1,
+                                       const float* b1, const float* w2, const float* b2, int mrf, int iters, float* out_fused,
+                                       float* out_ref, float* out_ms /*[2]: fused, unfused*/, int* out_cfg /*[8]*/,
+                                       long long* out_trace /*[64*8] or null*/) {
+  using namespace sbv2;
+  return guarded([&] {
+    SBV2_REQUIRE(x && lens && n_utt > 0 && w1 && w2 && out_fused && out_ref, "bad arguments");
+    sbv2_model owner;
+    owner.device = 0;
+    CUDA_CHECK(cudaSetDevice(0));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&owner.stream, cudaStreamNonBlocking));
+    LaunchCtx ctx = owner.ctx();
+    HostConv h1, h2;
+    h1.d0 = h1.d1 = h2.d0 = h2.d1 = C;
+    h1.k = h2.k = k;
+    h1.w.assign(w1, w1 + size_t(C) * C * k);
+    h2.w.assign(w2, w2 + size_t(C) * C * k);
+    h1.b.assign(b1, b1 + C);
+    h2.b.assign(b2, b2 + C);
+    PairLayer P;
+    if (!make_pair_layer(&owner, h1, dil, h2, &P)) fail(SBV2_ERR_UNSUPPORTED, "pair does not fit the fused plan");
+    if (out_cfg) {
+      int cfg[8] = {P.mt, P.out_rows, P.a_slots, P.nstages, P.sps, P.b_resident, int(P.smem), P.nkc};
+      memcpy(out_cfg, cfg, sizeof(cfg));
+    }
+    ConvLayer L1 = make_conv1d_layer(&owner, h1, dil, 16);
+    ConvLayer L2 = make_conv1d_layer(&owner, h2, 1, 16);
+    std::vector<int> ystart, ylen;
+    int tot = 0;
+    for (int i = 0; i < n_utt; ++i) {
+      ystart.push_back(tot);
+      ylen.push_back(lens[i]);
+      tot += lens[i];
+    }
+    float* d_x = static_cast<float*>(owner.upload_bytes(x, size_t(tot) * C * 4));
+    DBuf meta, xin, mid, of, orf, ra, rb, back;
+    PinnedBuf pin;
+    for (DBuf* b : {&meta, &xin, &mid, &of, &orf, &ra, &rb, &back}) b->stream = owner.stream;
+    std::vector<int> muls{1};
+    std::vector<std::vector<int>> heights{{P.out_rows}};
+    BatchGeom bg = build_geoms(&owner, meta, pin, ystart, ylen, muls, &heights);
+    const Geom& G = bg.g[0];
+    const size_t bytes = size_t(G.rows_tot) * C * 2;
+    for (DBuf* b : {&xin, &mid, &of, &orf, &ra, &rb}) {
+      b->ensure(bytes);
+      launch_zero_gaps(ctx, b->as<__half>(), C, G, n_utt);
+    }
+    back.ensure(size_t(tot) * C * 4);
+    launch_to_planar(ctx, xin.as<__half>(), d_x, C, C, bg.d_ystart, G, n_utt, ACT_LRELU);
+    if (mrf) {  // two more "ResBlock outputs": scaled copies of the input
+      launch_to_planar(ctx, ra.as<__half>(), d_x, C, C, bg.d_ystart, G, n_utt, ACT_LRELU);
+      launch_to_planar(ctx, rb.as<__half>(), d_x, C, C, bg.d_ystart, G, n_utt, ACT_NONE);
+    }
+    auto run_fused = [&] {
+      PairCall pc;
+      pc.in = xin.as<__half>();
+      pc.out = of.as<__half>();
+      if (mrf) {
+        pc.residual2 = ra.as<__half>();
+        pc.residual3 = rb.as<__half>();
+        pc.out_div = 3.f;
+      }
+      launch_umma_pair(ctx, P, G, pc, n_utt);
+    };
+    auto run_unfused = [&] {
+      ConvCall c;
+      c.in = xin.as<__half>();
+      c.out = mid.as<__half>();
+      c.act_out = ACT_LRELU;
+      launch_umma(ctx, L1, G, G, c, n_utt);
+      ConvCall d;
+      d.in = mid.as<__half>();
+      d.residual = xin.as<__half>();
+      d.out = orf.as<__half>();
+      d.act_out = ACT_LRELU;
+      if (mrf) {
+        d.residual2 = ra.as<__half>();
+        d.residual3 = rb.as<__half>();
+        d.out_div = 3.f;
+      }
+      launch_umma(ctx, L2, G, G, d, n_utt);
+    };
+    run_fused();
+    run_unfused();
+    launch_from_planar(ctx, back.as<float>(), of.as<__half>(), C, bg.d_ystart, G, n_utt);
+    CUDA_CHECK(cudaMemcpyAsync(out_fused, back.p, size_t(tot) * C * 4, cudaMemcpyDeviceToHost, owner.stream));
+    CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+    launch_from_planar(ctx, back.as<float>(), orf.as<__half>(), C, bg.d_ystart, G, n_utt);
+    CUDA_CHECK(cudaMemcpyAsync(out_ref, back.p, size_t(tot) * C * 4, cudaMemcpyDeviceToHost, owner.stream));
+    CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+    if (iters > 0 && out_ms) {
+      cudaEvent_t e0, e1, e2;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventCreate(&e2));
+      CUDA_CHECK(cudaEventRecord(e0, owner.stream));
+      for (int i = 0; i < iters; ++i) run_fused();
+      CUDA_CHECK(cudaEventRecord(e1, owner.stream));
+      for (int i = 0; i < iters; ++i) run_unfused();
+      CUDA_CHECK(cudaEventRecord(e2, owner.stream));
+      CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+      CUDA_CHECK(cudaEventElapsedTime(&out_ms[0], e0, e1));
+      CUDA_CHECK(cudaEventElapsedTime(&out_ms[1], e1, e2));
+      out_ms[0] /= iters;
+      out_ms[1] /= iters;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      cudaEventDestroy(e2);
+    }
+    if (out_trace) {
+      DBuf tr;
+      tr.stream = owner.stream;
+      tr.ensure(64 * 8 * 8);
+      CUDA_CHECK(cudaMemsetAsync(tr.p, 0, 64 * 8 * 8, owner.stream));
+      g_pair_trace = tr.as<long long>();
+      run_fused();
+      g_pair_trace = nullptr;
+      CUDA_CHECK(cudaStreamSynchronize(owner.stream));
+      CUDA_CHECK(cudaMemcpy(out_trace, tr.p, 64 * 8 * 8, cudaMemcpyDeviceToHost));
+    }
   });
 }

@@ -1,0 +1,241 @@
+// Device-side helpers shared by the tcgen05 kernels (umma_conv.cu, umma_pair.cu): PTX wrappers for
+// mbarrier / bulk copy / tcgen05, shared-memory descriptors and the fused epilogue.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+#include "umma_conv.h"
+
+namespace sbv2 {
+namespace {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
+
+// SWIZZLE_NONE, K-major shared-memory matrix descriptor (sm_100 "version 1")
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// The MMAs of one conv tap: MT row tiles x K16 K-steps, fully unrolled.  With runtime trip counts the compiler
+// re-reads the kernel parameters (LDCU) and rebuilds the descriptors inside the loop, and that dependent chain —
+// not the tensor pipe — sets the issue rate (~90 cycles per MMA instead of the 45-64 the pipe accepts).
+template <int MT, int K16>
+__device__ __forceinline__ void issue_mmas(uint32_t tacc0, uint64_t a0, uint64_t b0, uint32_t a_kstep, uint32_t b_kstep,
+                                           uint32_t acc_stride, uint32_t idesc, uint32_t accf) {
+#pragma unroll
+  for (int a = 0; a < MT; ++a) {
+#pragma unroll
+    for (int k = 0; k < K16; ++k)
+      tc_mma_f16(tacc0 + (uint32_t)a * acc_stride, a0 + (uint32_t)(a * 128) + (uint32_t)k * a_kstep, b0 + (uint32_t)k * b_kstep, idesc,
+                 k == 0 ? accf : 1u);
+  }
+}
+// Warp-uniform dispatch on (mt, k16); call from the elected lane only.
+__device__ __forceinline__ void issue_mmas_dyn(int mt, int k16, uint32_t tacc0, uint64_t a0, uint64_t b0, uint32_t a_kstep,
+                                               uint32_t b_kstep, uint32_t acc_stride, uint32_t idesc, uint32_t accf) {
+#define SBV2_MMA_CASE(M, K)                                                          \
+  case (M) * 8 + (K):                                                                \
+    issue_mmas<M, K>(tacc0, a0, b0, a_kstep, b_kstep, acc_stride, idesc, accf);      \
+    break;
+  switch (mt * 8 + k16) {
+    SBV2_MMA_CASE(1, 1) SBV2_MMA_CASE(1, 2) SBV2_MMA_CASE(1, 4)
+    SBV2_MMA_CASE(2, 1) SBV2_MMA_CASE(2, 2) SBV2_MMA_CASE(2, 4)
+    SBV2_MMA_CASE(4, 1) SBV2_MMA_CASE(4, 2) SBV2_MMA_CASE(4, 4)
+    SBV2_MMA_CASE(8, 1) SBV2_MMA_CASE(8, 2) SBV2_MMA_CASE(8, 4)
+    SBV2_MMA_CASE(16, 1) SBV2_MMA_CASE(16, 2) SBV2_MMA_CASE(16, 4)
+    default:
+      for (int a = 0; a < mt; ++a)
+        for (int k = 0; k < k16; ++k)
+          tc_mma_f16(tacc0 + (uint32_t)a * acc_stride, a0 + (uint32_t)(a * 128) + (uint32_t)k * a_kstep, b0 + (uint32_t)k * b_kstep,
+                     idesc, k == 0 ? accf : 1u);
+  }
+#undef SBV2_MMA_CASE
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_LRELU) return fmaxf(v, v * 0.1f);
+  if (act == ACT_LRELU01) return fmaxf(v, v * 0.01f);
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+// Epilogue of NCH (16 or 32) accumulator columns of one row.  Compile-time variants keep the
+// per-element code branch-free: activation is max(v, slope*v) (slope 1 = none, 0 = relu, 0.1 / 0.01 =
+// leaky relu); GELU (DeBERTa FFN only) is the one runtime branch, taken per plane.
+template <int NCH, bool ACC, int RES, class Args>
+__device__ __forceinline__ void epilogue_item(const Args& p, uint32_t taddr, bool valid, long long orow, int co0_global,
+                                              const float* bias) {
+  constexpr int NPL = NCH / 8;
+  uint32_t v[NCH];
+#pragma unroll
+  for (int q = 0; q < NCH / 16; ++q) tc_ld16(taddr + 16 * q, v + 16 * q);
+  // issue the global loads this item needs while the TMEM load is in flight
+  uint4 r[RES ? NPL : 1];
+  uint4 r2[RES == 3 ? NPL : 1], r3[RES == 3 ? NPL : 1];
+  float4 s[ACC ? 2 * NPL : 1];
+  const long long eoff0 = ((long long)co0_global >> 3) * p.out_plane_stride + orow * 8;
+#pragma unroll
+  for (int pl = 0; pl < NPL; ++pl) {
+    const long long eoff = eoff0 + pl * p.out_plane_stride;
+    if (RES && valid) r[pl] = *reinterpret_cast<const uint4*>(p.residual + eoff);
+    if (RES == 3 && valid) {
+      r2[pl] = *reinterpret_cast<const uint4*>(p.residual2 + eoff);
+      r3[pl] = *reinterpret_cast<const uint4*>(p.residual3 + eoff);
+    }
+    if (ACC && valid && p.accum_mode >= UACC_ADD) {
+      const float4* sp = reinterpret_cast<const float4*>(p.accum + eoff);
+      s[2 * pl] = sp[0];
+      s[2 * pl + 1] = sp[1];
+    }
+  }
+  tc_wait_ld();
+  if (!valid) return;
+  const float slope = p.act_slope;
+  const bool gelu = p.act_out == ACT_GELU;
+#pragma unroll
+  for (int pl = 0; pl < NPL; ++pl) {
+    const long long eoff = eoff0 + pl * p.out_plane_stride;
+    float f[8];
+    const int co = 8 * pl;  // offset within this item
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + co), b1 = *reinterpret_cast<const float4*>(bias + co + 4);
+      f[0] = __uint_as_float(v[co + 0]) + b0.x; f[1] = __uint_as_float(v[co + 1]) + b0.y;
+      f[2] = __uint_as_float(v[co + 2]) + b0.z; f[3] = __uint_as_float(v[co + 3]) + b0.w;
+      f[4] = __uint_as_float(v[co + 4]) + b1.x; f[5] = __uint_as_float(v[co + 5]) + b1.y;
+      f[6] = __uint_as_float(v[co + 6]) + b1.z; f[7] = __uint_as_float(v[co + 7]) + b1.w;
+    }
+    if (RES) {
+      const __half2* rh = reinterpret_cast<const __half2*>(&r[pl]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 y = __half22float2(rh[e]);
+        f[2 * e] += fminf(y.x, y.x * 10.f);  // inverse of lrelu(0.1): x = y >= 0 ? y : 10 y
+        f[2 * e + 1] += fminf(y.y, y.y * 10.f);
+      }
+    }
+    if (RES == 3) {
+      const __half2* ra = reinterpret_cast<const __half2*>(&r2[pl]);
+      const __half2* rb = reinterpret_cast<const __half2*>(&r3[pl]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 ya = __half22float2(ra[e]), yb = __half22float2(rb[e]);
+        // (r0 + r1) + r2 as the graph sums the resblocks, then / n
+        const float s0 = fminf(ya.x, ya.x * 10.f) + fminf(yb.x, yb.x * 10.f);
+        const float s1 = fminf(ya.y, ya.y * 10.f) + fminf(yb.y, yb.y * 10.f);
+        f[2 * e] = (s0 + f[2 * e]) / p.out_div;
+        f[2 * e + 1] = (s1 + f[2 * e + 1]) / p.out_div;
+      }
+    }
+    if (ACC) {
+      if (p.act_on_accum) {
+        if (gelu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752440f));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], f[e] * slope);
+        }
+      }
+      float4* sp = reinterpret_cast<float4*>(p.accum + eoff);
+      if (p.accum_mode >= UACC_ADD) {
+        const float4 s0 = s[2 * pl], s1 = s[2 * pl + 1];
+        f[0] += s0.x; f[1] += s0.y; f[2] += s0.z; f[3] += s0.w;
+        f[4] += s1.x; f[5] += s1.y; f[6] += s1.z; f[7] += s1.w;
+      }
+      if (p.accum_mode != UACC_FINAL) {
+        sp[0] = make_float4(f[0], f[1], f[2], f[3]);
+        sp[1] = make_float4(f[4], f[5], f[6], f[7]);
+        continue;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] / p.accum_div;
+    }
+    if (p.out) {
+      if (gelu && !(ACC && p.act_on_accum)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752440f));
+      } else if (!(ACC && p.act_on_accum)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], f[e] * slope);
+      }
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+      *reinterpret_cast<uint4*>(p.out + eoff) = o;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace sbv2

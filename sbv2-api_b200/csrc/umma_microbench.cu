@@ -83,7 +83,119 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int layout, int
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// Variant with the other warps of the CTA generating the traffic of an epilogue while one thread issues MMAs:
+// noise bit 0: tcgen05.ld of other TMEM columns, bit 1: 16-byte st.shared, bit 2: 16-byte global loads.
+__global__ void __launch_bounds__(544, 1) mma_rate2_kernel(int n, int ra, int iters, int nacc, int noise, const uint4* gsrc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    done = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t sA = smem_u32(smem), sB = sA + 150 * 1024;
+      const uint32_t idesc = (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+      const uint64_t hi = (uint64_t)(0x4000u | 8u) << 32;
+      const uint64_t ad = hi | ((uint64_t)ra << 16) | ((sA >> 4) + 3);
+      const uint64_t bd = hi | ((uint64_t)n << 16) | (sB >> 4);
+      long long t0 = clock64();
+      if (noise & 8) {
+        // conv-like pattern: 11 taps x 8 row tiles, the tap shifts the A start by one row and selects another B block
+        for (int i = 0; i < iters; i += 88) {
+          for (int tap = 0; tap < 11; ++tap) {
+            const uint64_t at = ad + (uint64_t)tap, bt = bd + (uint64_t)(tap * 2 * n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) MMA(tmem + (uint32_t)(q * n), at + (uint64_t)(q * 128), bt, tap > 0 ? 1u : 0u);
+          }
+        }
+      } else {
+        for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t acc = tmem + (uint32_t)((q % nacc) * n);
+            MMA(acc, ad + (uint64_t)((q & 3) * 128), bd, i > 0 ? 1u : 0u);
+          }
+        }
+      }
+      long long t1 = clock64();
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      asm volatile(
+          "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n" ::"r"(
+              smem_u32(&bar))
+          : "memory");
+      long long t2 = clock64();
+      done = 1;
+      if (blockIdx.x == 0) {
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+      }
+    }
+  } else if (noise) {
+    uint32_t acc = 0;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + (uint32_t)((warp >> 2) * 16);
+    uint4* sdst = reinterpret_cast<uint4*>(smem + 160 * 1024) + threadIdx.x;
+    const uint4* g = gsrc + (size_t)blockIdx.x * 65536 + threadIdx.x;
+    int it = 0;
+    while (!done) {
+      if (noise & 1) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        acc += v[0] + v[15];
+      }
+      if (noise & 4) {
+        const uint4 q = g[(it & 63) * 1024];
+        acc += q.x;
+      }
+      if (noise & 2) *sdst = make_uint4(acc, acc, acc, acc);
+      ++it;
+    }
+    if (acc == 0x12345678u) out[1] = acc;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace
+
+extern "C" int sbv2_debug_mma_rate2(int n, int ra, int iters, int nacc, int blocks, int noise, long long* out2) {
+  return sbv2::guarded([&] {
+    CUDA_CHECK(cudaSetDevice(0));
+    CUDA_CHECK(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long* d = nullptr;
+    uint4* g = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, 16));
+    CUDA_CHECK(cudaMalloc(&g, size_t(blocks + 1) * 65536 * 16));
+    CUDA_CHECK(cudaMemset(g, 0, size_t(blocks + 1) * 65536 * 16));
+    mma_rate2_kernel<<<blocks, 544, 200 * 1024>>>(n, ra, iters, nacc, noise, g, d);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(g);
+  });
+}
 
 extern "C" int sbv2_debug_mma_rate(int n, int layout, int shift_rows, int iters, int nacc, int blocks, long long* out2) {
   return sbv2::guarded([&] {
