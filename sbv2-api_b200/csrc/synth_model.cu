@@ -15,6 +15,7 @@ struct ConvW {
   float* w = nullptr;  // [taps][Cin][Cout]
   float* b = nullptr;
   int cin = 0, cout = 0, k = 1;
+  int tc = -1;  // index into SynthModel::text_tc (split-fp16 tensor-core layer) or -1
 };
 struct LNW {
   float* g = nullptr;
@@ -127,6 +128,13 @@ struct SynthModel : sbv2_model {
   std::vector<std::vector<HostConv>> flow_host;  // consumed at create: per coupling [pre, post, (qkv, o, f1, f2) x L]
   DBuf fl_x0p, fl_hp, fl_qkvp, fl_ctxp, fl_f1p, fl_y32, fl_m32, fl_meta;
   PinnedBuf fl_pin;
+  // text encoder / duration predictor convs on the tensor cores with two-term fp16 splits (~fp32 accuracy)
+  std::vector<ConvLayer> text_tc;
+  std::vector<std::pair<ConvW*, HostConv>> text_host;  // consumed at create
+  bool use_tc_text = true;
+  int text_tc_max_cin = 0;
+  DBuf tx_split, tx_meta;
+  PinnedBuf tx_pin;
 
   uint64_t seed = 0x5b2b200ULL, rng_offset = 0;
   // workspaces
@@ -547,6 +555,36 @@ void load_weights(SynthModel& M, const OnnxModel& m) {
     if (bias) hc.b = L.f32(p + ".bias");
     return hc;
   };
+  {
+    // text-side convs that always run over the phoneme rows (candidates for the split-fp16 tensor-core path)
+    auto reg = [&](ConvW& c, HostConv hc) {
+      if (hc.d0 % 16 == 0 && hc.d1 % 16 == 0) M.text_host.emplace_back(&c, std::move(hc));
+    };
+    auto as_conv = [&](HostConv hc) {  // Linear [out, in] -> Conv1d k = 1
+      hc.k = std::max(hc.k, 1);
+      return hc;
+    };
+    reg(M.bert_proj, as_conv(host_conv("enc_p.bert_proj", true)));
+    reg(M.enc_proj, host_conv("enc_p.proj", true));
+    for (size_t l = 0; l < M.enc.layers.size(); ++l) {
+      std::string a = "enc_p.encoder.attn_layers." + std::to_string(l);
+      HostConv q = host_conv(a + ".conv_q", true), k = host_conv(a + ".conv_k", true), vv = host_conv(a + ".conv_v", true);
+      HostConv qkv;
+      qkv.d0 = q.d0 + k.d0 + vv.d0;
+      qkv.d1 = q.d1;
+      qkv.k = 1;
+      for (const HostConv* hc : {&q, &k, &vv}) {
+        qkv.w.insert(qkv.w.end(), hc->w.begin(), hc->w.end());
+        qkv.b.insert(qkv.b.end(), hc->b.begin(), hc->b.end());
+      }
+      reg(M.enc.layers[l].qkv, std::move(qkv));
+      reg(M.enc.layers[l].o, host_conv(a + ".conv_o", true));
+      reg(M.enc.layers[l].f1, host_conv("enc_p.encoder.ffn_layers." + std::to_string(l) + ".conv_1", true));
+      reg(M.enc.layers[l].f2, host_conv("enc_p.encoder.ffn_layers." + std::to_string(l) + ".conv_2", true));
+    }
+    reg(M.dp_c1, host_conv("dp.conv_1", true));
+    reg(M.dp_c2, host_conv("dp.conv_2", true));
+  }
   if (hp.transformer_flow) {
     for (int i = 0; i < hp.n_flows; ++i) {
       std::string p = "flow.flows." + std::to_string(2 * i);
@@ -621,9 +659,28 @@ enum WS { W_BERT = 0, W_H, W_QKV, W_CTX, W_Y, W_F1, W_STATS, W_G, W_STYLE, W_GG,
 struct Fwd {
   SynthModel& M;
   LaunchCtx ctx;
+  // split-fp16 tensor-core path for convs over the phoneme rows (set by synth_run when enabled)
+  const Geom* tg = nullptr;
+  const int* tg_start = nullptr;   // device: first packed row of each utterance
+  const int* tg_seg_start = nullptr;  // the Segs::start the geometry was built for
+  __half* tg_split = nullptr;
+  int tg_n = 0;
 
   void conv(const ConvW& c, const float* in, int in_ld, float* out, int out_ld, const Segs& seg, int dil = 1, int act_in = ACT_NONE,
             int act_out = ACT_NONE, const float* residual = nullptr, const float* bias_utt = nullptr) {
+    if (c.tc >= 0 && tg != nullptr && seg.start == tg_seg_start && residual == nullptr && act_in == ACT_NONE && dil == 1 &&
+        (act_out == ACT_NONE || act_out == ACT_RELU) && out_ld % 4 == 0) {
+      launch_split_planar(ctx, tg_split, in, in_ld, c.cin, tg_start, *tg, tg_n);
+      ConvCall cc;
+      cc.in = tg_split;
+      cc.rm_out = out;
+      cc.rm_ld = out_ld;
+      cc.rm_start = tg_start;
+      cc.act_out = act_out;
+      cc.bias_utt = bias_utt;
+      launch_umma(ctx, M.text_tc[c.tc], *tg, *tg, cc, tg_n);
+      return;
+    }
     ConvArgs a;
     a.in = in;
     a.in_ld = in_ld;
@@ -769,6 +826,19 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
     }
   }
   M->flow_host.clear();
+  // SBV2_B200_TEXT=fp32 keeps the text encoder / duration predictor convs on the CUDA-core fp32 kernel.
+  const char* tenv = getenv("SBV2_B200_TEXT");
+  M->use_tc_text = !(tenv && std::string(tenv) == "fp32");
+  if (M->use_tc_text) {
+    for (auto& e : M->text_host) {
+      e.first->tc = int(M->text_tc.size());
+      M->text_tc.push_back(make_split_conv1d_layer(M.get(), e.second, 1, 1));
+      M->text_tc_max_cin = std::max(M->text_tc_max_cin, e.second.d1);
+    }
+    M->tx_split.stream = M->stream;
+    M->tx_meta.stream = M->stream;
+  }
+  M->text_host.clear();
   CUDA_CHECK(cudaStreamSynchronize(M->stream));
   return M.release();
 }
@@ -1113,6 +1183,19 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
 
   // ---- speaker embedding, text encoder ------------------------------------------------------
   M.region_begin("text");
+  BatchGeom tbg;
+  if (M.use_tc_text && !M.text_tc.empty()) {
+    std::vector<int> muls(1, 1);
+    tbg = build_geoms(&M, M.tx_meta, M.tx_pin, b->xstart, b->xlen, muls);
+    const Geom& TG = tbg.g[0];
+    M.tx_split.ensure(size_t(TG.rows_tot) * 3 * M.text_tc_max_cin * 2);
+    F.tg = &TG;
+    F.tg_start = tbg.d_ystart;
+    F.tg_seg_start = xseg.start;
+    F.tg_split = M.tx_split.as<__half>();
+    F.tg_n = B;
+    launch_zero_gaps(ctx, F.tg_split, 3 * M.text_tc_max_cin, TG, B);  // the splits only ever write utterance rows
+  }
   launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
   launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_bert), reinterpret_cast<const int64_t*>(in + b->o_bert_off),
                   nullptr, bert, hp.bert_dim, xseg);

@@ -73,6 +73,9 @@ struct UmmaConvArgs {
   float accum_div;
   int tmem_cols;
   unsigned idesc;
+  float* rm_out;        // fp32 row-major output (or null)
+  int rm_ld;
+  const int* rm_start;
   long long* trace;  // debug: [grid][64 items][8 events] clock64 stamps, or null
 };
 
@@ -208,66 +211,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       const uint64_t a_desc0 = desc_hi | ((uint64_t)((uint32_t)RA & 0x3FFF) << 16);    // LBO = RA*16 B
       const uint64_t b_desc0 = desc_hi | ((uint64_t)((uint32_t)p.nb & 0x3FFF) << 16);  // LBO = NB*16 B
       const uint32_t a_kstep = 2u * (uint32_t)RA, b_kstep = 2u * (uint32_t)p.nb;       // two planes per K=16 step (16-B units)
-      const int mt = p.mt;
       const uint32_t nb_u = (uint32_t)p.nb, idesc = p.idesc;
-      uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0, it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        mbar_wait(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
-        tc_fence_after();
-        if (lane == 0) TRACE(2, it);
-        const uint32_t tmem_acc = tmem_base + buf * acc_cols;
-        const int grp = (item % (p.n_nblk * p.n_groups)) / p.n_nblk;
-        int step = 0, si = 0;
-        for (int kc = 0; kc < p.nkc; ++kc) {
-          mbar_wait(bar_af + 8 * a_slot_i, a_par);
-          if (kc == 0 && lane == 0) TRACE(3, it);
-          const uint64_t a_chunk = a_desc0 + ((sA + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
-          for (int tap = 0; tap < p.taps; ++tap, ++step) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              if (it == 0 && step == 0) mbar_wait(bar_bf, 0);
-              b_addr = sB + step_bytes * step;
-            } else {
-              if (si == 0) mbar_wait(bar_bf + 8 * b_st, b_par);
-              b_addr = sB + stage_bytes * b_st + step_bytes * si;
-            }
-            const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
-            const uint64_t b_d = b_desc0 + (b_addr >> 4);
-            const uint32_t accf = step > 0 ? 1u : 0u;
-            if (elect_one_sync()) issue_mmas_dyn(mt, k16_per_chunk, tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
-            __syncwarp();
-            if (!p.b_resident) {
-              ++si;
-              if (si == p.sps || step == p.total_steps - 1) {
-                if (elect_one_sync()) tc_commit(bar_be + 8 * b_st);
-                __syncwarp();
-                si = 0;
-                if (++b_st == (uint32_t)p.nstages) {
-                  b_st = 0;
-                  b_par ^= 1;
+      const bool leader = elect_one_sync() != 0;  // the same lane issues every MMA / commit of this CTA
+      // MT / K16 are compile-time (dispatched once, below): a per-tap switch or elect costs ~140 cycles per tap, which
+      // the tensor pipe does not hide — it starts each MMA as it is issued (umma_microbench.cu, "issue shape")
+      auto run = [&](auto mtk) {
+        constexpr int MT = decltype(mtk)::mt, K16 = decltype(mtk)::k16;
+        uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0, it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+          const uint32_t buf = it & 1;
+          mbar_wait(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
+          tc_fence_after();
+          if (lane == 0) TRACE(2, it);
+          const uint32_t tmem_acc = tmem_base + buf * acc_cols;
+          const int grp = (item % (p.n_nblk * p.n_groups)) / p.n_nblk;
+          int step = 0, si = 0;
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            mbar_wait(bar_af + 8 * a_slot_i, a_par);
+            if (kc == 0 && lane == 0) TRACE(3, it);
+            const uint64_t a_chunk = a_desc0 + ((sA + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
+            for (int tap = 0; tap < p.taps; ++tap, ++step) {
+              uint32_t b_addr;
+              if (p.b_resident) {
+                if (it == 0 && step == 0) mbar_wait(bar_bf, 0);
+                b_addr = sB + step_bytes * step;
+              } else {
+                if (si == 0) mbar_wait(bar_bf + 8 * b_st, b_par);
+                b_addr = sB + stage_bytes * b_st + step_bytes * si;
+              }
+              const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
+              const uint64_t b_d = b_desc0 + (b_addr >> 4);
+              const uint32_t accf = step > 0 ? 1u : 0u;
+              if (leader) issue_mmas<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
+              if (!p.b_resident) {
+                ++si;
+                if (si == p.sps || step == p.total_steps - 1) {
+                  if (leader) tc_commit(bar_be + 8 * b_st);
+                  si = 0;
+                  if (++b_st == (uint32_t)p.nstages) {
+                    b_st = 0;
+                    b_par ^= 1;
+                  }
                 }
               }
             }
+            if (leader) tc_commit(bar_ae + 8 * a_slot_i);
+            if (++a_slot_i == (uint32_t)p.a_slots) {
+              a_slot_i = 0;
+              a_par ^= 1;
+            }
           }
-          if (elect_one_sync()) tc_commit(bar_ae + 8 * a_slot_i);
+          if (leader) tc_commit(bar_accf + 8 * buf);
           __syncwarp();
-          if (++a_slot_i == (uint32_t)p.a_slots) {
-            a_slot_i = 0;
-            a_par ^= 1;
-          }
+          if (lane == 0) TRACE(4, it);
         }
-        if (elect_one_sync()) tc_commit(bar_accf + 8 * buf);
-        __syncwarp();
-        if (lane == 0) TRACE(4, it);
+      };
+#define SBV2_ROLE_CASE(M, K) \
+  case (M) * 8 + (K):        \
+    run(MtK<M, K>{});        \
+    break;
+      switch (p.mt * 8 + k16_per_chunk) {
+        SBV2_ROLE_CASE(1, 1) SBV2_ROLE_CASE(1, 2) SBV2_ROLE_CASE(1, 3) SBV2_ROLE_CASE(1, 4)
+        SBV2_ROLE_CASE(2, 1) SBV2_ROLE_CASE(2, 2) SBV2_ROLE_CASE(2, 3) SBV2_ROLE_CASE(2, 4)
+        SBV2_ROLE_CASE(4, 1) SBV2_ROLE_CASE(4, 2) SBV2_ROLE_CASE(4, 3) SBV2_ROLE_CASE(4, 4)
+        SBV2_ROLE_CASE(8, 1) SBV2_ROLE_CASE(8, 2) SBV2_ROLE_CASE(8, 3) SBV2_ROLE_CASE(8, 4)
+        SBV2_ROLE_CASE(16, 1) SBV2_ROLE_CASE(16, 2) SBV2_ROLE_CASE(16, 3) SBV2_ROLE_CASE(16, 4)
+        default: __trap();  // make_layer only produces the combinations above (kc in {16, 32, 48, 64})
       }
+#undef SBV2_ROLE_CASE
     }
   } else {
     // ---------------- epilogue warps ----------------
     const int wq = warp & 3;           // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;  // NUM_EPI_WARPS/4 warps per quarter split the work items
     const int etid = threadIdx.x - 64;
-    const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE && p.has_res != 3;
+    const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE && p.has_res != 3 && p.rm_out == nullptr;
     const int nch = wide ? 32 : 16;
     const int items_per_acc = p.nb / nch;
     const int n_sub = p.mt * items_per_acc;
@@ -299,7 +317,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off + p.group_out_off[ti.grp];
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
         const int cg = ti.nblk * p.nb + c0;
-        if (p.accum_mode != UACC_NONE) {
+        if (p.rm_out != nullptr) {
+          epilogue_item_rm(p, taddr, valid, (long long)p.rm_start[ti.b] + t, cg, bias + c0);
+        } else if (p.accum_mode != UACC_NONE) {
           if (p.has_res) epilogue_item<16, true, 1>(p, taddr, valid, orow, cg, bias + c0);
           else epilogue_item<16, true, 0>(p, taddr, valid, orow, cg, bias + c0);
         } else if (p.has_res == 3) {
@@ -327,6 +347,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
 }
 
 // ---- glue kernels ----------------------------------------------------------------------------------
+// packed fp32 -> planar fp16 two-term split [hi | lo | hi]: hi = fp16(x), lo = fp16(x - hi)
+__global__ void split_planar_kernel(__half* out, long long plane_stride, const float* in, int in_ld, int C, const int* start,
+                                    const int* pstart, const int* len) {
+  int b = blockIdx.y;
+  int t = blockIdx.x * blockDim.y + threadIdx.y;
+  if (t >= len[b]) return;
+  const float* row = in + (size_t)(start[b] + t) * in_ld;
+  const int npl = C / 8;
+  for (int pl = threadIdx.x; pl < npl; pl += blockDim.x) {
+    uint4 oh, ol;
+    __half2* hh = reinterpret_cast<__half2*>(&oh);
+    __half2* hl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = row[pl * 8 + 2 * e], x1 = row[pl * 8 + 2 * e + 1];
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      hh[e] = h;
+      hl[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    }
+    const size_t r8 = (size_t)(pstart[b] + t) * 8;
+    *reinterpret_cast<uint4*>(out + (size_t)pl * plane_stride + r8) = oh;
+    *reinterpret_cast<uint4*>(out + (size_t)(npl + pl) * plane_stride + r8) = ol;
+    *reinterpret_cast<uint4*>(out + (size_t)(2 * npl + pl) * plane_stride + r8) = oh;
+  }
+}
+
 // packed fp32 [rows, in_ld] (utterance b at rows start[b]..) -> planar fp16 with gaps
 __global__ void to_planar_kernel(__half* out, long long plane_stride, const float* in, int in_ld, int C, const int* start,
                                  const int* pstart, const int* len, int act) {
@@ -515,6 +562,27 @@ ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int m
                     [=](int, int co, int ci, int tap) { return w[(size_t(co) * cin + ci) * k + tap]; }, mt_pref);
 }
 
+ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref) {
+  // [Cout][3*Cin][k]: input planes [hi | lo | hi] meet weights [whi | whi | wlo]
+  HostConv s3;
+  s3.d0 = c.d0;
+  s3.d1 = 3 * c.d1;
+  s3.k = c.k;
+  s3.b = c.b;
+  s3.w.resize(size_t(s3.d0) * s3.d1 * s3.k);
+  for (int co = 0; co < c.d0; ++co)
+    for (int ci = 0; ci < c.d1; ++ci)
+      for (int j = 0; j < c.k; ++j) {
+        const float w = c.w[(size_t(co) * c.d1 + ci) * c.k + j];
+        const float whi = __half2float(__float2half_rn(w));
+        const float wlo = __half2float(__float2half_rn(w - whi));
+        s3.w[(size_t(co) * s3.d1 + ci) * c.k + j] = whi;
+        s3.w[(size_t(co) * s3.d1 + c.d1 + ci) * c.k + j] = whi;
+        s3.w[(size_t(co) * s3.d1 + 2 * c.d1 + ci) * c.k + j] = wlo;
+      }
+  return make_conv1d_layer(owner, s3, dil, mt_pref);
+}
+
 ConvLayer make_upsample_layer(sbv2_model* owner, const HostConv& c, int u, int mt_pref) {
   // out[u*q + r] = bias + sum_m sum_ci w[ci][co][rr + u*m] * in[q + cc - m],  s = r + pad, rr = s % u, cc = s / u
   const int k = c.k, pad = (k - u) / 2, taps = k / u;
@@ -588,6 +656,9 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.accum_div = c.accum_div;
   a.tmem_cols = L.tmem_cols;
   a.idesc = L.idesc;
+  a.rm_out = c.rm_out;
+  a.rm_ld = c.rm_ld;
+  a.rm_start = c.rm_start;
   a.trace = g_trace;
   if (gi.n_tiles[slot] <= 0) return;
   a.n_items = gi.n_tiles[slot] * L.n_nblk * L.n_groups;
@@ -691,6 +762,15 @@ void launch_to_planar(const LaunchCtx& ctx, __half* out, const float* in, int in
   dim3 block(std::min(32, C / 8), 8);
   dim3 grid((g.max_len + 7) / 8, n_utt);
   to_planar_kernel<<<grid, block, 0, ctx.stream>>>(out, g.rows_tot * 8, in, in_ld, C, d_start, g.d_pstart, g.d_len, act);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+void launch_split_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
+                         int n_utt) {
+  dim3 block(std::min(32, C / 8), 8);
+  dim3 grid((g.max_len + 7) / 8, n_utt);
+  split_planar_kernel<<<grid, block, 0, ctx.stream>>>(out, g.rows_tot * 8, in, in_ld, C, d_start, g.d_pstart, g.d_len);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -80,6 +80,13 @@ struct PinnedBuf;
 BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::vector<int>& ystart, const std::vector<int>& ylen,
                       const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights = nullptr);
 
+// Conv1d evaluated to ~fp32 accuracy on the fp16 tensor cores: x = hi + lo (two fp16 terms), w = whi + wlo, and
+// x*w ~ hi*whi + lo*whi + hi*wlo (the dropped lo*wlo term is 2^-22 relative).  The layer has 3*Cin input channels; its
+// input is the planar tensor [hi | lo | hi] written by launch_split_planar.
+ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref);
+// packed fp32 [rows, in_ld] (first C columns) -> planar fp16 [hi | lo | hi] (3*C channels); gap rows are not written
+void launch_split_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
+                         int n_utt);
 enum UAccum { UACC_NONE = 0, UACC_SET = 1, UACC_ADD = 2, UACC_FINAL = 3 };
 struct ConvCall {
   const __half* in = nullptr;
@@ -95,6 +102,11 @@ struct ConvCall {
   bool act_on_accum = false;      // apply act_out before the fp32 accumulate/store instead of on the fp16 output
   const float* bias_utt = nullptr;
   int out_mul = 1, out_off = 0;
+  // fp32 row-major output [packed rows, rm_ld] instead of the planar ones (text encoder): packed row = rm_start[b] + t;
+  // act_out ACT_NONE / ACT_RELU only
+  float* rm_out = nullptr;
+  int rm_ld = 0;
+  const int* rm_start = nullptr;
 };
 void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt);
 void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, int n_utt);

@@ -85,6 +85,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+template <int MT, int K16>
+struct MtK {  // compile-time (row tiles, K steps) tag for the MMA role
+  static constexpr int mt = MT, k16 = K16;
+};
+
 // The MMAs of one conv tap: MT row tiles x K16 K-steps, fully unrolled.  With runtime trip counts the compiler
 // re-reads the kernel parameters (LDCU) and rebuilds the descriptors inside the loop, and that dependent chain —
 // not the tensor pipe — sets the issue rate (~90 cycles per MMA instead of the 45-64 the pipe accepts).
@@ -234,6 +239,26 @@ __device__ __forceinline__ void epilogue_item(const Args& p, uint32_t taddr, boo
       for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
       *reinterpret_cast<uint4*>(p.out + eoff) = o;
     }
+  }
+}
+
+// fp32 row-major epilogue of 16 accumulator columns of one row: out[row][co0 .. co0+15] = act(acc + bias)
+template <class Args>
+__device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, bool valid, long long rm_row, int co0_global,
+                                                 const float* bias) {
+  uint32_t v[16];
+  tc_ld16(taddr, v);
+  tc_wait_ld();
+  if (!valid) return;
+  float* dst = p.rm_out + rm_row * p.rm_ld + co0_global;
+  const bool relu = p.act_out == ACT_RELU;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+    float4 f = make_float4(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y, __uint_as_float(v[4 * q + 2]) + b.z,
+                           __uint_as_float(v[4 * q + 3]) + b.w);
+    if (relu) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
+    *reinterpret_cast<float4*>(dst + 4 * q) = f;
   }
 }
 

@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "model.h"
@@ -205,12 +206,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       if (b_si == 0) mbar_wait(bar_bf + 8 * b_st, b_par);
       return sB + stage_bytes * b_st + step_bytes * b_si;
     };
+    const bool leader = elect_one_sync() != 0;  // the same lane issues every MMA / commit of this CTA
     auto b_step_done = [&](int step) {
       if (p.b_resident) return;
       ++b_si;
       if (b_si == p.sps || step == p.total_steps - 1) {
-        if (elect_one_sync()) tc_commit(bar_be + 8 * b_st);
-        __syncwarp();
+        if (leader) tc_commit(bar_be + 8 * b_st);
         b_si = 0;
         if (++b_st == (uint32_t)p.nstages) {
           b_st = 0;
@@ -218,7 +219,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
         }
       }
     };
-    auto issue_p1 = [&](int it) {
+    // MT / K16 are compile-time (dispatched once, below): a per-tap switch or elect costs ~140 cycles per tap, which the
+    // tensor pipe does not hide — it starts each MMA as it is issued (umma_microbench.cu, "issue shape")
+    auto issue_p1 = [&](int it, auto mtk) {
+      constexpr int MT = decltype(mtk)::mt, K16 = decltype(mtk)::k16;
       const uint32_t buf = it & 1;
       mbar_wait(bar_a1e + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue-1 of item it-2 has drained this set
       tc_fence_after();
@@ -233,22 +237,21 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
           const uint64_t a_tap = a_chunk + (int64_t)p.shift1[tap];
           const uint64_t b_d = b_desc0 + (b_addr >> 4);
           const uint32_t accf = step > 0 ? 1u : 0u;
-          if (elect_one_sync()) issue_mmas_dyn(mt, k16, tacc0, a_tap, b_d, a_kstep, b_kstep, c_u, idesc, accf);
-          __syncwarp();
+          if (leader) issue_mmas<MT, K16>(tacc0, a_tap, b_d, a_kstep, b_kstep, c_u, idesc, accf);
           b_step_done(step);
         }
-        if (elect_one_sync()) tc_commit(bar_ae + 8 * a_slot_i);
-        __syncwarp();
+        if (leader) tc_commit(bar_ae + 8 * a_slot_i);
         if (++a_slot_i == (uint32_t)p.a_slots) {
           a_slot_i = 0;
           a_par ^= 1;
         }
       }
-      if (elect_one_sync()) tc_commit(bar_a1f + 8 * buf);
+      if (leader) tc_commit(bar_a1f + 8 * buf);
       __syncwarp();
       if (lane == 0) PTRACE(1, it);
     };
-    auto issue_p2 = [&](int it) {
+    auto issue_p2 = [&](int it, auto mtk) {
+      constexpr int MT = decltype(mtk)::mt, K16 = decltype(mtk)::k16;
       const uint32_t buf = it & 1;
       mbar_wait(bar_a2e + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue-2 of item it-2 has drained this set
       mbar_wait(bar_t1r + 8 * buf, (it >> 1) & 1);         // t1 tile written and visible to the async proxy
@@ -264,22 +267,29 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
           const uint64_t t_tap = t_chunk + (uint32_t)tap;  // out row m, tap j reads t1 row m + j
           const uint64_t b_d = b_desc0 + (b_addr >> 4);
           const uint32_t accf = step > 0 ? 1u : 0u;
-          if (elect_one_sync()) issue_mmas_dyn(mt, k16, tacc0, t_tap, b_d, t_kstep, b_kstep, c_u, idesc, accf);
-          __syncwarp();
+          if (leader) issue_mmas<MT, K16>(tacc0, t_tap, b_d, t_kstep, b_kstep, c_u, idesc, accf);
           b_step_done(step);
         }
       }
-      if (elect_one_sync()) {
+      if (leader) {
         tc_commit(bar_a2f + 8 * buf);
         tc_commit(bar_t1f + 8 * buf);
       }
       __syncwarp();
       if (lane == 0) PTRACE(3, it);
     };
-    if (n_my > 0) issue_p1(0);
-    for (int it = 0; it < n_my; ++it) {
-      if (it + 1 < n_my) issue_p1(it + 1);
-      issue_p2(it);
+    auto run = [&](auto mtk) {
+      if (n_my > 0) issue_p1(0, mtk);
+      for (int it = 0; it < n_my; ++it) {
+        if (it + 1 < n_my) issue_p1(it + 1, mtk);
+        issue_p2(it, mtk);
+      }
+    };
+    switch (mt * 8 + k16) {  // (128 / C, min(C, 64) / 16)
+      case 8 * 8 + 1: run(MtK<8, 1>{}); break;
+      case 4 * 8 + 2: run(MtK<4, 2>{}); break;
+      case 2 * 8 + 4: run(MtK<2, 4>{}); break;
+      default: run(MtK<1, 4>{}); break;
     }
   } else {
     // ---------------- epilogue warps ----------------
@@ -517,7 +527,11 @@ void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, c
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  umma_pair_kernel<<<std::min(a.n_items, num_sms), P_THREADS, L.smem, ctx.stream>>>(a);
+  int grid = std::min(a.n_items, num_sms);
+  if (g_pair_trace != nullptr) {
+    if (const char* e = getenv("SBV2_B200_PAIR_GRID")) grid = std::max(1, std::min(grid, atoi(e)));  // debugging: fewer CTAs
+  }
+  umma_pair_kernel<<<grid, P_THREADS, L.smem, ctx.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -94,6 +94,10 @@ def run(lens, c, k, dil, mrf=0, iters=0, seed=0, check_np=True, trace=False):
 if __name__ == "__main__":
     perf = len(sys.argv) > 1 and sys.argv[1] == "perf"
     if len(sys.argv) > 1 and sys.argv[1] == "trace":
+        if os.environ.get("SBV2_B200_PAIR_GRID"):
+            run([1014 * 60], 16, 11, 5, iters=0, check_np=False, trace=True)
+            run([246 * 60], 64, 11, 5, iters=0, check_np=False, trace=True)
+            sys.exit(0)
         for c, mul in ((64, 128), (32, 256), (16, 512)):
             for k, d in ((3, 1), (11, 5)):
                 run([860 * mul] * 32, c, k, d, iters=3, check_np=False, trace=True)
