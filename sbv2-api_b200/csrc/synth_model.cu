@@ -132,6 +132,7 @@ struct SynthModel : sbv2_model {
   std::vector<ConvLayer> text_tc;
   std::vector<std::pair<ConvW*, HostConv>> text_host;  // consumed at create
   bool use_tc_text = true;
+  int text_terms = 2;  // fp16 terms per operand (2: 3 cross products, 3: 6 cross products)
   int text_tc_max_cin = 0;
   DBuf tx_split, tx_meta;
   PinnedBuf tx_pin;
@@ -670,7 +671,7 @@ struct Fwd {
             int act_out = ACT_NONE, const float* residual = nullptr, const float* bias_utt = nullptr) {
     if (c.tc >= 0 && tg != nullptr && seg.start == tg_seg_start && residual == nullptr && act_in == ACT_NONE && dil == 1 &&
         (act_out == ACT_NONE || act_out == ACT_RELU) && out_ld % 4 == 0) {
-      launch_split_planar(ctx, tg_split, in, in_ld, c.cin, tg_start, *tg, tg_n);
+      launch_split_planar(ctx, tg_split, in, in_ld, c.cin, tg_start, *tg, tg_n, M.text_terms, M.text_tc[c.tc].in_scale);
       ConvCall cc;
       cc.in = tg_split;
       cc.rm_out = out;
@@ -785,17 +786,21 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
   const char* fenv = getenv("SBV2_B200_FLOW");
   M->use_tc_flow = M->hp.transformer_flow && !(fenv && std::string(fenv) == "fp32") && M->hp.hidden % 16 == 0 &&
                    M->hp.hidden / 8 <= 32 && (M->hp.inter / 2) % 16 == 0;
+  // SBV2_B200_FLOW_NB: largest N block of the flow / text convs.  128 (256-row work items, half the weight bytes per
+  // row from L2) measured slower than 256 on the bench workload (flow 7.8 vs 7.1 ms): more items, narrower MMAs.
+  int flow_nb = 256;
+  if (const char* e = getenv("SBV2_B200_FLOW_NB")) flow_nb = atoi(e);
   if (M->use_tc_flow) {
     for (auto& v : M->flow_host) {
       FlowTC f;
-      f.pre = make_conv1d_layer(M.get(), v[0], 1, 2);
-      f.post = make_conv1d_layer(M.get(), v[1], 1, 2);
+      f.pre = make_conv1d_layer(M.get(), v[0], 1, 2, flow_nb);
+      f.post = make_conv1d_layer(M.get(), v[1], 1, 2, flow_nb);
       for (size_t l = 0; 2 + 4 * l + 3 < v.size(); ++l) {
         FlowTCLayer fl;
-        fl.qkv = make_conv1d_layer(M.get(), v[2 + 4 * l], 1, 2);
-        fl.o = make_conv1d_layer(M.get(), v[3 + 4 * l], 1, 2);
-        fl.f1 = make_conv1d_layer(M.get(), v[4 + 4 * l], 1, 2);
-        fl.f2 = make_conv1d_layer(M.get(), v[5 + 4 * l], 1, 2);
+        fl.qkv = make_conv1d_layer(M.get(), v[2 + 4 * l], 1, 2, flow_nb);
+        fl.o = make_conv1d_layer(M.get(), v[3 + 4 * l], 1, 2, flow_nb);
+        fl.f1 = make_conv1d_layer(M.get(), v[4 + 4 * l], 1, 2, flow_nb);
+        fl.f2 = make_conv1d_layer(M.get(), v[5 + 4 * l], 1, 2, flow_nb);
         f.layers.push_back(fl);
       }
       M->flow_tc.push_back(std::move(f));
@@ -826,13 +831,16 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
     }
   }
   M->flow_host.clear();
-  // SBV2_B200_TEXT=fp32 keeps the text encoder / duration predictor convs on the CUDA-core fp32 kernel.
+  // SBV2_B200_TEXT=fp32 keeps the text encoder / duration predictor convs on the CUDA-core fp32 kernel; =split3 uses
+  // three fp16 terms per operand.  Measured against the oracle both splits give the same error (enc_x 1e-5 relative,
+  // 3x the CUDA-core kernel's): the tensor core's fp32 accumulation, not the operand split, sets it.
   const char* tenv = getenv("SBV2_B200_TEXT");
   M->use_tc_text = !(tenv && std::string(tenv) == "fp32");
+  M->text_terms = (tenv && std::string(tenv) == "split3") ? 3 : 2;
   if (M->use_tc_text) {
     for (auto& e : M->text_host) {
       e.first->tc = int(M->text_tc.size());
-      M->text_tc.push_back(make_split_conv1d_layer(M.get(), e.second, 1, 1));
+      M->text_tc.push_back(make_split_conv1d_layer(M.get(), e.second, 1, 2, M->text_terms, flow_nb));
       M->text_tc_max_cin = std::max(M->text_tc_max_cin, e.second.d1);
     }
     M->tx_split.stream = M->stream;
@@ -1188,13 +1196,14 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     std::vector<int> muls(1, 1);
     tbg = build_geoms(&M, M.tx_meta, M.tx_pin, b->xstart, b->xlen, muls);
     const Geom& TG = tbg.g[0];
-    M.tx_split.ensure(size_t(TG.rows_tot) * 3 * M.text_tc_max_cin * 2);
+    const int nblk = M.text_terms == 3 ? 6 : 3;
+    M.tx_split.ensure(size_t(TG.rows_tot) * nblk * M.text_tc_max_cin * 2);
     F.tg = &TG;
     F.tg_start = tbg.d_ystart;
     F.tg_seg_start = xseg.start;
     F.tg_split = M.tx_split.as<__half>();
     F.tg_n = B;
-    launch_zero_gaps(ctx, F.tg_split, 3 * M.text_tc_max_cin, TG, B);  // the splits only ever write utterance rows
+    launch_zero_gaps(ctx, F.tg_split, nblk * M.text_tc_max_cin, TG, B);  // the splits only ever write utterance rows
   }
   launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
   launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_bert), reinterpret_cast<const int64_t*>(in + b->o_bert_off),

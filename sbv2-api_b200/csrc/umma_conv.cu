@@ -74,6 +74,7 @@ struct UmmaConvArgs {
   int tmem_cols;
   unsigned idesc;
   float* rm_out;        // fp32 row-major output (or null)
+  float rm_scale;       // accumulator scale of the row-major epilogue
   int rm_ld;
   const int* rm_start;
   long long* trace;  // debug: [grid][64 items][8 events] clock64 stamps, or null
@@ -347,33 +348,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
 }
 
 // ---- glue kernels ----------------------------------------------------------------------------------
-// packed fp32 -> planar fp16 two-term split [hi | lo | hi]: hi = fp16(x), lo = fp16(x - hi)
+// packed fp32 -> planar fp16 split.  TERMS = 2: x ~ h0 + h1, planes [h0 | h1 | h0]; TERMS = 3: x ~ h0 + h1 + h2,
+// planes [h0 | h1 | h2 | h0 | h1 | h0] (h0 = fp16(x), h1 = fp16(x - h0), h2 = fp16(x - h0 - h1))
+template <int TERMS>
 __global__ void split_planar_kernel(__half* out, long long plane_stride, const float* in, int in_ld, int C, const int* start,
-                                    const int* pstart, const int* len) {
+                                    const int* pstart, const int* len, float in_scale) {
   int b = blockIdx.y;
   int t = blockIdx.x * blockDim.y + threadIdx.y;
   if (t >= len[b]) return;
   const float* row = in + (size_t)(start[b] + t) * in_ld;
   const int npl = C / 8;
   for (int pl = threadIdx.x; pl < npl; pl += blockDim.x) {
-    uint4 oh, ol;
-    __half2* hh = reinterpret_cast<__half2*>(&oh);
-    __half2* hl = reinterpret_cast<__half2*>(&ol);
+    uint4 o0, o1, o2;
+    __half2* q0 = reinterpret_cast<__half2*>(&o0);
+    __half2* q1 = reinterpret_cast<__half2*>(&o1);
+    __half2* q2 = reinterpret_cast<__half2*>(&o2);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float x0 = row[pl * 8 + 2 * e], x1 = row[pl * 8 + 2 * e + 1];
-      const __half2 h = __floats2half2_rn(x0, x1);
-      const float2 hf = __half22float2(h);
-      hh[e] = h;
-      hl[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      const float x0 = row[pl * 8 + 2 * e] * in_scale, x1 = row[pl * 8 + 2 * e + 1] * in_scale;  // power of two: exact
+      const __half2 h0 = __floats2half2_rn(x0, x1);
+      const float2 f0 = __half22float2(h0);
+      const float r0 = x0 - f0.x, r1 = x1 - f0.y;  // exact
+      const __half2 h1 = __floats2half2_rn(r0, r1);
+      const float2 f1 = __half22float2(h1);
+      q0[e] = h0;
+      q1[e] = h1;
+      q2[e] = __floats2half2_rn(r0 - f1.x, r1 - f1.y);
     }
     const size_t r8 = (size_t)(pstart[b] + t) * 8;
-    *reinterpret_cast<uint4*>(out + (size_t)pl * plane_stride + r8) = oh;
-    *reinterpret_cast<uint4*>(out + (size_t)(npl + pl) * plane_stride + r8) = ol;
-    *reinterpret_cast<uint4*>(out + (size_t)(2 * npl + pl) * plane_stride + r8) = oh;
+    __half* base = out + (size_t)pl * plane_stride + r8;
+    const size_t blk = (size_t)npl * plane_stride;
+    if (TERMS == 2) {
+      *reinterpret_cast<uint4*>(base) = o0;
+      *reinterpret_cast<uint4*>(base + blk) = o1;
+      *reinterpret_cast<uint4*>(base + 2 * blk) = o0;
+    } else {
+      *reinterpret_cast<uint4*>(base) = o0;
+      *reinterpret_cast<uint4*>(base + blk) = o1;
+      *reinterpret_cast<uint4*>(base + 2 * blk) = o2;
+      *reinterpret_cast<uint4*>(base + 3 * blk) = o0;
+      *reinterpret_cast<uint4*>(base + 4 * blk) = o1;
+      *reinterpret_cast<uint4*>(base + 5 * blk) = o0;
+    }
   }
 }
-
 // packed fp32 [rows, in_ld] (utterance b at rows start[b]..) -> planar fp16 with gaps
 __global__ void to_planar_kernel(__half* out, long long plane_stride, const float* in, int in_ld, int C, const int* start,
                                  const int* pstart, const int* len, int act) {
@@ -442,7 +460,7 @@ size_t layer_smem(int planes_per_chunk, int ra, int a_slots, size_t stage_bytes,
 // shifts[g][tap] the input-row shift of that tap.
 template <class WSel>
 ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_groups, const int (*shifts)[MAX_TAPS], const int* group_out_off,
-                     const float* bias, WSel wsel, int mt_pref) {
+                     const float* bias, WSel wsel, int mt_pref, int nb_max = 256) {
   ConvLayer L;
   L.cin = cin;
   L.cout = cout;
@@ -453,7 +471,7 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_group
   if (cin % 16 != 0 || cout % 16 != 0) fail(SBV2_ERR_UNSUPPORTED, "tensor-core conv needs channel counts divisible by 16");
   // N block: largest multiple of 16 that divides cout and is <= 256
   L.nb = 0;
-  for (int nb = std::min(cout, 256); nb >= 16; nb -= 16)
+  for (int nb = std::min(cout, std::max(16, std::min(nb_max, 256))); nb >= 16; nb -= 16)
     if (cout % nb == 0) {
       L.nb = nb;
       break;
@@ -551,7 +569,7 @@ void set_smem_attr() {
 
 }  // namespace
 
-ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref) {
+ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int nb_max) {
   int shifts[1][MAX_TAPS] = {{0}};
   if (c.k > MAX_TAPS) fail(SBV2_ERR_UNSUPPORTED, "kernel size too large");
   // "same" padding as the graph builds it: left (k-1)/2 * dil (FFN even kernels pad ((k-1)/2, k/2))
@@ -559,28 +577,47 @@ ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int m
   const int cin = c.d1, k = c.k;
   const float* w = c.w.data();
   return make_layer(owner, c.d1, c.d0, c.k, 1, shifts, nullptr, c.b.empty() ? nullptr : c.b.data(),
-                    [=](int, int co, int ci, int tap) { return w[(size_t(co) * cin + ci) * k + tap]; }, mt_pref);
+                    [=](int, int co, int ci, int tap) { return w[(size_t(co) * cin + ci) * k + tap]; }, mt_pref, nb_max);
 }
 
-ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref) {
-  // [Cout][3*Cin][k]: input planes [hi | lo | hi] meet weights [whi | whi | wlo]
+ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int terms, int nb_max) {
+  // [Cout][n*Cin][k]: terms = 2: input planes [h0 | h1 | h0] meet weights [w0 | w0 | w1];
+  // terms = 3: [h0 | h1 | h2 | h0 | h1 | h0] meet [w0 | w0 | w0 | w1 | w1 | w2]
+  const int nblk = terms == 3 ? 6 : 3;
+  static const int wsel2[3] = {0, 0, 1}, wsel3[6] = {0, 0, 0, 1, 1, 2};
+  const int* wsel = terms == 3 ? wsel3 : wsel2;
   HostConv s3;
   s3.d0 = c.d0;
-  s3.d1 = 3 * c.d1;
+  s3.d1 = nblk * c.d1;
   s3.k = c.k;
   s3.b = c.b;
   s3.w.resize(size_t(s3.d0) * s3.d1 * s3.k);
+  // weight scale: the largest power of two with max|w| * scale <= 2^13 (fp16 overflows at 65504)
+  float wmax = 0.f;
+  for (float v : c.w) wmax = std::max(wmax, std::fabs(v));
+  int wexp = 0;
+  if (wmax > 0.f) {
+    std::frexp(wmax, &wexp);  // wmax = m * 2^wexp, m in [0.5, 1)
+    wexp = 13 - wexp;
+  }
+  const float wscale = std::ldexp(1.0f, wexp);
+  const float in_scale = 16.f;  // activations up to ~4000 in magnitude stay finite in fp16
   for (int co = 0; co < c.d0; ++co)
     for (int ci = 0; ci < c.d1; ++ci)
       for (int j = 0; j < c.k; ++j) {
-        const float w = c.w[(size_t(co) * c.d1 + ci) * c.k + j];
-        const float whi = __half2float(__float2half_rn(w));
-        const float wlo = __half2float(__float2half_rn(w - whi));
-        s3.w[(size_t(co) * s3.d1 + ci) * c.k + j] = whi;
-        s3.w[(size_t(co) * s3.d1 + c.d1 + ci) * c.k + j] = whi;
-        s3.w[(size_t(co) * s3.d1 + 2 * c.d1 + ci) * c.k + j] = wlo;
+        const float w = c.w[(size_t(co) * c.d1 + ci) * c.k + j] * wscale;
+        float wt[3];
+        wt[0] = __half2float(__float2half_rn(w));
+        wt[1] = __half2float(__float2half_rn(w - wt[0]));
+        wt[2] = __half2float(__float2half_rn(w - wt[0] - wt[1]));
+        for (int q = 0; q < nblk; ++q) s3.w[(size_t(co) * s3.d1 + size_t(q) * c.d1 + ci) * c.k + j] = wt[wsel[q]];
       }
-  return make_conv1d_layer(owner, s3, dil, mt_pref);
+  s3.b.clear();  // the bias is added after the accumulator has been scaled back: keep it out of the packed layer ...
+  ConvLayer L = make_conv1d_layer(owner, s3, dil, mt_pref, nb_max);
+  if (!c.b.empty()) L.bias = owner->upload_f32(c.b);  // ... and attach the unscaled one
+  L.in_scale = in_scale;
+  L.out_scale = 1.0f / (in_scale * wscale);
+  return L;
 }
 
 ConvLayer make_upsample_layer(sbv2_model* owner, const HostConv& c, int u, int mt_pref) {
@@ -657,6 +694,7 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.tmem_cols = L.tmem_cols;
   a.idesc = L.idesc;
   a.rm_out = c.rm_out;
+  a.rm_scale = L.out_scale;
   a.rm_ld = c.rm_ld;
   a.rm_start = c.rm_start;
   a.trace = g_trace;
@@ -767,10 +805,13 @@ void launch_to_planar(const LaunchCtx& ctx, __half* out, const float* in, int in
 }
 
 void launch_split_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
-                         int n_utt) {
+                         int n_utt, int terms, float in_scale) {
   dim3 block(std::min(32, C / 8), 8);
   dim3 grid((g.max_len + 7) / 8, n_utt);
-  split_planar_kernel<<<grid, block, 0, ctx.stream>>>(out, g.rows_tot * 8, in, in_ld, C, d_start, g.d_pstart, g.d_len);
+  if (terms == 3)
+    split_planar_kernel<3><<<grid, block, 0, ctx.stream>>>(out, g.rows_tot * 8, in, in_ld, C, d_start, g.d_pstart, g.d_len, in_scale);
+  else
+    split_planar_kernel<2><<<grid, block, 0, ctx.stream>>>(out, g.rows_tot * 8, in, in_ld, C, d_start, g.d_pstart, g.d_len, in_scale);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -49,10 +49,14 @@ struct ConvLayer {
   size_t smem = 0;
   int tmem_cols = 32;
   unsigned idesc = 0;
+  float in_scale = 1.f, out_scale = 1.f;  // split layers: power-of-two operand scaling (see make_split_conv1d_layer)
 };
 
 // Conv1d weight [Cout][Cin][k], "same" padding, dilation dil.
-ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref);
+// mt_pref: preferred number of 128-row tiles per work item; nb_max: largest N block (output channels per item).  A work
+// item streams its N block's weights once, so few-row problems (flow, text encoder) want nb_max = 128 and mt_pref = 2:
+// twice the rows per weight byte read from L2.
+ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int nb_max = 256);
 // ConvTranspose1d weight [Cin][Cout][k], stride u, pad (k-u)/2 as u polyphase groups of k/u taps (one launch;
 // launch with ConvCall::out_mul = u)
 ConvLayer make_upsample_layer(sbv2_model* owner, const HostConv& c, int u, int mt_pref);
@@ -80,13 +84,18 @@ struct PinnedBuf;
 BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::vector<int>& ystart, const std::vector<int>& ylen,
                       const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights = nullptr);
 
-// Conv1d evaluated to ~fp32 accuracy on the fp16 tensor cores: x = hi + lo (two fp16 terms), w = whi + wlo, and
-// x*w ~ hi*whi + lo*whi + hi*wlo (the dropped lo*wlo term is 2^-22 relative).  The layer has 3*Cin input channels; its
-// input is the planar tensor [hi | lo | hi] written by launch_split_planar.
-ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref);
-// packed fp32 [rows, in_ld] (first C columns) -> planar fp16 [hi | lo | hi] (3*C channels); gap rows are not written
+// Conv1d evaluated to ~fp32 accuracy on the fp16 tensor cores by splitting both operands into fp16 terms
+// (x = h0 + h1 [+ h2], w = w0 + w1 [+ w2]) and stacking the cross products along K:
+//   terms = 2: h0 w0 + h1 w0 + h0 w1                               (3*Cin input channels, ~2^-21 relative error)
+//   terms = 3: h0 w0 + h1 w0 + h2 w0 + h0 w1 + h1 w1 + h0 w2        (6*Cin input channels, fp32-level error)
+// Both operands are scaled by powers of two first (weights so that max|w| ~ 2^13, activations by ConvLayer::in_scale)
+// so that the low-order terms stay out of fp16's subnormal range; the fp32 row-major epilogue multiplies the
+// accumulator by ConvLayer::out_scale = 1 / (in_scale * weight scale) — exact.
+// The layer's input is the planar tensor written by launch_split_planar with the same `terms` and in_scale.
+ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int terms, int nb_max = 256);
+// packed fp32 [rows, in_ld] (first C columns) * in_scale -> planar fp16 split terms; gap rows are not written
 void launch_split_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
-                         int n_utt);
+                         int n_utt, int terms, float in_scale);
 enum UAccum { UACC_NONE = 0, UACC_SET = 1, UACC_ADD = 2, UACC_FINAL = 3 };
 struct ConvCall {
   const __half* in = nullptr;

@@ -16,30 +16,42 @@ namespace sbv2 {
 extern long long* g_pair_trace;
 namespace {
 
-// decoder post: out[t] = tanh(sum_j sum_c w[c][j] * x[t+j-pad][c]); x planar fp16 already activated (lrelu 0.01)
-__global__ void post_planar_kernel(float* wave, const __half* x, long long plane_stride, const float* w, int C, int k, const int* pstart,
-                                   const int* wstart, const int* len) {
-  extern __shared__ float ws[];  // [k][C]
-  for (int i = threadIdx.x; i < C * k; i += blockDim.x) {
+// decoder post: out[t] = tanh(sum_j sum_c w[c][j] * x[t+j-pad][c]); x planar fp16 already activated (lrelu 0.01).
+// A block stages its 256 + k - 1 input rows in shared memory once (coalesced 16-byte loads); every thread then reads its
+// k taps from there — the direct version issued k * C/8 global loads per output and was load/store-unit bound.
+constexpr int POST_T = 256;
+__global__ void __launch_bounds__(POST_T) post_planar_kernel(float* wave, const __half* x, long long plane_stride, const float* w, int C,
+                                                             int k, const int* pstart, const int* wstart, const int* len) {
+  extern __shared__ __align__(16) uint8_t post_smem[];
+  const int npl = C / 8, pad = (k - 1) / 2, rows = POST_T + k - 1;
+  float* ws = reinterpret_cast<float*>(post_smem);                               // [k][C]
+  uint4* xs = reinterpret_cast<uint4*>(post_smem + (((size_t)k * C * 4 + 15) & ~size_t(15)));  // [npl][rows]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * POST_T;
+  if (t0 >= len[b]) return;
+  for (int i = threadIdx.x; i < C * k; i += POST_T) {
     int c = i / k, j = i % k;
     ws[j * C + c] = w[i];
   }
+  const long long r0 = (long long)pstart[b] + t0 - pad;  // gap rows are zero: no bounds test needed
+  for (int i = threadIdx.x; i < npl * rows; i += POST_T) {
+    const int pl = i / rows, r = i - pl * rows;
+    xs[pl * rows + r] = *reinterpret_cast<const uint4*>(x + (size_t)pl * plane_stride + (r0 + r) * 8);
+  }
   __syncthreads();
-  int b = blockIdx.y;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = t0 + threadIdx.x;
   if (t >= len[b]) return;
-  const int pad = (k - 1) / 2;
   float acc = 0.f;
   for (int j = 0; j < k; ++j) {
-    long long r = (long long)pstart[b] + t + j - pad;  // gap rows are zero: no bounds test needed
-    for (int pl = 0; pl < C / 8; ++pl) {
-      uint4 q = *reinterpret_cast<const uint4*>(x + (size_t)pl * plane_stride + r * 8);
+    for (int pl = 0; pl < npl; ++pl) {
+      const uint4 q = xs[pl * rows + threadIdx.x + j];
       const __half2* qh = reinterpret_cast<const __half2*>(&q);
+      const float* wj = ws + j * C + pl * 8;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float2 y = __half22float2(qh[e]);
-        acc = fmaf(ws[j * C + pl * 8 + 2 * e], y.x, acc);
-        acc = fmaf(ws[j * C + pl * 8 + 2 * e + 1], y.y, acc);
+        const float2 y = __half22float2(qh[e]);
+        acc = fmaf(wj[2 * e], y.x, acc);
+        acc = fmaf(wj[2 * e + 1], y.y, acc);
       }
     }
   }
@@ -297,9 +309,10 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
   }
   const Geom& GL = bg.g.back();
   {
-    dim3 grid((GL.max_len + 255) / 256, B);
-    post_planar_kernel<<<grid, 256, sizeof(float) * D->post_c * D->post_k, ctx.stream>>>(wave, xs, GL.rows_tot * 8, D->post_w, D->post_c,
-                                                                                        D->post_k, GL.d_pstart, bg.d_wstart, GL.d_len);
+    dim3 grid((GL.max_len + POST_T - 1) / POST_T, B);
+    const size_t smem = ((sizeof(float) * D->post_c * D->post_k + 15) & ~size_t(15)) + size_t(D->post_c / 8) * (POST_T + D->post_k - 1) * 16;
+    post_planar_kernel<<<grid, POST_T, smem, ctx.stream>>>(wave, xs, GL.rows_tot * 8, D->post_w, D->post_c, D->post_k, GL.d_pstart,
+                                                           bg.d_wstart, GL.d_len);
     CUDA_CHECK(cudaGetLastError());
     ctx.count();
   }

@@ -255,8 +255,9 @@ __device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
-    float4 f = make_float4(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y, __uint_as_float(v[4 * q + 2]) + b.z,
-                           __uint_as_float(v[4 * q + 3]) + b.w);
+    const float sc = p.rm_scale;  // power of two
+    float4 f = make_float4(__uint_as_float(v[4 * q]) * sc + b.x, __uint_as_float(v[4 * q + 1]) * sc + b.y,
+                           __uint_as_float(v[4 * q + 2]) * sc + b.z, __uint_as_float(v[4 * q + 3]) * sc + b.w);
     if (relu) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
     *reinterpret_cast<float4*>(dst + 4 * q) = f;
   }

@@ -17,8 +17,10 @@ for row in csv.DictReader(lines):
         per[kid][name] = v * mul
     elif name == "gpu__time_duration.sum":
         per[kid]["us"] = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
-umma = [per[k] for k in order if "umma_conv" in per[k]["name"]]
-dec = umma[-113:]  # the decoder's convs are the last 113 tensor-core conv launches of a step
+# the decoder's tensor-core launches are the umma_conv / umma_pair launches after the step's last to_planar_kernel
+names = [per[k]["name"] for k in order]
+last_tp = max(i for i, n in enumerate(names) if "to_planar_kernel" in n)
+dec = [per[k] for i, k in enumerate(order) if i > last_tp and ("umma_conv" in per[k]["name"] or "umma_pair" in per[k]["name"])]
 rd = sum(k.get("dram__bytes_read.sum", 0) for k in dec)
 wr = sum(k.get("dram__bytes_write.sum", 0) for k in dec)
 us = sum(k.get("us", 0) for k in dec)
