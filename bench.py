@@ -308,7 +308,7 @@ def main():
         line = {
             "metric": "audio-sec/sec", "value": audio_total / (ms_max * 1e-3), "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (decoder); f32 (text, flow)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate on tcgen05 (decoder, flow; text encoder with two-term fp16 splits); f32 elsewhere",
             "data": "synthetic",
             "config": {"workload": workload, "batch_per_gpu": args.batch, "audio_s_per_step_per_gpu": audio_s_step,
                        "frames_per_step_per_gpu": int(frames), "weights": "random-init tsukuyomi-shaped JP-Extra, seed 0",
@@ -320,7 +320,7 @@ def main():
             "gpu_launches": launches_total,
             "replicas_per_gpu": R,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "umma_conv_kernel (HiFi-GAN decoder, timed region = whole decoder)",
+            "roofline": {"bound": "tensor", "kernel": "umma_conv_kernel + umma_pair_kernel (HiFi-GAN decoder, timed region = whole decoder)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src},
         }

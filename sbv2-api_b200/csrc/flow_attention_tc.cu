@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
                                                                     long long* trace) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
+  // grid slots are handed out in (x, y, z) order: with z walking the utterances longest-first the long CTAs start early
+  // and the short ones fill the last wave
+  const int b = s.order ? s.order[blockIdx.z] : (int)blockIdx.z, h = blockIdx.y;
   const int len = s.len[b];
   const int q0 = blockIdx.x * QT;
   if (q0 >= len) return;  // uniform per CTA

@@ -125,6 +125,7 @@ struct PlanarSegs {
   const int* start = nullptr;   // packed fp32 rows
   const int* pstart = nullptr;  // planar rows
   const int* len = nullptr;
+  const int* order = nullptr;   // optional: utterance processed by grid slot z (longest first); null = identity
   int n = 0, max_len = 0;
   long long plane_stride = 0;   // elements between planes (= rows_tot * 8)
 };

@@ -1355,6 +1355,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     ps.start = bg.d_ystart;
     ps.pstart = G.d_pstart;
     ps.len = G.d_len;
+    ps.order = bg.d_order;
     ps.n = B;
     ps.max_len = ymax;
     ps.plane_stride = G.rows_tot * 8;

@@ -730,7 +730,7 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
     const size_t n_extra = extra_heights && s < extra_heights->size() ? (*extra_heights)[s].size() : 0;
     goff[s + 1] = goff[s] + size_t(2) * B + size_t(5 + n_extra) * (B + 1);
   }
-  const size_t total = goff.back() + size_t(2) * B;
+  const size_t total = goff.back() + size_t(3) * B;  // + ystart, wstart, order
   // the pinned blob of the previous run may still be in flight on the stream
   CUDA_CHECK(cudaStreamSynchronize(owner->stream));
   pin.ensure(total * 4);
@@ -777,6 +777,13 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
     tail[b] = ystart[b];
     tail[B + b] = int((long long)ystart[b] * hop);
   }
+  {
+    // utterances by decreasing length: kernels with one CTA per (utterance, tile) start the long ones first
+    std::vector<int> order(B);
+    for (int b = 0; b < B; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ylen[x] > ylen[y]; });
+    for (int b = 0; b < B; ++b) tail[2 * B + b] = order[b];
+  }
   dev.stream = owner->stream;
   dev.ensure(total * 4);
   CUDA_CHECK(cudaMemcpyAsync(dev.p, h, total * 4, cudaMemcpyHostToDevice, owner->stream));
@@ -792,6 +799,7 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
   }
   bg.d_ystart = d + goff.back();
   bg.d_wstart = bg.d_ystart + B;
+  bg.d_order = bg.d_ystart + 2 * B;
   return bg;
 }
 

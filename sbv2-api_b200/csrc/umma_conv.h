@@ -78,6 +78,7 @@ struct BatchGeom {
   std::vector<Geom> g;
   const int* d_ystart = nullptr;  // first row of each utterance in the packed fp32 [rows, C] matrices
   const int* d_wstart = nullptr;  // sample offset of each utterance in the waveform buffer
+  const int* d_order = nullptr;   // utterance indices by decreasing length
 };
 struct DBuf;
 struct PinnedBuf;

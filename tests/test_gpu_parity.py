@@ -153,17 +153,19 @@ def test_decoder_alone_cfg3_shape(full):
 
 
 def test_fp32_cuda_path_matches_oracle_tightly(S):
-    """The CUDA-core fp32 kernels (selected with SBV2_B200_DECODER/FLOW=fp32) reproduce the oracle
+    """The CUDA-core fp32 kernels (selected with SBV2_B200_DECODER/FLOW/TEXT=fp32) reproduce the oracle
     to fp32 round-off; this separates kernel-logic errors from fp16 operand rounding."""
     hp = ov.HParams()
     oracle, onnx = util.synth_assets(hp, seed=0)
     os.environ["SBV2_B200_DECODER"] = "fp32"
     os.environ["SBV2_B200_FLOW"] = "fp32"
+    os.environ["SBV2_B200_TEXT"] = "fp32"
     try:
         model = S.Model(onnx, bert=False)
     finally:
         del os.environ["SBV2_B200_DECODER"]
         del os.environ["SBV2_B200_FLOW"]
+        del os.environ["SBV2_B200_TEXT"]
     u = util.make_utterance(hp, 61, seed=77, sdp_ratio=0.5)
     ref, inter = util.oracle_run(oracle, u)
     audio, dur, f2p = run_gpu(model, u)
