@@ -218,10 +218,10 @@ def main():
     ev0.record(streams[0])
     for st in streams[1:]:
         st.wait_event(ev0)  # nothing of any replica starts before ev0
-    threads = [threading.Thread(target=kworker, args=(i,)) for i in range(R)]
-    for th in threads:
+    kthreads = [threading.Thread(target=kworker, args=(i,)) for i in range(R)]
+    for th in kthreads:
         th.start()
-    for th in threads:
+    for th in kthreads:
         th.join()
     barrier()
     launches = sum(m.launch_count for m in replicas) - l0
@@ -268,10 +268,10 @@ def main():
 
     barrier()
     t0 = time.perf_counter()
-    threads = [threading.Thread(target=worker, args=(i,)) for i in range(R)]
-    for th in threads:
+    ethreads = [threading.Thread(target=worker, args=(i,)) for i in range(R)]
+    for th in ethreads:
         th.start()
-    for th in threads:
+    for th in ethreads:
         th.join()
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0

@@ -58,6 +58,10 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
   M->is_bert = true;
   CUDA_CHECK(cudaSetDevice(device));
   CUDA_CHECK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+  {
+    const char* pe = getenv("SBV2_B200_PDL");
+    M->pdl = pe && pe[0] == '1';
+  }
   M->metadata = m.metadata;
   const std::string P = find_prefix(m);
   auto get = [&](const std::string& n) -> const OnnxTensor& {

@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: the qkv projection's output is visible from here on
 
   const int q_plane0 = h * DP, k_plane0 = heads * DP + h * DP, v_plane0 = 2 * heads * DP + h * DP;
   const int n_tiles_total = 2 * n_kt;  // pass A tiles then pass B tiles
@@ -449,8 +451,8 @@ void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __hal
     attr_set = true;
   }
   dim3 grid((s.max_len + QT - 1) / QT, heads, s.n);
-  flow_attention_tc_kernel<<<grid, 32 * (NSM_WARPS + 1), smem, ctx.stream>>>(ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s, trace);
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(ctx.pdl, flow_attention_tc_kernel, grid, dim3(32 * (NSM_WARPS + 1)), smem, ctx.stream, ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s,
+             trace);
   ctx.count();
 }
 

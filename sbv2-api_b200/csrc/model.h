@@ -72,7 +72,8 @@ struct sbv2_model {
   float region_ms(const std::string& name);
 
   virtual ~sbv2_model();
-  sbv2::LaunchCtx ctx() { return sbv2::LaunchCtx{stream, &launches}; }
+  bool pdl = false;  // SBV2_B200_PDL=1 (read at model creation): programmatic dependent launch of the tensor-core kernels
+  sbv2::LaunchCtx ctx() { return sbv2::LaunchCtx{stream, &launches, pdl}; }
   void bind_device() const;
   // uploads host data, tracked for release at destroy
   void* upload_bytes(const void* host, size_t bytes);

@@ -774,6 +774,10 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
   M->is_bert = false;
   CUDA_CHECK(cudaSetDevice(device));
   CUDA_CHECK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+  {
+    const char* pe = getenv("SBV2_B200_PDL");
+    M->pdl = pe && pe[0] == '1';
+  }
   for (auto& w : M->ws) w.stream = M->stream;
   M->metadata = m.metadata;
   load_weights(*M, m);

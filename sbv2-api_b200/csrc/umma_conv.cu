@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // PDL: everything above overlapped the previous kernel's tail; its results are visible after the wait
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -707,8 +710,7 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
     CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   dim3 grid(std::min(a.n_items, num_sms));
-  umma_conv_kernel<<<grid, NUM_THREADS, L.smem, ctx.stream>>>(a);
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(ctx.pdl, umma_conv_kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
   ctx.count();
 }
 

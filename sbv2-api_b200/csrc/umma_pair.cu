@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // PDL: everything above overlapped the previous kernel's tail; its results are visible after the wait
+  pdl_launch_dependents();
+  pdl_wait();
   const int n_my = p.n_items > (int)blockIdx.x ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;  // items of this CTA
 
   if (warp == 0) {
@@ -531,8 +534,7 @@ void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, c
   if (g_pair_trace != nullptr) {
     if (const char* e = getenv("SBV2_B200_PAIR_GRID")) grid = std::max(1, std::min(grid, atoi(e)));  // debugging: fewer CTAs
   }
-  umma_pair_kernel<<<grid, P_THREADS, L.smem, ctx.stream>>>(a);
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(ctx.pdl, umma_pair_kernel, dim3(grid), dim3(P_THREADS), L.smem, ctx.stream, a);
   ctx.count();
 }
 
