@@ -58,6 +58,47 @@ __global__ void __launch_bounds__(POST_T) post_planar_kernel(float* wave, const 
   wave[(size_t)wstart[b] + t] = tanhf(acc);
 }
 
+// The JP-Extra shape (16 channels, 7 taps) with the weights in the kernel's constant parameter bank: the generic kernel
+// spends one shared-memory load per FMA on the weights, here they are FFMA constant operands.
+template <int C, int K>
+struct PostWeights {
+  float w[K][C];  // [tap][channel]
+};
+template <int C, int K>
+__global__ void __launch_bounds__(POST_T) post_planar_const_kernel(float* wave, const __half* x, long long plane_stride,
+                                                                   const __grid_constant__ PostWeights<C, K> pw, const int* pstart,
+                                                                   const int* wstart, const int* len) {
+  constexpr int NPL = C / 8, PAD = (K - 1) / 2, ROWS = POST_T + K - 1;
+  __shared__ uint4 xs[NPL * ROWS];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * POST_T;
+  if (t0 >= len[b]) return;
+  const long long r0 = (long long)pstart[b] + t0 - PAD;
+  for (int i = threadIdx.x; i < NPL * ROWS; i += POST_T) {
+    const int pl = i / ROWS, r = i - pl * ROWS;
+    xs[pl * ROWS + r] = *reinterpret_cast<const uint4*>(x + (size_t)pl * plane_stride + (r0 + r) * 8);
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= len[b]) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl) {
+      const uint4 q = xs[pl * ROWS + threadIdx.x + j];
+      const __half2* qh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 y = __half22float2(qh[e]);
+        acc = fmaf(pw.w[j][pl * 8 + 2 * e], y.x, acc);
+        acc = fmaf(pw.w[j][pl * 8 + 2 * e + 1], y.y, acc);
+      }
+    }
+  }
+  wave[(size_t)wstart[b] + t] = tanhf(acc);
+}
+
 }  // namespace
 
 // ---- decoder plan -----------------------------------------------------------------------------------------
@@ -73,6 +114,7 @@ struct UmmaDecoder {
   std::vector<std::vector<char>> fused;
   std::vector<std::vector<int>> pair_heights;  // [geometry level]: tile heights the fused pairs need
   float* post_w = nullptr;
+  std::vector<float> post_w_host;  // [1][C][k], for the constant-bank kernel
   DBuf zp, xs, xu, t1, r, rj0, rj1, sum, meta, gcond;
   PinnedBuf pin_meta;
 };
@@ -136,6 +178,7 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
   D->post_k = w.post.k;
   if (D->post_c != C || D->post_c % 8 != 0) fail(SBV2_ERR_UNSUPPORTED, "decoder conv_post channel mismatch");
   D->post_w = owner->upload_f32(w.post.w);
+  D->post_w_host = w.post.w;
   for (DBuf* b : {&D->zp, &D->xs, &D->xu, &D->t1, &D->r, &D->rj0, &D->rj1, &D->sum, &D->meta, &D->gcond}) b->stream = owner->stream;
   return D.release();
 }
@@ -310,9 +353,16 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
   const Geom& GL = bg.g.back();
   {
     dim3 grid((GL.max_len + POST_T - 1) / POST_T, B);
-    const size_t smem = ((sizeof(float) * D->post_c * D->post_k + 15) & ~size_t(15)) + size_t(D->post_c / 8) * (POST_T + D->post_k - 1) * 16;
-    post_planar_kernel<<<grid, POST_T, smem, ctx.stream>>>(wave, xs, GL.rows_tot * 8, D->post_w, D->post_c, D->post_k, GL.d_pstart,
-                                                           bg.d_wstart, GL.d_len);
+    if (D->post_c == 16 && D->post_k == 7) {
+      PostWeights<16, 7> pw;
+      for (int c = 0; c < 16; ++c)
+        for (int j = 0; j < 7; ++j) pw.w[j][c] = D->post_w_host[size_t(c) * 7 + j];
+      post_planar_const_kernel<16, 7><<<grid, POST_T, 0, ctx.stream>>>(wave, xs, GL.rows_tot * 8, pw, GL.d_pstart, bg.d_wstart, GL.d_len);
+    } else {
+      const size_t smem = ((sizeof(float) * D->post_c * D->post_k + 15) & ~size_t(15)) + size_t(D->post_c / 8) * (POST_T + D->post_k - 1) * 16;
+      post_planar_kernel<<<grid, POST_T, smem, ctx.stream>>>(wave, xs, GL.rows_tot * 8, D->post_w, D->post_c, D->post_k, GL.d_pstart,
+                                                             bg.d_wstart, GL.d_len);
+    }
     CUDA_CHECK(cudaGetLastError());
     ctx.count();
   }
