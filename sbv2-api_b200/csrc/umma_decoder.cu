@@ -521,7 +521,7 @@ extern "C" int sbv2_debug_conv_trace(int64_t T, int cin, int cout, int k, int di
 extern "C" int sbv2_debug_pair_compare(const float* x, const int* lens, int n_utt, int C, int k, int dil, const float* w1,
                                        const float* b1, const float* w2, const float* b2, int mrf, int iters, float* out_fused,
                                        float* out_ref, float* out_ms /*[2]: fused, unfused*/, int* out_cfg /*[8]*/,
-                                       long long* out_trace /*[64*8] or null*/) {
+                                       long long* out_trace /*[64*16] or null*/) {
   using namespace sbv2;
   return guarded([&] {
     SBV2_REQUIRE(x && lens && n_utt > 0 && w1 && w2 && out_fused && out_ref, "bad arguments");
@@ -630,13 +630,13 @@ extern "C" int sbv2_debug_pair_compare(const float* x, const int* lens, int n_ut
     if (out_trace) {
       DBuf tr;
       tr.stream = owner.stream;
-      tr.ensure(64 * 8 * 8);
-      CUDA_CHECK(cudaMemsetAsync(tr.p, 0, 64 * 8 * 8, owner.stream));
+      tr.ensure(64 * 16 * 8);
+      CUDA_CHECK(cudaMemsetAsync(tr.p, 0, 64 * 16 * 8, owner.stream));
       g_pair_trace = tr.as<long long>();
       run_fused();
       g_pair_trace = nullptr;
       CUDA_CHECK(cudaStreamSynchronize(owner.stream));
-      CUDA_CHECK(cudaMemcpy(out_trace, tr.p, 64 * 8 * 8, cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(out_trace, tr.p, 64 * 16 * 8, cudaMemcpyDeviceToHost));
     }
   });
 }

@@ -63,23 +63,32 @@ struct PairArgs {
 
 #define PTRACE(ev, itv)                                                                          \
   do {                                                                                            \
-    if (p.trace != nullptr && blockIdx.x == 0 && (itv) < 64) p.trace[(itv) * 8 + (ev)] = clock64(); \
+    if (p.trace != nullptr && blockIdx.x == 0 && (itv) < 64) p.trace[(itv) * 16 + (ev)] = clock64(); \
   } while (0)
 
 struct PTile {
-  int b, t0, len;
+  int b, t0, len, pstart;
 };
-__device__ __forceinline__ PTile locate_pair_item(const PairArgs& p, int item) {
+constexpr int P_TABLE_UTTS = 128;  // batches up to this size keep the geometry tables in shared memory
+// geometry tables (tile prefix [n+1], len [n], pstart [n]): shared-memory copies when the batch is small enough — the
+// binary search is five dependent loads, ~2000 cycles from L2 per epilogue call, ~30 from shared memory
+struct PTables {
+  const int* prefix;
+  const int* len;
+  const int* pstart;
+};
+__device__ __forceinline__ PTile locate_pair_item(const PairArgs& p, const PTables& tb, int item) {
   PTile ti;
   int lo = 0, hi = p.n_utt;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (p.tile_prefix[mid] <= item) lo = mid;
+    if (tb.prefix[mid] <= item) lo = mid;
     else hi = mid;
   }
   ti.b = lo;
-  ti.t0 = (item - p.tile_prefix[lo]) * p.out_rows;
-  ti.len = p.len[lo];
+  ti.t0 = (item - tb.prefix[lo]) * p.out_rows;
+  ti.len = tb.len[lo];
+  ti.pstart = tb.pstart[lo];
   return ti;
 }
 
@@ -124,6 +133,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 2 * p.c; i += P_THREADS) bias_s[i] = i < p.c ? p.bias1[i] : p.bias2[i - p.c];
+  PTables tb{p.tile_prefix, p.len, p.pstart};
+  if (p.n_utt <= P_TABLE_UTTS) {
+    int* tab = reinterpret_cast<int*>(bias_s + 2 * p.c);  // [n+1 | n | n]
+    for (int i = threadIdx.x; i <= p.n_utt; i += P_THREADS) tab[i] = p.tile_prefix[i];
+    for (int i = threadIdx.x; i < p.n_utt; i += P_THREADS) {
+      tab[p.n_utt + 1 + i] = p.len[i];
+      tab[2 * p.n_utt + 1 + i] = p.pstart[i];
+    }
+    tb.prefix = tab;
+    tb.len = tab + p.n_utt + 1;
+    tb.pstart = tab + 2 * p.n_utt + 1;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -142,8 +163,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       // ---------------- producer: A chunks for phase 1, weight stages in MMA consumption order ----------------
       uint32_t a_it = 0, b_it = 0;
       auto load_a_item = [&](int it) {
-        const PTile ti = locate_pair_item(p, (int)blockIdx.x + it * (int)gridDim.x);
-        const long long in_row0 = (long long)p.pstart[ti.b] + ti.t0 - p.h2 - p.h1;
+        const PTile ti = locate_pair_item(p, tb, (int)blockIdx.x + it * (int)gridDim.x);
+        const long long in_row0 = (long long)ti.pstart + ti.t0 - p.h2 - p.h1;
         for (int kc = 0; kc < p.nkc; ++kc, ++a_it) {
           const uint32_t slot = a_it % p.a_slots;
           mbar_wait(bar_ae + 8 * slot, ((a_it / p.a_slots) & 1) ^ 1);
@@ -256,7 +277,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
     auto issue_p2 = [&](int it, auto mtk) {
       constexpr int MT = decltype(mtk)::mt, K16 = decltype(mtk)::k16;
       const uint32_t buf = it & 1;
+      if (lane == 0) PTRACE(8, it);
       mbar_wait(bar_a2e + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue-2 of item it-2 has drained this set
+      if (lane == 0) PTRACE(9, it);
       mbar_wait(bar_t1r + 8 * buf, (it >> 1) & 1);         // t1 tile written and visible to the async proxy
       tc_fence_after();
       if (lane == 0) PTRACE(2, it);
@@ -304,11 +327,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
     // epilogue 1: t1 = lrelu(acc + b1) -> fp16 -> shared tile; rows outside [0, len) are conv2's zero padding
     auto epi1 = [&](int it) {
       const uint32_t buf = it & 1;
-      const PTile ti = locate_pair_item(p, (int)blockIdx.x + it * (int)gridDim.x);
+      const PTile ti = locate_pair_item(p, tb, (int)blockIdx.x + it * (int)gridDim.x);
       mbar_wait(bar_a1f + 8 * buf, (it >> 1) & 1);
       mbar_wait(bar_t1f + 8 * buf, ((it >> 1) & 1) ^ 1);  // phase 2 of item it-2 has finished reading this tile
       tc_fence_after();
       if (threadIdx.x == 64) PTRACE(4, it);
+      if (threadIdx.x == 64 + 15 * 32) PTRACE(10, it);
       const uint32_t tacc0 = tmem_base + buf * acc_cols;
       uint8_t* t1 = smem + (sT1 - sA) + buf * t1_bytes;
       const int n_sub = p.mt * (p.c / 16);
@@ -342,6 +366,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 64) PTRACE(5, it);
+      if (threadIdx.x == 64 + 15 * 32) PTRACE(11, it);
       if (lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a1e + 8 * buf) : "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_t1r + 8 * buf) : "memory");
@@ -350,10 +375,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
     // epilogue 2: out = act((acc + b2 + x [+ r0 + r1]) [/ 3])
     auto epi2 = [&](int it) {
       const uint32_t buf = it & 1;
-      const PTile ti = locate_pair_item(p, (int)blockIdx.x + it * (int)gridDim.x);
+      const PTile ti = locate_pair_item(p, tb, (int)blockIdx.x + it * (int)gridDim.x);
       mbar_wait(bar_a2f + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 64) PTRACE(6, it);
+      if (threadIdx.x == 64 + 15 * 32) PTRACE(12, it);
       const uint32_t tacc0 = tmem_base + (2 + buf) * acc_cols;
       const bool wide = (p.c % 32 == 0) && p.has_res != 3;
       const int nch = wide ? 32 : 16;
@@ -365,7 +391,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
         const int m = a * 128 + wq * 32 + lane;  // output row within the item
         const int t = ti.t0 + m;
         const bool valid = m < p.out_rows && t < ti.len;
-        const long long orow = (long long)p.pstart[ti.b] + t;
+        const long long orow = (long long)ti.pstart + t;
         const uint32_t taddr = tacc0 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.c + c0);
         if (p.has_res == 3) epilogue_item<16, false, 3>(p, taddr, valid, orow, c0, b2s + c0);
         else if (wide) epilogue_item<32, false, 1>(p, taddr, valid, orow, c0, b2s + c0);
@@ -374,6 +400,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 64) PTRACE(7, it);
+      if (threadIdx.x == 64 + 15 * 32) PTRACE(13, it);
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a2e + 8 * buf) : "memory");
     };
     if (n_my > 0) epi1(0);
@@ -431,7 +458,7 @@ bool make_pair_layer(sbv2_model* owner, const HostConv& c1, int dil, const HostC
   const size_t w_bytes = step_bytes * L.total_steps;
   const size_t slot = size_t(L.kc / 8) * (L.t1rows + 2 * L.h1) * 16;
   const size_t t1 = size_t(C / 8) * L.t1pitch * 16;
-  const size_t misc = 384 + size_t(2) * C * 4 + 256;
+  const size_t misc = 384 + size_t(2) * C * 4 + 256 + size_t(3 * P_TABLE_UTTS + 1) * 4;  // barriers, biases, geometry tables
   const size_t budget = P_SMEM_LIMIT;
   const int min_slots = std::max(2, std::min(2 * L.nkc, P_MAX_ASLOTS));
   if (2 * w_bytes + slot * min_slots + 2 * t1 + misc <= budget) {

@@ -46,7 +46,7 @@ def run(lens, c, k, dil, mrf=0, iters=0, seed=0, check_np=True, trace=False):
     orf = np.zeros((tot, c), np.float32)
     ms = np.zeros(2, np.float32)
     cfg = np.zeros(8, np.int32)
-    tr = np.zeros((64, 8), np.int64)
+    tr = np.zeros((64, 16), np.int64)
     st = fn(x.ctypes.data_as(pf), lens.ctypes.data_as(pi), len(lens), c, k, dil, w1.ctypes.data_as(pf), b1.ctypes.data_as(pf),
             w2.ctypes.data_as(pf), b2.ctypes.data_as(pf), mrf, iters, of.ctypes.data_as(pf), orf.ctypes.data_as(pf),
             ms.ctypes.data_as(pf), cfg.ctypes.data_as(pi), tr.ctypes.data_as(C.POINTER(C.c_longlong)) if trace else None)
@@ -79,11 +79,12 @@ def run(lens, c, k, dil, mrf=0, iters=0, seed=0, check_np=True, trace=False):
         msg += f"  fused {ms[0] * 1e3:.1f} us, unfused {ms[1] * 1e3:.1f} us"
     print(("OK  " if ok else "BAD ") + msg)
     if trace:
-        names = ["p1_go", "p1_issued", "p2_go", "p2_issued", "e1_go", "e1_end", "e2_go", "e2_end"]
+        names = ["p1_go", "p1_issued", "p2_go", "p2_issued", "e1_go", "e1_end", "e2_go", "e2_end", "p2_enter", "p2_acc2_free", "w17_e1_go",
+                 "w17_e1_end", "w17_e2_go", "w17_e2_end"]
         n = int((tr[:, 7] > 0).sum())
         base = tr[tr > 0].min()
-        for i in list(range(min(n, 5))) + list(range(max(5, n - 3), n)):
-            print("   item %2d: " % i + " ".join(f"{names[e]}={tr[i, e] - base:7d}" for e in range(8)))
+        for i in list(range(max(3, n - 6), n)):
+            print("   item %2d: " % i + " ".join(f"{names[e]}={tr[i, e] - base:7d}" for e in range(14)))
         if n > 6:
             print(f"   steady period {(tr[n - 1, 7] - tr[3, 7]) / (n - 4):.0f} cyc/item; e1 {np.mean(tr[3:n, 5] - tr[3:n, 4]):.0f}; e2 "
                   f"{np.mean(tr[3:n, 7] - tr[3:n, 6]):.0f}; p1 issue {np.mean(tr[3:n, 1] - tr[3:n, 0]):.0f}; p2 issue "
@@ -98,8 +99,8 @@ if __name__ == "__main__":
             run([1014 * 60], 16, 11, 5, iters=0, check_np=False, trace=True)
             run([246 * 60], 64, 11, 5, iters=0, check_np=False, trace=True)
             sys.exit(0)
-        for c, mul in ((64, 128), (32, 256), (16, 512)):
-            for k, d in ((3, 1), (11, 5)):
+        for c, mul in ((16, 512),):
+            for k, d in ((3, 1),):
                 run([860 * mul] * 32, c, k, d, iters=3, check_np=False, trace=True)
         sys.exit(0)
     good = True
