@@ -112,6 +112,17 @@ int sbv2_synthesize_with_noise(sbv2_model* synth, const float* bert, const int64
                                int64_t* n_samples, int32_t* out_durations, int32_t** out_frame2ph,
                                int64_t* t_y);
 
+/* SURVEY.md §8f row 1 — `parse_text` + `synthesize` of one sentence without the host round trip of the BERT features:
+ * replaces bert::predict (bert.rs:6-24) -> word2ph repeat + transpose (tts_util.rs:129-154) -> model::synthesize
+ * (model.rs:53-111).  The DeBERTa output stays on the device; phoneme i reads the row of its token
+ * (token k is repeated word2ph[k] times, sum(word2ph) == t_x).  Both models must be on the same device.  The result is
+ * bit-identical to sbv2_bert_predict + host expansion + sbv2_synthesize with the same generator state. */
+int sbv2_synthesize_from_tokens(sbv2_model* synth, sbv2_model* bert, const int64_t* input_ids, const int64_t* attention_mask,
+                                int64_t t_tok, const int32_t* word2ph /* [t_tok] */, const int64_t* x_tst, const int64_t* tones,
+                                const int64_t* lang_ids, int64_t t_x, int64_t sid, const float* style_vec, float sdp_ratio,
+                                float length_scale, float noise_scale, float noise_scale_w, float** out_samples,
+                                int64_t* n_samples);
+
 /* Batched, variable-length extension.  Per-utterance pointer arrays of length `batch`; every
  * utterance's result is bit-identical to its own batch-1 call.  Results land in one pinned block:
  * `*out_samples` float32 [sum n_samples[b]] back to back, `out_n_samples` int64 [batch] caller

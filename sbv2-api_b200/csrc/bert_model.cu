@@ -206,7 +206,9 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
 
 int bert_hidden(const sbv2_model* m) { return static_cast<const BertModel*>(m)->hidden; }
 
-void bert_predict(sbv2_model* mm, const int64_t* ids, const int64_t* mask, int batch, int64_t S, float* out) {
+// Forward pass; the features [batch, S, H] (zero rows where the mask is 0) stay on the device in M.outd.  Returns null
+// when no token is valid.  The caller owns the synchronisation with M.stream.
+const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64_t* mask, int batch, int64_t S) {
   auto* Mp = static_cast<BertModel*>(mm);
   BertModel& M = *Mp;
   SBV2_REQUIRE(batch > 0 && S > 0, "empty input");
@@ -228,12 +230,10 @@ void bert_predict(sbv2_model* mm, const int64_t* ids, const int64_t* mask, int b
     max_len = std::max(max_len, l);
   }
   const size_t out_elems = size_t(batch) * S * H;
-  if (n == 0) {
-    memset(out, 0, out_elems * 4);
-    return;
-  }
+  if (n == 0) return nullptr;
   LaunchCtx ctx = M.ctx();
   // ids of the valid tokens, packed
+  CUDA_CHECK(cudaStreamSynchronize(M.stream));  // the previous call's copies out of / into the staging buffer are done
   M.pin_io.ensure(std::max(size_t(n) * 4, out_elems * 4));
   int* hid = M.pin_io.as<int>();
   for (int b = 0; b < batch; ++b)
@@ -302,8 +302,19 @@ void bert_predict(sbv2_model* mm, const int64_t* ids, const int64_t* mask, int b
   }
   launch_scatter_rows(ctx, M.outd.as<float>(), h, H, int(S), ps);
   M.debug["bert_h"] = DebugView{h, n, H, 4};
+  return M.outd.as<float>();
+}
+
+void bert_predict(sbv2_model* mm, const int64_t* ids, const int64_t* mask, int batch, int64_t S, float* out) {
+  auto& M = *static_cast<BertModel*>(mm);
+  const size_t out_elems = size_t(batch) * S * M.hidden;
+  const float* d = bert_forward_device(mm, ids, mask, batch, S);
+  if (!d) {
+    memset(out, 0, out_elems * 4);
+    return;
+  }
   float* ho = M.pin_io.as<float>();
-  CUDA_CHECK(cudaMemcpyAsync(ho, M.outd.p, out_elems * 4, cudaMemcpyDeviceToHost, M.stream));
+  CUDA_CHECK(cudaMemcpyAsync(ho, d, out_elems * 4, cudaMemcpyDeviceToHost, M.stream));
   CUDA_CHECK(cudaStreamSynchronize(M.stream));
   memcpy(out, ho, out_elems * 4);
 }

@@ -174,6 +174,57 @@ int sbv2_synthesize_with_noise(sbv2_model* synth, const float* bert, const int64
   });
 }
 
+int sbv2_synthesize_from_tokens(sbv2_model* synth, sbv2_model* bert, const int64_t* input_ids, const int64_t* attention_mask,
+                                int64_t t_tok, const int32_t* word2ph, const int64_t* x_tst, const int64_t* tones, const int64_t* lang_ids,
+                                int64_t t_x, int64_t sid, const float* style_vec, float sdp_ratio, float length_scale,
+                                float noise_scale, float noise_scale_w, float** out_samples, int64_t* n_samples) {
+  return guarded([&] {
+    SBV2_REQUIRE(synth && bert && input_ids && attention_mask && word2ph && out_samples && n_samples, "null argument");
+    SBV2_REQUIRE(!synth->is_bert, "synthesize called on a BERT model");
+    SBV2_REQUIRE(bert->is_bert, "bert_predict called on a synthesizer model");
+    SBV2_REQUIRE(synth->device == bert->device, "the BERT and synthesizer models must live on the same device");
+    SBV2_REQUIRE(t_tok > 0 && t_x > 0, "empty input");
+    *out_samples = nullptr;
+    // phoneme -> token row (tts_util.rs:129-154: token i is repeated word2ph[i] times)
+    std::vector<int64_t> ph2tok;
+    ph2tok.reserve(size_t(t_x));
+    for (int64_t i = 0; i < t_tok; ++i) {
+      SBV2_REQUIRE(word2ph[i] >= 0, "negative word2ph entry");
+      for (int32_t j = 0; j < word2ph[i]; ++j) ph2tok.push_back(i);
+    }
+    SBV2_REQUIRE(int64_t(ph2tok.size()) == t_x, "sum(word2ph) must equal the number of phonemes");
+    const float* rows = bert_forward_device(bert, input_ids, attention_mask, 1, t_tok);
+    SBV2_REQUIRE(rows != nullptr, "attention_mask selects no token");
+    cudaEvent_t ready = nullptr;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    struct EventGuard {
+      cudaEvent_t e;
+      ~EventGuard() { cudaEventDestroy(e); }
+    } guard{ready};
+    CUDA_CHECK(cudaEventRecord(ready, bert->stream));
+    DeviceBert dev;
+    dev.rows = rows;
+    dev.n_rows = t_tok;
+    dev.hidden = bert_hidden(bert);
+    dev.ph2tok = ph2tok.data();
+    dev.ready = ready;
+    sbv2_utterance u{};
+    u.x_tst = x_tst;
+    u.tones = tones;
+    u.lang_ids = lang_ids;
+    u.t_x = t_x;
+    u.sid = sid;
+    u.style_vec = style_vec;
+    u.sdp_ratio = sdp_ratio;
+    u.length_scale = length_scale;
+    u.noise_scale = noise_scale;
+    u.noise_scale_w = noise_scale_w;
+    std::unique_ptr<sbv2_device_batch, void (*)(sbv2_device_batch*)> b(synth_upload(synth, &u, 1, &dev), synth_batch_free);
+    synth_run(synth, b.get());
+    synth_download(synth, b.get(), out_samples, n_samples, nullptr, nullptr);  // synchronises: the BERT rows are free again
+  });
+}
+
 int sbv2_synthesize(sbv2_model* synth, const float* bert, const int64_t* x_tst, const int64_t* tones, const int64_t* lang_ids,
                     int64_t t_x, int64_t sid, const float* style_vec, float sdp_ratio, float length_scale, float noise_scale,
                     float noise_scale_w, float** out_samples, int64_t* n_samples) {

@@ -88,7 +88,15 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device);
 sbv2_model* create_bert_model(const OnnxModel& m, int device);
 
 // synthesizer entry points (synth_model.cu)
-sbv2_device_batch* synth_upload(sbv2_model* m, const sbv2_utterance* utts, int batch);
+// BERT features of one utterance that are already on the synthesizer's device (sbv2_synthesize_from_tokens)
+struct DeviceBert {
+  const float* rows = nullptr;     // [n_rows, hidden] fp32 on the device
+  int64_t n_rows = 0;
+  int hidden = 0;
+  const int64_t* ph2tok = nullptr;  // host, [t_x]: BERT row of each phoneme
+  cudaEvent_t ready = nullptr;      // recorded on the producer's stream after the rows were written
+};
+sbv2_device_batch* synth_upload(sbv2_model* m, const sbv2_utterance* utts, int batch, const DeviceBert* dev_bert = nullptr);
 void synth_run(sbv2_model* m, sbv2_device_batch* b);
 void synth_download(sbv2_model* m, sbv2_device_batch* b, float** out_samples, int64_t* out_n, int32_t** out_dur,
                     int32_t** out_f2p);
@@ -101,6 +109,8 @@ void synth_decode(sbv2_model* m, const float* const* z, const int64_t* t_y, cons
 
 // bert entry points (bert_model.cu)
 void bert_predict(sbv2_model* m, const int64_t* ids, const int64_t* mask, int batch, int64_t s, float* out);
+// features stay on the device ([batch, s, hidden], zero rows where the mask is 0); null when no token is valid
+const float* bert_forward_device(sbv2_model* m, const int64_t* ids, const int64_t* mask, int batch, int64_t s);
 int bert_hidden(const sbv2_model* m);
 
 }  // namespace sbv2

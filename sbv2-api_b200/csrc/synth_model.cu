@@ -170,6 +170,10 @@ struct sbv2_device_batch {
          o_bert_off = 0, o_nsdp_off = 0, o_style = 0, o_bert = 0, o_nsdp = 0, o_zp_off = 0, o_zp_ld = 0;
   bool ran = false;
   bool decode_only = false;
+  // BERT rows already on this device (batch 1): gathered by ph2tok (int64 [t_x] at o_bert) instead of uploaded
+  const float* dev_bert_rows = nullptr;
+  int64_t dev_bert_n = 0;
+  cudaEvent_t dev_bert_ready = nullptr;
 };
 
 namespace sbv2 {
@@ -864,7 +868,7 @@ void synth_set_seed(sbv2_model* m, uint64_t seed) {
 // ---------------------------------------------------------------------------------------------
 // upload
 // ---------------------------------------------------------------------------------------------
-sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int batch) {
+sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int batch, const DeviceBert* dev_bert) {
   auto* M = static_cast<SynthModel*>(mm);
   SBV2_REQUIRE(!M->is_bert, "synthesize called on a BERT model");
   SBV2_REQUIRE(utts && batch > 0, "empty batch");
@@ -881,7 +885,7 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
     const sbv2_utterance& u = utts[i];
     SBV2_REQUIRE(u.t_x > 0, "t_x must be positive");
     SBV2_REQUIRE(u.t_x < (1 << 20), "t_x too large");
-    SBV2_REQUIRE(u.bert && u.x_tst && u.tones && u.lang_ids && u.style_vec, "null input pointer");
+    SBV2_REQUIRE((u.bert || dev_bert) && u.x_tst && u.tones && u.lang_ids && u.style_vec, "null input pointer");
     SBV2_REQUIRE(u.sid >= 0 && u.sid < hp.n_speakers, "speaker id out of range");
     SBV2_REQUIRE(std::isfinite(u.sdp_ratio) && std::isfinite(u.length_scale) && std::isfinite(u.noise_scale) && std::isfinite(u.noise_scale_w),
                  "non-finite scalar input");
@@ -906,6 +910,15 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
   b->has_noise_sdp = n_nsdp > 0;
   b->has_noise_zp = n_nzp > 0;
   b->Nx = nx;
+  if (dev_bert) {
+    SBV2_REQUIRE(batch == 1, "device-resident BERT features are supported for one utterance per call");
+    SBV2_REQUIRE(dev_bert->rows && dev_bert->ph2tok && dev_bert->hidden == hp.bert_dim, "BERT hidden size does not match the synthesizer");
+    for (int64_t t = 0; t < nx; ++t)
+      SBV2_REQUIRE(dev_bert->ph2tok[t] >= 0 && dev_bert->ph2tok[t] < dev_bert->n_rows, "word2ph maps a phoneme past the last token");
+    b->dev_bert_rows = dev_bert->rows;
+    b->dev_bert_n = dev_bert->n_rows;
+    b->dev_bert_ready = dev_bert->ready;
+  }
 
   // blob layout
   size_t off = 0;
@@ -975,6 +988,11 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
   // utterance overlaps the staging memcpy of the next
   CUDA_CHECK(cudaMemcpyAsync(b->in.p, h, b->o_bert, cudaMemcpyHostToDevice, M->stream));
   CUDA_CHECK(cudaMemcpyAsync(b->in.as<uint8_t>() + b->o_nsdp, h + b->o_nsdp, size_t(nx) * 2 * 4, cudaMemcpyHostToDevice, M->stream));
+  if (dev_bert) {
+    // the feature region only carries the phoneme -> token-row map
+    memcpy(hbert, dev_bert->ph2tok, size_t(nx) * 8);
+    CUDA_CHECK(cudaMemcpyAsync(b->in.as<uint8_t>() + b->o_bert, hbert, size_t(nx) * 8, cudaMemcpyHostToDevice, M->stream));
+  } else
   for (int i = 0; i < batch; ++i) {
     const size_t off_f = size_t(b->xstart[i]) * hp.bert_dim, cnt = size_t(b->xlen[i]) * hp.bert_dim * 4;
     memcpy(hbert + off_f, utts[i].bert, cnt);
@@ -1210,8 +1228,14 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     launch_zero_gaps(ctx, F.tg_split, nblk * M.text_tc_max_cin, TG, B);  // the splits only ever write utterance rows
   }
   launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
-  launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_bert), reinterpret_cast<const int64_t*>(in + b->o_bert_off),
-                  nullptr, bert, hp.bert_dim, xseg);
+  if (b->dev_bert_rows) {
+    // tts_util.rs:129-154 on the device: phoneme row i is the BERT row of its token (word2ph repeat), no transposes
+    if (b->dev_bert_ready) CUDA_CHECK(cudaStreamWaitEvent(M.stream, b->dev_bert_ready, 0));
+    launch_gather_rows(ctx, bert, b->dev_bert_rows, reinterpret_cast<const int64_t*>(in + b->o_bert), int(Nx), hp.bert_dim,
+                       int(b->dev_bert_n));
+  } else
+    launch_cm_to_rm(ctx, reinterpret_cast<const float*>(in + b->o_bert), reinterpret_cast<const int64_t*>(in + b->o_bert_off),
+                    nullptr, bert, hp.bert_dim, xseg);
   F.conv(M.bert_proj, bert, hp.bert_dim, h, H, xseg);
   F.conv(M.style_proj, d_style, hp.style_dim, style_emb, H, bseg);
   launch_embed_combine(ctx, h, d_x, d_tone, d_lang, M.emb, M.tone_emb, M.lang_emb, style_emb, H, hp.n_vocab, hp.n_tones,

@@ -79,6 +79,28 @@ std::vector<float> synthesize(Session& session, const Array2& bert_ori, const st
   return out;
 }
 
+std::vector<float> synthesize_from_tokens(Session& session, Session& bert, const std::vector<int64_t>& token_ids,
+                                          const std::vector<int64_t>& attention_masks, const std::vector<int32_t>& word2ph,
+                                          const std::vector<int64_t>& x_tst, const std::vector<int64_t>& spk_ids,
+                                          const std::vector<int64_t>& tones, const std::vector<int64_t>& lang_ids,
+                                          const std::vector<float>& style_vector, float sdp_ratio, float length_scale,
+                                          float noise_scale, float noise_scale_w) {
+  const int64_t t_x = int64_t(x_tst.size());
+  if (spk_ids.size() != 1) throw Error(ErrorKind::OrtError, "sid must have exactly one element");
+  if (int64_t(tones.size()) != t_x || int64_t(lang_ids.size()) != t_x)
+    throw Error(ErrorKind::OrtError, "x_tst, tones and language must agree on x_tst_max_length");
+  if (token_ids.size() != attention_masks.size() || word2ph.size() != token_ids.size())
+    throw Error(ErrorKind::OtherError, "word2ph length must equal the number of BERT rows");
+  float* samples = nullptr;
+  int64_t n = 0;
+  check(sbv2_synthesize_from_tokens(session.get(), bert.get(), token_ids.data(), attention_masks.data(), int64_t(token_ids.size()),
+                                    word2ph.data(), x_tst.data(), tones.data(), lang_ids.data(), t_x, spk_ids[0], style_vector.data(),
+                                    sdp_ratio, length_scale, noise_scale, noise_scale_w, &samples, &n));
+  std::vector<float> out(samples, samples + n);
+  sbv2_free(samples);
+  return out;
+}
+
 }  // namespace model
 
 namespace bert {

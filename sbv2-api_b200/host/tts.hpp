@@ -56,6 +56,14 @@ std::vector<float> synthesize(Session& session, const Array2& bert_ori /*[1024,T
                               const std::vector<int64_t>& spk_ids, const std::vector<int64_t>& tones,
                               const std::vector<int64_t>& lang_ids, const std::vector<float>& style_vector, float sdp_ratio,
                               float length_scale, float noise_scale, float noise_scale_w);
+// Additive entry: bert::predict + tts_util word2ph expansion + synthesize in one call, the BERT
+// features never leave the device.  Same result as the three separate calls.
+std::vector<float> synthesize_from_tokens(Session& session, Session& bert, const std::vector<int64_t>& token_ids,
+                                          const std::vector<int64_t>& attention_masks, const std::vector<int32_t>& word2ph,
+                                          const std::vector<int64_t>& x_tst, const std::vector<int64_t>& spk_ids,
+                                          const std::vector<int64_t>& tones, const std::vector<int64_t>& lang_ids,
+                                          const std::vector<float>& style_vector, float sdp_ratio, float length_scale,
+                                          float noise_scale, float noise_scale_w);
 }  // namespace model
 
 namespace bert {

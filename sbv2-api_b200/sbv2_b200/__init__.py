@@ -61,6 +61,8 @@ def _load() -> C.CDLL:
         "sbv2_bert_predict_batch": (C.c_int, [vp, pi64, pi64, C.c_int, i64, pf]),
         "sbv2_bert_hidden_size": (C.c_int, [vp, C.POINTER(C.c_int)]),
         "sbv2_synthesize": (C.c_int, [vp, pf, pi64, pi64, pi64, i64, i64, pf, f32, f32, f32, f32, C.POINTER(pf), pi64]),
+        "sbv2_synthesize_from_tokens": (C.c_int, [vp, vp, pi64, pi64, i64, pi32, pi64, pi64, pi64, i64, i64, pf, f32, f32, f32, f32,
+                                                  C.POINTER(pf), pi64]),
         "sbv2_model_seed": (C.c_int, [vp, C.c_uint64]),
         "sbv2_synthesize_with_noise": (C.c_int, [vp, pf, pi64, pi64, pi64, i64, i64, pf, f32, f32, f32, f32, pf, pf, i64,
                                                  C.POINTER(pf), pi64, pi32, C.POINTER(pi32), pi64]),
@@ -313,6 +315,21 @@ class Model:
         _check(lib.sbv2_synthesize(self._h, _pf(bert), _pi64(x), _pi64(t), _pi64(l), x.size, int(spk[0]), _pf(sv), sdp_ratio,
                                    length_scale, noise_scale, noise_scale_w, C.byref(p), C.byref(n)))
         return _take(p, n.value, np.float32).reshape(1, 1, -1)
+
+    def synthesize_from_tokens(self, bert_model: "Model", token_ids, attention_masks, word2ph, x_tst, sid: int, tones, lang_ids,
+                               style_vector, sdp_ratio: float, length_scale: float, noise_scale: float,
+                               noise_scale_w: float) -> np.ndarray:
+        """bert::predict -> word2ph expansion -> synthesize with the BERT features kept on the device (SURVEY §8f row 1).
+        -> audio [N]."""
+        ids, mask, w2p = _i64(token_ids), _i64(attention_masks), np.ascontiguousarray(word2ph, dtype=np.int32)
+        x, t, l, sv = _i64(x_tst), _i64(tones), _i64(lang_ids), _f32(style_vector)
+        if ids.size != mask.size or w2p.size != ids.size or t.size != x.size or l.size != x.size:
+            raise Sbv2Error(ERR_INVALID_ARGUMENT, "inconsistent input shapes")
+        p, n = C.POINTER(C.c_float)(), C.c_int64()
+        _check(lib.sbv2_synthesize_from_tokens(self._h, bert_model._h, _pi64(ids), _pi64(mask), ids.size,
+                                               w2p.ctypes.data_as(C.POINTER(C.c_int32)), _pi64(x), _pi64(t), _pi64(l), x.size, sid,
+                                               _pf(sv), sdp_ratio, length_scale, noise_scale, noise_scale_w, C.byref(p), C.byref(n)))
+        return _take(p, n.value, np.float32)
 
     def synthesize_with_noise(self, bert_ori, x_tst, sid: int, tones, lang_ids, style_vector, sdp_ratio, length_scale,
                               noise_scale, noise_scale_w, noise_sdp, noise_zp):

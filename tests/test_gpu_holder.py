@@ -138,3 +138,39 @@ def test_bert_features_expansion(S, blobs):
     # the expansion itself is exact: repeated columns are bit-identical
     assert np.array_equal(got[:, 0], got[:, 2]) and np.array_equal(got[:, 3], got[:, 6])
     h.close()
+
+
+def test_synthesize_from_tokens_matches_host_expansion(S):
+    """SURVEY §8f row 1: bert::predict + word2ph repeat + synthesize with the BERT features kept on the device is
+    bit-identical to the three separate calls (same generator state), including zero-length word2ph entries."""
+    import torch
+    from oracle import deberta as od
+    from oracle import vits as ov
+    from sbv2_b200 import assets
+    import util
+    hp = ov.tiny_hparams(bert_dim=128)
+    _, onnx = util.synth_assets(hp, seed=0)
+    synth = S.Model(onnx, bert=False)
+    cfg = od.tiny_config()
+    bert = S.Model(assets.deberta_onnx(od.state_dict_numpy(od.build_model(cfg, seed=1))), bert=True)
+    assert bert.hidden_size() == hp.bert_dim
+    word2ph = np.array([1, 2, 3, 0, 2, 4, 1, 2, 4], np.int32)  # sum = 19 (odd, as the frontend's blank interleave gives)
+    t_tok, t_x = len(word2ph), int(word2ph.sum())
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(3, cfg.vocab_size, (t_tok,), generator=g).numpy()
+    mask = np.ones(t_tok, np.int64)
+    x, tone, lang, _, style = ov.synthetic_inputs(hp, t_x, seed=11)
+    x, tone, lang, style = x[0].numpy(), tone[0].numpy(), lang[0].numpy(), style[0].numpy()
+    feats = bert.predict(ids, mask)                          # [t_tok, 128]
+    expanded = np.repeat(feats, word2ph, axis=0).T.copy()    # tts_util.rs:129-154 -> [128, t_x]
+    synth.seed(123)
+    a = synth.synthesize(expanded, x, [0], tone, lang, style, 0.2, 1.0, 0.677, 0.8).reshape(-1)
+    synth.seed(123)
+    b = synth.synthesize_from_tokens(bert, ids, mask, word2ph, x, 0, tone, lang, style, 0.2, 1.0, 0.677, 0.8)
+    assert a.shape == b.shape and a.size > 0
+    assert np.array_equal(a, b)
+    # error paths: word2ph that does not cover the phonemes, models swapped
+    with pytest.raises(S.Sbv2Error):
+        synth.synthesize_from_tokens(bert, ids, mask, word2ph[::-1].copy() * 0 + 1, x, 0, tone, lang, style, 0.2, 1.0, 0.677, 0.8)
+    with pytest.raises(S.Sbv2Error):
+        bert.synthesize_from_tokens(synth, ids, mask, word2ph, x, 0, tone, lang, style, 0.2, 1.0, 0.677, 0.8)
