@@ -271,13 +271,49 @@ std::vector<uint8_t> TTSModelHolder::easy_synthesize(const std::string& ident, c
                              options.length_scale, 0.677f, 0.8f);
   };
   if (options.split_sentences) {
+    // tts.rs:290-326 runs the lines one after the other; here the non-empty lines of a request go through the
+    // synthesizer as ONE batch and the 22 050-sample pauses are laid out around the results.
+    TTSModel* m = find_model(ident);
+    if (!m || !m->vits2) throw Error(ErrorKind::ModelNotFoundError, "model not found error: " + ident);
+    std::vector<sbv2_utterance> utts;
+    std::vector<size_t> line_of;
     for (size_t i = 0; i < lines.size(); ++i) {
       if (!lines[i]) continue;  // empty line
-      std::vector<float> a = synth_one(*lines[i]);
-      audio.insert(audio.end(), a.begin(), a.end());
-      if (i != lines.size() - 1) audio.insert(audio.end(), 22050, 0.0f);
+      const ParsedText& t = *lines[i];
+      const int64_t t_x = int64_t(t.phones.size());
+      if (int64_t(t.tones.size()) != t_x || int64_t(t.lang_ids.size()) != t_x || t.bert_ori.cols != t_x)
+        throw Error(ErrorKind::OrtError, "x_tst, tones, language and bert must agree on x_tst_max_length");
+      sbv2_utterance u{};
+      u.bert = t.bert_ori.data.data();
+      u.x_tst = t.phones.data();
+      u.tones = t.tones.data();
+      u.lang_ids = t.lang_ids.data();
+      u.t_x = t_x;
+      u.sid = speaker_id;
+      u.style_vec = style_vector.data();
+      u.sdp_ratio = options.sdp_ratio;
+      u.length_scale = options.length_scale;
+      u.noise_scale = 0.677f;
+      u.noise_scale_w = 0.8f;
+      utts.push_back(u);
+      line_of.push_back(i);
     }
-    if (audio.empty() && lines.empty()) throw Error(ErrorKind::NdArrayError, "NDArray error: nothing to concatenate");
+    if (utts.empty() && lines.empty()) throw Error(ErrorKind::NdArrayError, "NDArray error: nothing to concatenate");
+    if (!utts.empty()) {
+      float* samples = nullptr;
+      std::vector<int64_t> n(utts.size(), 0);
+      check(sbv2_synthesize_batch(m->vits2->get(), utts.data(), int(utts.size()), &samples, n.data(), nullptr, nullptr));
+      size_t total = 0;
+      for (size_t k = 0; k < utts.size(); ++k) total += size_t(n[k]) + (line_of[k] != lines.size() - 1 ? 22050 : 0);
+      audio.reserve(total);
+      const float* src = samples;
+      for (size_t k = 0; k < utts.size(); ++k) {
+        audio.insert(audio.end(), src, src + n[k]);
+        src += n[k];
+        if (line_of[k] != lines.size() - 1) audio.insert(audio.end(), 22050, 0.0f);
+      }
+      sbv2_free(samples);
+    }
   } else {
     if (lines.size() != 1 || !lines[0]) throw Error(ErrorKind::ValueError, "split_sentences=false expects exactly one parsed text");
     audio = synth_one(*lines[0]);
