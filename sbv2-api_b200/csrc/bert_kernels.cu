@@ -104,17 +104,21 @@ __global__ void scatter_rows_kernel(float* out, const float* h, int C, int S, Pl
 // most 127 rows (idx is monotone in i-j), so both bias terms are small tile GEMMs followed by a gather.
 // ---------------------------------------------------------------------------------------------
 constexpr int BQ = 64, BK = 64, BD = 64, BP = 128;
+// row pitches (floats) of the shared-memory tiles: multiples of 4 so that the GEMM inner loops read their operands with
+// 16-byte loads (3 LDS.128 per 32 FMA instead of 12 LDS.32)
+constexpr int PQ = BQ + 4, PK = BK + 4, PPS = BQ + 4, PPT = BP + 4, PCP = BP + 2;
 
-__global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, const __half* qkv, const float* pos_k, const float* pos_q,
-                                                                const int* bucket_idx, int max_rel, int heads, PlanarSegs s) {
-  extern __shared__ float sm[];
-  float* Qt = sm;                     // [BD][BQ+1]   (scaled)
-  float* Kt = Qt + BD * (BQ + 1);     // [BD][BK+1]
-  float* Vs = Kt + BD * (BK + 1);     // [BK][BD]
-  float* Ps = Vs + BK * BD;           // [BQ][BK+1]
-  float* Pt = Ps + BQ * (BK + 1);     // [BD][BP+1]   position rows (transposed), posK then posQ
-  float* C2P = Pt + BD * (BP + 1);    // [BQ][BP+1]
-  float* P2C = C2P + BQ * (BP + 1);   // [BK][BP+1]
+// pos_k_t / pos_q_t: the position projections transposed to [hidden][n_pos] so that a tile's rows load coalesced
+__global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, const __half* qkv, const float* pos_k_t, const float* pos_q_t,
+                                                                int n_pos, const int* bucket_idx, int max_rel, int heads, PlanarSegs s) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qt = sm;                     // [BD][PQ]   (scaled)
+  float* Kt = Qt + BD * PQ;           // [BD][PK]
+  float* Pt = Kt + BD * PK;           // [BD][PPT]  position rows (transposed), posK then posQ
+  float* Pst = Pt;                    // [BK][PPS]  probabilities, key-major (Pt is dead once both bias tiles exist)
+  __half* Vs = reinterpret_cast<__half*>(Pt + BD * PPT);  // [BK][BD]
+  __half* C2P = Vs + BK * BD;         // [BQ][PCP]  bias tiles in fp16 (110 KB per CTA: two CTAs per SM overlap each
+  __half* P2C = C2P + BQ * PCP;       // [BK][PCP]   other's synchronous load phases)
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int len = s.len[b];
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) Qt[(pl * 8 + e) * (BQ + 1) + r] = f[e];
+    for (int e = 0; e < 8; ++e) Qt[(pl * 8 + e) * PQ + r] = f[e];
   }
 
   float m_run[4], l_run[4], o[4][4];
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        Kt[(pl * 8 + e) * (BK + 1) + r] = kf[e];
-        Vs[r * BD + pl * 8 + e] = vf[e];
+        Kt[(pl * 8 + e) * PK + r] = kf[e];
+        Vs[r * BD + pl * 8 + e] = __float2half_rn(vf[e]);
       }
     }
     // position range of this tile pair: delta = i - j in [q0-k0-63, q0-k0+63]
@@ -186,37 +190,39 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
     const int pmin = bucket_idx[dmin + max_rel], pmax = bucket_idx[dmax + max_rel];
     const int np = pmax - pmin + 1;  // <= 127
     for (int phase = 0; phase < 2; ++phase) {
-      const float* pos = phase == 0 ? pos_k : pos_q;
+      const float* pos = phase == 0 ? pos_k_t : pos_q_t;
       __syncthreads();  // Pt free (and K/V/Q tiles visible on the first pass)
-      for (int i = tid; i < np * BD; i += 256) {
-        const int pr = i / BD, d = i % BD;
-        Pt[d * (BP + 1) + pr] = pos[(size_t)(pmin + pr) * HD + h * BD + d];
+      for (int d = tid >> 5; d < BD; d += 8) {
+        const float* src = pos + (size_t)(h * BD + d) * n_pos + pmin;
+        for (int pr = tid & 31; pr < BP; pr += 32) Pt[d * PPT + pr] = pr < np ? src[pr] : 0.f;
       }
       __syncthreads();
-      // [64 x np] = X[64 x 64] . Pt[64 x np]; thread: rows ty*4.., cols tx*8..
+      // [64 x 128] = X[64 x 64] . Pt[64 x 128]; thread: rows ty*4.., cols tx*8..
       float acc[4][8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
       const float* X = phase == 0 ? Qt : Kt;
+      const int px = phase == 0 ? PQ : PK;
+#pragma unroll 4
       for (int d = 0; d < BD; ++d) {
-        float xa[4], pb[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xa[i] = X[d * (BQ + 1) + ty * 4 + i];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) pb[c] = Pt[d * (BP + 1) + tx * 8 + c];
+        const float4 xa = *reinterpret_cast<const float4*>(X + d * px + ty * 4);
+        const float4 p0 = *reinterpret_cast<const float4*>(Pt + d * PPT + tx * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(Pt + d * PPT + tx * 8 + 4);
+        const float xr[4] = {xa.x, xa.y, xa.z, xa.w};
+        const float pb[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(xa[i], pb[c], acc[i][c]);
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(xr[i], pb[c], acc[i][c]);
       }
-      float* dst = phase == 0 ? C2P : P2C;
+      __half* dst = phase == 0 ? C2P : P2C;
       const float mul = phase == 0 ? 1.0f : scale;  // Q is pre-scaled, K is not
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[(ty * 4 + i) * (BP + 1) + tx * 8 + c] = acc[i][c] * mul;
+        for (int c = 0; c < 8; ++c) dst[(ty * 4 + i) * PCP + tx * 8 + c] = __float2half_rn(acc[i][c] * mul);
     }
     __syncthreads();
     float sc[4][4];
@@ -224,12 +230,12 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
+#pragma unroll 4
     for (int d = 0; d < BD; ++d) {
-      float qa[4], kb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = Qt[d * (BQ + 1) + ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) kb[j] = Kt[d * (BK + 1) + tx * 4 + j];
+      const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * PQ + ty * 4);
+      const float4 k4 = *reinterpret_cast<const float4*>(Kt + d * PK + tx * 4);
+      const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+      const float kb[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
         delta = delta < -max_rel ? -max_rel : (delta > max_rel ? max_rel : delta);
         int pi = bucket_idx[delta + max_rel] - pmin;
         pi = pi < 0 ? 0 : (pi >= np ? np - 1 : pi);
-        sc[i][j] += C2P[(ty * 4 + i) * (BP + 1) + pi] + P2C[(tx * 4 + j) * (BP + 1) + pi];
+        sc[i][j] += __half2float(C2P[(ty * 4 + i) * PCP + pi]) + __half2float(P2C[(tx * 4 + j) * PCP + pi]);
         if (kj >= len) sc[i][j] = -CUDART_INF_F;
         mx = fmaxf(mx, sc[i][j]);
       }
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float pv = (sc[i][j] == -CUDART_INF_F) ? 0.f : expf(sc[i][j] - m_new);
-        Ps[(ty * 4 + i) * (BK + 1) + tx * 4 + j] = pv;
+        Pst[(tx * 4 + j) * PPS + ty * 4 + i] = pv;
         psum += pv;
       }
 #pragma unroll
@@ -269,12 +275,13 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
       for (int c = 0; c < 4; ++c) o[i][c] *= corr;
     }
     __syncthreads();
+#pragma unroll 4
     for (int j = 0; j < BK; ++j) {
-      float pv[4], vv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = Ps[(ty * 4 + i) * (BK + 1) + j];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) vv[c] = Vs[j * BD + tx * 4 + c];
+      const float4 p4 = *reinterpret_cast<const float4*>(Pst + j * PPS + ty * 4);
+      const uint2 v4 = *reinterpret_cast<const uint2*>(Vs + j * BD + tx * 4);
+      const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&v4.x)), vb = __half22float2(*reinterpret_cast<const __half2*>(&v4.y));
+      const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+      const float vv[4] = {va.x, va.y, vb.x, vb.y};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
     }
   }
   __syncthreads();
-  float* Os = Kt;  // [BQ][BD] fits in BD*(BK+1)
+  float* Os = Kt;  // [BQ][BD] fits in BD*PK
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float inv = 1.0f / l_run[i];
@@ -334,18 +341,18 @@ void launch_scatter_rows(const LaunchCtx& ctx, float* out, const float* h, int C
   POST_LAUNCH(ctx);
 }
 
-void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k, const float* pos_q,
-                              const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s) {
+void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k_t, const float* pos_q_t,
+                              int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != BD) fail(SBV2_ERR_UNSUPPORTED, "deberta attention: head_dim must be 64");
-  size_t smem = sizeof(float) * (size_t)(BD * (BQ + 1) + BD * (BK + 1) + BK * BD + BQ * (BK + 1) + BD * (BP + 1) + BQ * (BP + 1) + BK * (BP + 1));
+  size_t smem = sizeof(float) * (size_t)(BD * PQ + BD * PK + BD * PPT) + sizeof(__half) * (size_t)(BK * BD + BQ * PCP + BK * PCP);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   dim3 grid((s.max_len + BQ - 1) / BQ, heads, s.n);
-  deberta_attention_kernel<<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k, pos_q, bucket_idx, max_rel, heads, s);
+  deberta_attention_kernel<<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s);
   POST_LAUNCH(ctx);
 }
 

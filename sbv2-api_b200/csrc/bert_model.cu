@@ -17,7 +17,7 @@ namespace {
 struct BertLayer {
   ConvLayer qkv, o, f1, f2;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
-  float *pos_k = nullptr, *pos_q = nullptr;  // [2*span, hidden] projections of LN(rel_embeddings)
+  float *pos_k = nullptr, *pos_q = nullptr;  // [hidden, 2*span] (transposed) projections of LN(rel_embeddings)
 };
 
 struct BertModel : sbv2_model {
@@ -156,6 +156,15 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
       a.seg = pseg;
       launch_conv(ctx, a);
       CUDA_CHECK(cudaStreamSynchronize(M->stream));  // `t` and wt are reused
+      {
+        // the attention kernel reads position rows per (head, channel): keep the projections transposed, [hidden][2*span]
+        const size_t np2 = size_t(2) * M->span;
+        std::vector<float> hrow(np2 * H), ht(np2 * H);
+        CUDA_CHECK(cudaMemcpy(hrow.data(), dst, hrow.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t r = 0; r < np2; ++r)
+          for (int c = 0; c < H; ++c) ht[size_t(c) * np2 + r] = hrow[r * H + c];
+        CUDA_CHECK(cudaMemcpy(dst, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice));
+      }
       (which == 0 ? B.pos_k : B.pos_q) = dst;
     }
     HostConv qkv;
@@ -288,7 +297,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     const BertLayer& B = M.layers[l];
     const __half* in = l == 0 ? embp : hp;
     umma(B.qkv, in, qkvp, nullptr, ACT_NONE);
-    launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+    launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
     umma(B.o, ctxp, nullptr, y32, ACT_NONE);
     launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln1_g, B.ln1_b, M.eps, H, ps);
     umma(B.f1, hp, f1p, nullptr, ACT_GELU);

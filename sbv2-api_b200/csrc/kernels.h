@@ -182,8 +182,8 @@ void launch_embed_rows(const LaunchCtx& ctx, float* h, const float* table, const
 // DeBERTa-v2 disentangled attention (c2p + p2c, shared keys) on planar fp16 q|k|v -> planar fp16 ctx.
 // pos_k/pos_q: fp32 [2*span, heads*64] projections of the normalised relative embeddings;
 // bucket_idx: int [2*max_rel+1] = clamp(bucket(delta) + span, 0, 2*span-1) for delta = -max_rel..max_rel.
-void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k, const float* pos_q,
-                              const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
+void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k_t, const float* pos_q_t,
+                              int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
 // out[b, t, :] = h[start[b] + t, :] for t < len[b], zeros elsewhere (out: [n, S, C] fp32)
 void launch_scatter_rows(const LaunchCtx& ctx, float* out, const float* h, int C, int S, const PlanarSegs& s);
 }  // namespace sbv2

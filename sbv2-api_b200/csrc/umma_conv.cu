@@ -39,7 +39,6 @@ constexpr int MAX_TAPS = UMMA_MAX_TAPS;
 constexpr int MAX_ASLOTS = 8;
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int SMEM_TWO_CTAS = 113 * 1024;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
@@ -453,11 +452,6 @@ int pow2_at_least(int v) {
 }
 
 uint16_t f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
-
-size_t layer_smem(int planes_per_chunk, int ra, int a_slots, size_t stage_bytes, int nstages) {
-  size_t a = (size_t(planes_per_chunk) * ra * 16 * a_slots + 127) & ~size_t(127);
-  return a + stage_bytes * nstages + 256 + 1024;  // barriers + bias
-}
 
 // wsel(g, co, ci, tap) returns the weight of group g, output channel co, input channel ci, tap index `tap`;
 // shifts[g][tap] the input-row shift of that tap.

@@ -374,7 +374,7 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
 
 // ---- test hook: one convolution through both the fp32 kernel and the tensor-core kernel -------------------
 extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const float* w, const float* bias, int cout, int k,
-                                       int dil, int mt_pref, int with_residual, int dbg_swap, float* out_umma, float* out_ref) {
+                                       int dil, int mt_pref, int with_residual, float* out_umma, float* out_ref) {
   using namespace sbv2;
   return guarded([&] {
     SBV2_REQUIRE(x && w && out_umma && out_ref && T > 0, "bad arguments");
@@ -417,7 +417,6 @@ extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const
       SBV2_REQUIRE(cin == cout, "residual test needs cin == cout");
       c.residual = xin.as<__half>();  // interpreted as lrelu-stored values
     }
-    (void)dbg_swap;
     launch_umma(ctx, L, G, G, c, 1);
     launch_from_planar(ctx, back.as<float>(), xout.as<__half>(), cout, bg.d_ystart, G, 1);
     // reference
