@@ -1,0 +1,342 @@
+// DeBERTa-v2 disentangled attention on tcgen05 tensor cores for sequences of at most 128 tokens (one query tile and one
+// key tile per (utterance, head); longer sequences use deberta_attention_kernel in bert_kernels.cu).
+//
+//   score[i][j] = (Q_i.K_j + Q_i.posK[b(i-j)] + K_j.posQ[b(i-j)]) / sqrt(3 D),   out = softmax(score) V
+//
+// For |i - j| <= 127 the log-bucket map b() of HF `make_log_bucket_position` is linear (b = i - j + span, checked on the
+// host), so the two bias terms are windows of two dense products against 256 consecutive position rows:
+//   C2P = Q posK_win^T  [128 x 256]     c2p(i, j) = C2P[i][i - j + 127]
+//   P2C = K posQ_win^T  [128 x 256]     p2c(i, j) = P2C[j][i - j + 127]
+// Both run as N = 256 MMAs into TMEM.  Their diagonal windows cannot be read from TMEM directly (a tcgen05.ld addresses
+// the same columns for every lane), so each thread copies the 128 entries of its row that are needed into a skewed
+// fp16 tile in shared memory — C2P as [i][127 - j], P2C transposed as [i][j] — and the softmax then reads plain rows.
+// P (unnormalised, fp16) goes back to shared memory as the A operand of O = P V; the row sums divide O in the epilogue.
+// oracle: oracle/deberta.py (HF DebertaV2Model, DisentangledSelfAttention).
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "kernels.h"
+
+namespace sbv2 {
+namespace {
+
+constexpr int T = 128, D = 64, DPL = D / 8, W = 256;     // tile, head dim, planes per head, position window
+constexpr uint32_t QKV_BYTES = DPL * T * 16;              // 16 KB per Q / K / V tile
+constexpr uint32_t POS_BYTES = DPL * W * 16;              // 32 KB per position window
+constexpr uint32_t P_BYTES = (T / 8) * T * 16;            // 32 KB
+constexpr int PCS = T + 2;                                // skewed bias tiles: row pitch in halfs
+constexpr uint32_t SKEW_BYTES = T * PCS * 2;              // 33 280 B each
+constexpr int TM_S = 0, TM_B = 128, TM_O = 384, TM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// no-swizzle descriptor: start (16-B units), LBO, SBO in bytes
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+constexpr uint32_t idesc_f16(int n, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// warps 0..3: one query row (and, while staging P2C, one key row) per thread; warp 4: loads + MMA issue
+// pos_k_p / pos_q_p: fp16 [heads][D/8][n_pos][8]; win0: first position row of the window (span - 127)
+__global__ void __launch_bounds__(160, 1) deberta_attention_tc_kernel(__half* out, const __half* qkv, const __half* pos_k_p,
+                                                                      const __half* pos_q_p, int n_pos, int win0, int heads,
+                                                                      PlanarSegs s) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int len = s.len[b];
+  if (len <= 0) return;
+  const long long pbase = s.pstart[b];
+
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + QKV_BYTES, sV = sK + QKV_BYTES, sPK = sV + QKV_BYTES, sPQ = sPK + POS_BYTES, sP = sPQ + POS_BYTES;
+  const uint32_t sC = sP + P_BYTES, sDd = sC + SKEW_BYTES, sBar = sDd + SKEW_BYTES;
+  const uint32_t bar_load = sBar, bar_s1 = sBar + 8, bar_c = sBar + 16, bar_s2 = sBar + 24, bar_p = sBar + 32, bar_o = sBar + 40;
+  const uint32_t tmem_slot = sBar + 48;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ));
+  __half* Cs = reinterpret_cast<__half*>(smem + (sC - sQ));   // c2p(i, j) at [i][127 - j]
+  __half* Ds = reinterpret_cast<__half*>(smem + (sDd - sQ));  // p2c(i, j) at [i][j]
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_c, 128);
+    mbar_init(bar_s2, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  const int q_plane0 = h * DPL, k_plane0 = heads * DPL + h * DPL, v_plane0 = 2 * heads * DPL + h * DPL;
+
+  if (warp == 4) {
+    // ---------------- control warp: loads and MMA issue ----------------
+    if (lane == 0) mbar_expect_tx(bar_load, 3 * QKV_BYTES + 2 * POS_BYTES);
+    __syncwarp();
+    if (lane < DPL) {
+      const size_t row8 = (size_t)pbase * 8;
+      bulk_g2s(sQ + lane * T * 16, qkv + (size_t)(q_plane0 + lane) * s.plane_stride + row8, T * 16, bar_load);
+      bulk_g2s(sK + lane * T * 16, qkv + (size_t)(k_plane0 + lane) * s.plane_stride + row8, T * 16, bar_load);
+      bulk_g2s(sV + lane * T * 16, qkv + (size_t)(v_plane0 + lane) * s.plane_stride + row8, T * 16, bar_load);
+    } else if (lane < 2 * DPL) {
+      const int pl = lane - DPL;
+      bulk_g2s(sPK + pl * W * 16, pos_k_p + ((size_t)(h * DPL + pl) * n_pos + win0) * 8, W * 16, bar_load);
+    } else if (lane < 3 * DPL) {
+      const int pl = lane - 2 * DPL;
+      bulk_g2s(sPQ + pl * W * 16, pos_q_p + ((size_t)(h * DPL + pl) * n_pos + win0) * 8, W * 16, bar_load);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    const uint64_t dq = make_desc(sQ, T * 16, 128), dk = make_desc(sK, T * 16, 128);
+    const uint64_t dpk = make_desc(sPK, W * 16, 128), dpq = make_desc(sPQ, W * 16, 128);
+    const uint64_t dp = make_desc(sP, T * 16, 128);
+    const uint64_t dv = make_desc(sV, 128, T * 16);  // MN-major B: SBO = next 8-column plane, LBO = next 8 K rows
+    constexpr uint32_t ID_S = idesc_f16(T, 0), ID_B = idesc_f16(W, 0), ID_O = idesc_f16(D, 1);
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) tc_mma_f16(tmem + TM_S, dq + (uint64_t)(k * 2 * T), dk + (uint64_t)(k * 2 * T), ID_S, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) tc_mma_f16(tmem + TM_B, dq + (uint64_t)(k * 2 * T), dpk + (uint64_t)(k * 2 * W), ID_B, k > 0 ? 1u : 0u);
+      tc_commit(bar_s1);
+    }
+    __syncwarp();
+    mbar_wait(bar_c, 0);  // C2P has been copied out of TMEM
+    tc_fence_after();
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) tc_mma_f16(tmem + TM_B, dk + (uint64_t)(k * 2 * T), dpq + (uint64_t)(k * 2 * W), ID_B, k > 0 ? 1u : 0u);
+      tc_commit(bar_s2);
+    }
+    __syncwarp();
+    mbar_wait(bar_p, 0);  // P tile (and the zeroed V rows) visible to the async proxy
+    tc_fence_after();
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp + (uint64_t)(k * 2 * T), dv + (uint64_t)(k * 16), ID_O, k > 0 ? 1u : 0u);
+      tc_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- softmax threads ----------------
+    const int row = warp * 32 + lane;  // query row i; also key row j while staging P2C
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c_scale = 1.4426950408889634f / sqrtf(3.0f * (float)D);  // log2(e) / sqrt(3 d)
+    // rows of V past the utterance must be finite (they meet P = 0): the buffer tail is not written by anyone
+    mbar_wait(bar_load, 0);
+    if (row >= len) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int pl = 0; pl < DPL; ++pl) *reinterpret_cast<uint4*>(smem + (sV - sQ) + (size_t)(pl * T + row) * 16) = z;
+    }
+    // C2P: keep columns c = i - j + 127, j in [0, 127], at Cs[i][c - i]
+    mbar_wait(bar_s1, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int q = 0; q < W / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_B + q * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int jj = q * 32 + e - row;  // 127 - j
+        if (jj >= 0 && jj < T) Cs[row * PCS + jj] = __float2half_rn(__uint_as_float(v[e]));
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar_c);
+    // P2C: thread = key row j; entry for query i = c + j - 127 goes to Ds[i][j]
+    mbar_wait(bar_s2, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int q = 0; q < W / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_B + q * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int ii = q * 32 + e + row - (T - 1);
+        if (ii >= 0 && ii < T) Ds[ii * PCS + row] = __float2half_rn(__uint_as_float(v[e]));
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // all of Ds (and Cs) written
+    // pass 1: row maximum
+    const __half* crow = Cs + row * PCS;
+    const __half* drow = Ds + row * PCS;
+    float m = -CUDART_INF_F;
+#pragma unroll 1
+    for (int q = 0; q < T / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_S + q * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = q * 32 + e;
+        const float sc = __uint_as_float(v[e]) + __half2float(crow[T - 1 - j]) + __half2float(drow[j]);
+        m = fmaxf(m, j < len ? sc : -CUDART_INF_F);
+      }
+    }
+    // pass 2: p = 2^((s - m) * c), unnormalised, fp16 into the P tile; row sum in fp32
+    float l = 0.f;
+    uint8_t* prow = smem + (sP - sQ) + row * 16;
+    const float mc = m * c_scale;
+#pragma unroll 1
+    for (int q = 0; q < T / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_S + q * 32, v);
+      tc_wait_ld();
+      float pv[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = q * 32 + e;
+        const float sc = __uint_as_float(v[e]) + __half2float(crow[T - 1 - j]) + __half2float(drow[j]);
+        const float p = j < len ? ex2_approx(fmaf(sc, c_scale, -mc)) : 0.f;
+        pv[e] = p;
+        l += p;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(pv[g * 8 + 2 * e], pv[g * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(prow + (size_t)(q * 4 + g) * T * 16) = u;
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P and V-row writes -> visible to the MMA's async proxy
+    mbar_arrive(bar_p);
+    // epilogue: O / l -> fp16 planar ctx
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+#pragma unroll 1
+    for (int q = 0; q < D / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_O + q * 32, v);
+      tc_wait_ld();
+      if (row < len) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            uh[e] = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * e]) * inv_l, __uint_as_float(v[g * 8 + 2 * e + 1]) * inv_l);
+          *reinterpret_cast<uint4*>(out + (size_t)(h * DPL + q * 4 + g) * s.plane_stride + (pbase + row) * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+bool deberta_attention_tc_supported(int head_dim, int span, int max_len) { return head_dim == D && span >= 254 && max_len <= T; }
+
+void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
+                                 int n_pos, int span, int heads, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (!deberta_attention_tc_supported(D, span, s.max_len)) fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention: unsupported shape");
+  const int win0 = span - (T - 1);
+  if (win0 < 0 || win0 + W > n_pos) fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention: position window out of range");
+  const size_t smem = 3 * QKV_BYTES + 2 * POS_BYTES + P_BYTES + 2 * SKEW_BYTES + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(heads, s.n);
+  deberta_attention_tc_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, pos_k_p, pos_q_p, n_pos, win0, heads, s);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+}  // namespace sbv2

@@ -18,6 +18,7 @@ struct BertLayer {
   ConvLayer qkv, o, f1, f2;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   float *pos_k = nullptr, *pos_q = nullptr;  // [hidden, 2*span] (transposed) projections of LN(rel_embeddings)
+  __half *pos_k_p = nullptr, *pos_q_p = nullptr;  // the same as fp16 [heads][64/8][2*span][8] (tensor-core attention operands)
 };
 
 struct BertModel : sbv2_model {
@@ -31,6 +32,8 @@ struct BertModel : sbv2_model {
   float *conv_g = nullptr, *conv_b = nullptr;
   int* bucket_idx = nullptr;  // device [2*max_rel+1]
   DBuf ids, h, embp, hp, qkvp, ctxp, f1p, y32, meta, outd;
+  void* qkvp_cleared = nullptr;  // last qkv buffer that was zero-filled (its tail rows must be finite)
+  bool use_tc_attn = true;       // SBV2_B200_BERT_ATTN=simt (read at model creation) keeps the CUDA-core attention
   PinnedBuf pin_meta, pin_io;
 };
 
@@ -82,6 +85,10 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
   if (m.find(P + "embeddings.position_embeddings.weight")) fail(SBV2_ERR_UNSUPPORTED, "position_biased_input=True is not supported");
   if (M->hidden % 64 != 0 || M->hidden > 1024) fail(SBV2_ERR_UNSUPPORTED, "hidden size must be a multiple of 64 and <= 1024");
   M->heads = M->hidden / 64;
+  {
+    const char* e = getenv("SBV2_B200_BERT_ATTN");
+    M->use_tc_attn = !(e && std::string(e) == "simt");
+  }
   M->word_emb = M->upload_f32(m.as_f32(we));
   M->emb_g = vec("embeddings.LayerNorm.weight", M->hidden);
   M->emb_b = vec("embeddings.LayerNorm.bias", M->hidden);
@@ -164,6 +171,11 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
         for (size_t r = 0; r < np2; ++r)
           for (int c = 0; c < H; ++c) ht[size_t(c) * np2 + r] = hrow[r * H + c];
         CUDA_CHECK(cudaMemcpy(dst, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice));
+        // planar fp16 per head: [head][channel / 8][row][channel % 8]
+        std::vector<__half> hp16(np2 * H);
+        for (int c = 0; c < H; ++c)
+          for (size_t r = 0; r < np2; ++r) hp16[(size_t(c / 8) * np2 + r) * 8 + c % 8] = __float2half_rn(hrow[r * H + c]);
+        (which == 0 ? B.pos_k_p : B.pos_q_p) = static_cast<__half*>(M->upload_bytes(hp16.data(), hp16.size() * 2));
       }
       (which == 0 ? B.pos_k : B.pos_q) = dst;
     }
@@ -293,11 +305,19 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     c.act_on_accum = acc32 != nullptr && act != ACT_NONE;
     launch_umma(ctx, L, G, G, c, batch);
   };
+  // sequences of at most 128 tokens: disentangled attention on the tensor cores (SBV2_B200_BERT_ATTN=simt: CUDA cores)
+  const bool tc_attn = M.use_tc_attn && M.hidden / M.heads == 64 && deberta_attention_tc_supported(64, M.span, max_len);
+  if (tc_attn && M.qkvp.p != M.qkvp_cleared) {
+    // rows past an utterance's end are read by the tensor-core attention: they must hold finite values
+    CUDA_CHECK(cudaMemsetAsync(M.qkvp.p, 0, M.qkvp.cap, M.stream));
+    M.qkvp_cleared = M.qkvp.p;
+  }
   for (int l = 0; l < M.n_run; ++l) {
     const BertLayer& B = M.layers[l];
     const __half* in = l == 0 ? embp : hp;
     umma(B.qkv, in, qkvp, nullptr, ACT_NONE);
-    launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+    if (tc_attn) launch_deberta_attention_tc(ctx, ctxp, qkvp, B.pos_k_p, B.pos_q_p, 2 * M.span, M.span, M.heads, ps);
+    else launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
     umma(B.o, ctxp, nullptr, y32, ACT_NONE);
     launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln1_g, B.ln1_b, M.eps, H, ps);
     umma(B.f1, hp, f1p, nullptr, ACT_GELU);

@@ -93,3 +93,30 @@ def test_error_paths(tiny, S):
         model.synthesize(np.zeros((1024, 3), np.float32), [0, 1, 0], [0], [0, 6, 0], [0, 1, 0], np.zeros(256, np.float32),
                          0.0, 1.0, 0.677, 0.8)
     assert model.predict([5, 6, 7], [1, 1, 1]).shape == (3, cfg.hidden_size)
+
+
+def test_tensor_core_attention_matches_cuda_core_attention(S):
+    """Sequences of at most 128 tokens run the disentangled attention on tcgen05 (bert_attention_tc.cu); the CUDA-core
+    kernel (SBV2_B200_BERT_ATTN=simt) is the cross-check, on a ragged right-padded batch."""
+    from sbv2_b200 import assets
+    cfg = od.tiny_config()
+    onnx = assets.deberta_onnx(od.state_dict_numpy(od.build_model(cfg, seed=1)))
+    tc = S.Model(onnx, bert=True)
+    os.environ["SBV2_B200_BERT_ATTN"] = "simt"
+    try:
+        simt = S.Model(onnx, bert=True)
+    finally:
+        del os.environ["SBV2_B200_BERT_ATTN"]
+    g = torch.Generator().manual_seed(9)
+    lens = [128, 1, 77, 128, 5, 100]
+    ids = torch.randint(3, cfg.vocab_size, (len(lens), 128), generator=g).numpy()
+    mask = np.zeros((len(lens), 128), np.int64)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    a = tc.predict_batch(ids, mask)
+    b_ = simt.predict_batch(ids, mask)
+    assert a.shape == b_.shape == (len(lens), 128, cfg.hidden_size)
+    assert np.isfinite(a).all()
+    for i, n in enumerate(lens):
+        assert not a[i, n:].any()
+        close(a[i, :n], b_[i, :n])
