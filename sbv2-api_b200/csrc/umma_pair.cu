@@ -92,15 +92,25 @@ __device__ __forceinline__ PTile locate_pair_item(const PairArgs& p, const PTabl
   return ti;
 }
 
+template <int C>
+struct PairShape {
+  static constexpr int c = C, mt = 128 / C, kc = C < 64 ? C : 64, nkc = C / kc, t1rows = 128 * mt, t1pitch = t1rows + 16;
+};
+
+// Channel count as a template parameter: the row-tile count, K chunking and tile pitches become constants, so the
+// epilogues' index arithmetic (divisions by C / 16, plane and pitch multiplies) folds away — it was a third of the
+// kernel's instructions (profiles/r1_ncu_full_summary.txt).
+template <int C>
 __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_constant__ PairArgs p) {
+  using K = PairShape<C>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int RA = p.t1rows + 2 * p.h1;           // input rows per chunk: t1 rows + conv1 halo
-  const int ppc = p.kc / 8;
+  const int RA = K::t1rows + 2 * p.h1;           // input rows per chunk: t1 rows + conv1 halo
+  const int ppc = K::kc / 8;
   const uint32_t slot_bytes = (uint32_t)ppc * RA * 16;
-  const uint32_t step_bytes = (uint32_t)p.c * p.kc * 2;
+  const uint32_t step_bytes = (uint32_t)K::c * K::kc * 2;
   const uint32_t stage_bytes = step_bytes * p.sps;
-  const uint32_t t1_bytes = (uint32_t)(p.c / 8) * p.t1pitch * 16;
+  const uint32_t t1_bytes = (uint32_t)(K::c / 8) * K::t1pitch * 16;
   const uint32_t sA = smem_u32(smem);
   const uint32_t sT1 = sA + ((slot_bytes * p.a_slots + 127u) & ~127u);
   const uint32_t sB = sT1 + 2 * t1_bytes;
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
   const uint32_t tmem_slot = bar_t1f + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sA));
   float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 384);  // [2][C]: b1 | b2
-  const int acc_cols = p.mt * p.c;  // one accumulator set; TMEM: acc1[0], acc1[1], acc2[0], acc2[1]
+  const int acc_cols = K::mt * K::c;  // one accumulator set; TMEM: acc1[0], acc1[1], acc2[0], acc2[1]
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) {
@@ -132,10 +142,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 2 * p.c; i += P_THREADS) bias_s[i] = i < p.c ? p.bias1[i] : p.bias2[i - p.c];
+  for (int i = threadIdx.x; i < 2 * K::c; i += P_THREADS) bias_s[i] = i < K::c ? p.bias1[i] : p.bias2[i - K::c];
   PTables tb{p.tile_prefix, p.len, p.pstart};
   if (p.n_utt <= P_TABLE_UTTS) {
-    int* tab = reinterpret_cast<int*>(bias_s + 2 * p.c);  // [n+1 | n | n]
+    int* tab = reinterpret_cast<int*>(bias_s + 2 * K::c);  // [n+1 | n | n]
     for (int i = threadIdx.x; i <= p.n_utt; i += P_THREADS) tab[i] = p.tile_prefix[i];
     for (int i = threadIdx.x; i < p.n_utt; i += P_THREADS) {
       tab[p.n_utt + 1 + i] = p.len[i];
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       auto load_a_item = [&](int it) {
         const PTile ti = locate_pair_item(p, tb, (int)blockIdx.x + it * (int)gridDim.x);
         const long long in_row0 = (long long)ti.pstart + ti.t0 - p.h2 - p.h1;
-        for (int kc = 0; kc < p.nkc; ++kc, ++a_it) {
+        for (int kc = 0; kc < K::nkc; ++kc, ++a_it) {
           const uint32_t slot = a_it % p.a_slots;
           mbar_wait(bar_ae + 8 * slot, ((a_it / p.a_slots) & 1) ^ 1);
           mbar_expect_tx(bar_af + 8 * slot, slot_bytes);
@@ -208,13 +218,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues) ----------------
-    const int k16 = p.kc / 16, mt = p.mt;
-    const uint32_t c_u = (uint32_t)p.c, idesc = p.idesc;
+    const int k16 = K::kc / 16, mt = K::mt;
+    const uint32_t c_u = (uint32_t)K::c, idesc = p.idesc;
     const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
     const uint64_t a_desc0 = desc_hi | ((uint64_t)((uint32_t)RA & 0x3FFF) << 16);
-    const uint64_t t_desc0 = desc_hi | ((uint64_t)((uint32_t)p.t1pitch & 0x3FFF) << 16);
-    const uint64_t b_desc0 = desc_hi | ((uint64_t)((uint32_t)p.c & 0x3FFF) << 16);
-    const uint32_t a_kstep = 2u * (uint32_t)RA, t_kstep = 2u * (uint32_t)p.t1pitch, b_kstep = 2u * (uint32_t)p.c;
+    const uint64_t t_desc0 = desc_hi | ((uint64_t)((uint32_t)K::t1pitch & 0x3FFF) << 16);
+    const uint64_t b_desc0 = desc_hi | ((uint64_t)((uint32_t)K::c & 0x3FFF) << 16);
+    const uint32_t a_kstep = 2u * (uint32_t)RA, t_kstep = 2u * (uint32_t)K::t1pitch, b_kstep = 2u * (uint32_t)K::c;
     uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0;
     int b_si = 0;
     bool resident_ready = false;
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       if (lane == 0) PTRACE(0, it);
       const uint32_t tacc0 = tmem_base + buf * acc_cols;
       int step = 0;
-      for (int kc = 0; kc < p.nkc; ++kc) {
+      for (int kc = 0; kc < K::nkc; ++kc) {
         mbar_wait(bar_af + 8 * a_slot_i, a_par);
         const uint64_t a_chunk = a_desc0 + ((sA + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.h1;
         for (int tap = 0; tap < p.taps; ++tap, ++step) {
@@ -286,8 +296,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       const uint32_t tacc0 = tmem_base + (2 + buf) * acc_cols;
       const uint64_t t_tile = t_desc0 + ((sT1 + buf * t1_bytes) >> 4);
       int step = 0;
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        const uint64_t t_chunk = t_tile + (uint32_t)(kc * ppc * p.t1pitch);
+      for (int kc = 0; kc < K::nkc; ++kc) {
+        const uint64_t t_chunk = t_tile + (uint32_t)(kc * ppc * K::t1pitch);
         for (int tap = 0; tap < p.taps; ++tap, ++step) {
           const uint32_t b_addr = b_step_addr(1, step);
           const uint64_t t_tap = t_chunk + (uint32_t)tap;  // out row m, tap j reads t1 row m + j
@@ -311,19 +321,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
         issue_p2(it, mtk);
       }
     };
-    switch (mt * 8 + k16) {  // (128 / C, min(C, 64) / 16)
-      case 8 * 8 + 1: run(MtK<8, 1>{}); break;
-      case 4 * 8 + 2: run(MtK<4, 2>{}); break;
-      case 2 * 8 + 4: run(MtK<2, 4>{}); break;
-      default: run(MtK<1, 4>{}); break;
-    }
+    run(MtK<K::mt, K::kc / 16>{});
   } else {
     // ---------------- epilogue warps ----------------
     const int wq = warp & 3;
     const int part = (warp - 2) >> 2;  // 4 warps per TMEM lane quarter
     constexpr int NPART = P_EPI_WARPS / 4;
     const float* b1s = bias_s;
-    const float* b2s = bias_s + p.c;
+    const float* b2s = bias_s + K::c;
     // epilogue 1: t1 = lrelu(acc + b1) -> fp16 -> shared tile; rows outside [0, len) are conv2's zero padding
     auto epi1 = [&](int it) {
       const uint32_t buf = it & 1;
@@ -335,15 +340,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       if (threadIdx.x == 64 + 15 * 32) PTRACE(10, it);
       const uint32_t tacc0 = tmem_base + buf * acc_cols;
       uint8_t* t1 = smem + (sT1 - sA) + buf * t1_bytes;
-      const int n_sub = p.mt * (p.c / 16);
+      const int n_sub = K::mt * (K::c / 16);
       for (int sub = part; sub < n_sub; sub += NPART) {
-        const int a = sub / (p.c / 16);
-        const int c0 = (sub - a * (p.c / 16)) * 16;
+        const int a = sub / (K::c / 16);
+        const int c0 = (sub - a * (K::c / 16)) * 16;
         const int r = a * 128 + wq * 32 + lane;  // t1 row of this thread
         const int pos = ti.t0 - p.h2 + r;
         const bool inside = pos >= 0 && pos < ti.len;
         uint32_t v[16];
-        tc_ld16(tacc0 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.c + c0), v);
+        tc_ld16(tacc0 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * K::c + c0), v);
         tc_wait_ld();
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
 #pragma unroll
             for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(fmaxf(f[2 * e], f[2 * e] * 0.1f), fmaxf(f[2 * e + 1], f[2 * e + 1] * 0.1f));
           }
-          *reinterpret_cast<uint4*>(t1 + ((size_t)((c0 >> 3) + pl) * p.t1pitch + r) * 16) = o;
+          *reinterpret_cast<uint4*>(t1 + ((size_t)((c0 >> 3) + pl) * K::t1pitch + r) * 16) = o;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // t1 writes -> visible to the MMA's async proxy
@@ -381,10 +386,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
       if (threadIdx.x == 64) PTRACE(6, it);
       if (threadIdx.x == 64 + 15 * 32) PTRACE(12, it);
       const uint32_t tacc0 = tmem_base + (2 + buf) * acc_cols;
-      const bool wide = (p.c % 32 == 0) && p.has_res != 3;
+      const bool wide = (K::c % 32 == 0) && p.has_res != 3;
       const int nch = wide ? 32 : 16;
-      const int per_acc = p.c / nch;
-      const int n_sub = p.mt * per_acc;
+      const int per_acc = K::c / nch;
+      const int n_sub = K::mt * per_acc;
       for (int sub = part; sub < n_sub; sub += NPART) {
         const int a = sub / per_acc;
         const int c0 = (sub - a * per_acc) * nch;
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
         const int t = ti.t0 + m;
         const bool valid = m < p.out_rows && t < ti.len;
         const long long orow = (long long)ti.pstart + t;
-        const uint32_t taddr = tacc0 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.c + c0);
+        const uint32_t taddr = tacc0 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * K::c + c0);
         if (p.has_res == 3) epilogue_item<16, false, 3>(p, taddr, valid, orow, c0, b2s + c0);
         else if (wide) epilogue_item<32, false, 1>(p, taddr, valid, orow, c0, b2s + c0);
         else epilogue_item<16, false, 1>(p, taddr, valid, orow, c0, b2s + c0);
@@ -439,7 +444,7 @@ bool make_pair_layer(sbv2_model* owner, const HostConv& c1, int dil, const HostC
   PairLayer L;
   const int C = c1.d0, k = c1.k;
   if (c1.d1 != C || c2.d0 != C || c2.d1 != C || c2.k != k || k % 2 == 0 || k > UMMA_MAX_TAPS) return false;
-  if (C % 16 != 0 || C > 128) return false;  // 4 accumulator sets of MT*C columns must fit the 512 TMEM columns
+  if (C != 16 && C != 32 && C != 64 && C != 128) return false;  // instantiated shapes; 4 accumulator sets of MT*C = 128 TMEM columns
   L.c = C;
   L.taps = k;
   L.h1 = dil * (k - 1) / 2;
@@ -501,7 +506,10 @@ bool make_pair_layer(sbv2_model* owner, const HostConv& c1, int dil, const HostC
 void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, const PairCall& c, int n_utt) {
   static bool attr = false;
   if (!attr) {
-    CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
     attr = true;
   }
   auto it = g.extra.find(L.out_rows);
@@ -561,7 +569,15 @@ void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, c
   if (g_pair_trace != nullptr) {
     if (const char* e = getenv("SBV2_B200_PAIR_GRID")) grid = std::max(1, std::min(grid, atoi(e)));  // debugging: fewer CTAs
   }
-  launch_pdl(ctx.pdl, umma_pair_kernel, dim3(grid), dim3(P_THREADS), L.smem, ctx.stream, a);
+  void (*kernel)(PairArgs) = nullptr;
+  switch (L.c) {
+    case 16: kernel = umma_pair_kernel<16>; break;
+    case 32: kernel = umma_pair_kernel<32>; break;
+    case 64: kernel = umma_pair_kernel<64>; break;
+    case 128: kernel = umma_pair_kernel<128>; break;
+    default: fail(SBV2_ERR_INTERNAL, "fused ResBlock pair: unsupported channel count");
+  }
+  launch_pdl(ctx.pdl, kernel, dim3(grid), dim3(P_THREADS), L.smem, ctx.stream, a);
   ctx.count();
 }
 
