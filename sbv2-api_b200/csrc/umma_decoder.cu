@@ -135,8 +135,9 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
     D->cond_w = owner->upload_f32(t);
     D->cond_b = owner->upload_f32(w.cond.b);
   }
-  // ResBlock pairs are fused for C <= 64: there the unfused convs are bound by HBM traffic, not by the tensor pipe
-  // (C = 128 would stream 2 x 360 KB of weights from L2 per 118 output rows).  SBV2_B200_PAIR_MAXC=0 disables fusion.
+  // ResBlock pairs are fused for C <= 64 (and the k = 3 pairs of C = 128): there the unfused convs are bound by HBM traffic
+  // and epilogue work, not by the tensor pipe (a C = 128, k = 11 pair would stream 2 x 360 KB of weights from L2 per 118
+  // output rows).  SBV2_B200_PAIR_MAXC=0 disables fusion.
   int pair_maxc = 64;
   if (const char* e = getenv("SBV2_B200_PAIR_MAXC")) pair_maxc = atoi(e);
   D->pair_heights.assign(size_t(D->n_stages) + 1, {});
@@ -155,7 +156,9 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
       std::vector<char> lf;
       for (size_t l = 0; l < w.res_c1[rb].size(); ++l) {
         PairLayer P;
-        const bool f = (w.per == 1 || w.per == 3) && C <= pair_maxc && make_pair_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], w.res_c2[rb][l], &P);
+        // C = 128 pairs are fused only for k = 3 (measured: 461 vs 523 us; k = 7 / 11 stream too many weight bytes per item)
+        const bool want = C <= pair_maxc || (C == 128 && pair_maxc >= 64 && w.res_c1[rb][l].k == 3);
+        const bool f = (w.per == 1 || w.per == 3) && want && make_pair_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], w.res_c2[rb][l], &P);
         lf.push_back(f ? 1 : 0);
         lp.push_back(P);
         if (f) {
