@@ -63,7 +63,7 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
   {
     const char* pe = getenv("SBV2_B200_PDL");
-    M->pdl = pe && pe[0] == '1';
+    M->pdl = !(pe && pe[0] == '0');  // on by default
   }
   M->metadata = m.metadata;
   const std::string P = find_prefix(m);

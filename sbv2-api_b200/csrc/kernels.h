@@ -32,8 +32,8 @@ struct LaunchCtx {
 // Programmatic dependent launch (PDL): the grid may become resident while its predecessor in the stream drains, so its
 // prologue (barrier init, TMEM allocation, launch latency) overlaps the predecessor's tail.  The kernel MUST execute
 // griddepcontrol.wait (pdl_wait() in the kernels) before it reads or writes anything another kernel touches.
-// Measured on the bench workload: -0.7 ms of 31 on a single stream, but -3 % aggregate with two replicas per GPU (the
-// early-resident CTAs hold SMs the other replica would use), so it is opt-in (SBV2_B200_PDL=1; latency-oriented serving).
+// Measured on the bench workload: -0.65 ms of 29 on a single stream (batch-1 latency 5.3 -> 4.9 ms) and neutral for two
+// replicas per GPU once the mbarrier waits sleep instead of polling; on by default, SBV2_B200_PDL=0 disables it.
 #ifdef __CUDACC__
 template <class... KArgs, class... Args>
 inline void launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

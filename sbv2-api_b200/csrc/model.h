@@ -72,7 +72,7 @@ struct sbv2_model {
   float region_ms(const std::string& name);
 
   virtual ~sbv2_model();
-  bool pdl = false;  // SBV2_B200_PDL=1 (read at model creation): programmatic dependent launch of the tensor-core kernels
+  bool pdl = true;  // programmatic dependent launch of the tensor-core kernels (SBV2_B200_PDL=0, read at model creation, disables)
   sbv2::LaunchCtx ctx() { return sbv2::LaunchCtx{stream, &launches, pdl}; }
   void bind_device() const;
   // uploads host data, tracked for release at destroy

@@ -780,7 +780,7 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
   {
     const char* pe = getenv("SBV2_B200_PDL");
-    M->pdl = pe && pe[0] == '1';
+    M->pdl = !(pe && pe[0] == '0');  // on by default
   }
   for (auto& w : M->ws) w.stream = M->stream;
   M->metadata = m.metadata;
