@@ -256,3 +256,22 @@ def test_internal_noise_is_seeded(tiny):
     assert a.shape[:2] == (1, 1) and np.array_equal(a, b)
     assert a.shape != c.shape or not np.array_equal(a, c)
     assert a.shape[2] % 512 == 0 and np.isfinite(a).all()
+
+
+def test_programmatic_dependent_launch_does_not_change_results(S):
+    """The tensor-core kernels are launched with programmatic stream serialization by default; SBV2_B200_PDL=0 launches
+    them normally.  Same inputs and noise -> bit-identical audio and alignment."""
+    hp = ov.HParams()
+    oracle, onnx = util.synth_assets(hp, seed=0)
+    u = util.make_utterance(hp, 45, seed=21, sdp_ratio=0.3)
+    outs = []
+    for pdl in ("1", "0"):
+        os.environ["SBV2_B200_PDL"] = pdl
+        try:
+            model = S.Model(onnx, bert=False)
+        finally:
+            del os.environ["SBV2_B200_PDL"]
+        outs.append(run_gpu(model, u))
+        del model
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
