@@ -37,7 +37,7 @@ constexpr int GAP = UMMA_GAP;
 constexpr int TAIL_ROWS = UMMA_TAIL_ROWS;
 constexpr int MAX_TAPS = UMMA_MAX_TAPS;
 constexpr int MAX_ASLOTS = 8;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
                  bar_accf = bar_be + 8 * MAX_STAGES, bar_acce = bar_accf + 16;
   const uint32_t tmem_slot = bar_acce + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sA));
-  float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 256);  // [2][NB]
+  float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 320);  // [2][NB] (after 36 barriers + the TMEM slot)
   const int acc_cols = p.mt * p.nb;  // TMEM columns of one accumulator set
 
   if (threadIdx.x == 0) {
@@ -520,8 +520,12 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_group
     L.sps = std::min(L.sps, L.total_steps);
     L.nloads = (L.total_steps + L.sps - 1) / L.sps;
     const size_t stage_bytes = step_bytes * L.sps;
+    // Weight stages first: a stage is 16-25 KB and arrives after ~2 us of L2 latency, so the bytes in flight set the
+    // streaming rate (4 stages = 64 KB gave ~17 B/clk where the big decoder layers consume 32 B/clk); the activation
+    // ring needs far fewer bytes in flight, three chunk slots keep one chunk of lookahead.
+    const int ring_min_slots = std::max(2, std::min(L.nkc + 1, 3));
     for (int ns = std::min(MAX_STAGES, std::max(2, L.nloads)); ns >= 2 && !placed; --ns) {
-      for (int slots = MAX_ASLOTS; slots >= min_slots && !placed; --slots) {
+      for (int slots = std::min(MAX_ASLOTS, std::max(ring_min_slots, L.nkc + 1)); slots >= ring_min_slots && !placed; --slots) {
         size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + kMisc;
         if (sm <= size_t(SMEM_LIMIT)) {
           L.mt = mt;
