@@ -45,6 +45,10 @@ const char* sbv2_last_error(void);
 void sbv2_free(void* p);
 /* Allocates a buffer that sbv2_free releases (for host layers built above this ABI). */
 void* sbv2_alloc(size_t bytes);
+/* Page-locked host memory (cudaHostAlloc) that sbv2_free releases.  Input buffers that live in page-locked memory —
+ * from here, cudaHostAlloc or cudaHostRegister — are read by the copy engine in place; pageable inputs are staged through
+ * an internal pinned block first (one extra memcpy of the BERT features per call). */
+void* sbv2_alloc_pinned(size_t bytes);
 /* Sets the calling thread's last-error message (for host layers built above this ABI). */
 void sbv2_set_last_error(const char* message);
 /* "sbv2_b200 <version> sm_100a"; static storage. */
@@ -61,6 +65,11 @@ int sbv2_device_count(void);
  * (model.onnx inside a .sbv2, scripts/convert/convert_model.py). */
 int sbv2_model_create(const void* onnx_bytes, size_t n_bytes, int is_bert, int device_ordinal,
                       sbv2_model** out_model);
+/* Diagnostic (no device needed): JSON object describing which initializer every structurally bound weight name resolves to
+ * — real exports constant-fold weight-normed convs and 3-D-input Linears into anonymous onnx::Conv_N / transposed
+ * onnx::MatMul_N initializers (scripts/convert/convert_model.py:115-156, convert_deberta.py:36-52); the loaders recover
+ * them through the still-named biases.  `*json` is library-allocated (sbv2_free). */
+int sbv2_onnx_bind_report(const void* onnx_bytes, size_t n_bytes, int is_bert, char** json);
 /* Replaces `Drop for Session` (unload / eviction, crates/sbv2_core/src/tts.rs:182-195, :238-241):
  * frees all device and pinned buffers. NULL is allowed. */
 void sbv2_model_destroy(sbv2_model* model);
@@ -122,6 +131,31 @@ int sbv2_synthesize_from_tokens(sbv2_model* synth, sbv2_model* bert, const int64
                                 const int64_t* lang_ids, int64_t t_x, int64_t sid, const float* style_vec, float sdp_ratio,
                                 float length_scale, float noise_scale, float noise_scale_w, float** out_samples,
                                 int64_t* n_samples);
+
+/* SURVEY.md §8f row 2 — the sentences of one request as one batch: replaces the per-line loop of
+ * `easy_synthesize` (tts.rs:290-326: parse_text -> bert::predict -> synthesize per line, then concatenate with 22 050 zero
+ * samples).  DeBERTa runs once over all sentences (right-padded batch), the features stay on the device, the synthesizer
+ * runs once over all sentences, and `pause_after[i]` zero samples (NULL: none) are laid out after sentence i ON THE DEVICE,
+ * so `*out_samples` (float32 [*out_total], pinned, sbv2_free) is the concatenated audio in one D2H copy.
+ * out_n_samples (optional, int64 [batch]): synthesized samples of each sentence (without its pause).
+ * Each sentence's audio is bit-identical to sbv2_synthesize_from_tokens of that sentence with the same generator state
+ * only for batch == 1 (the internal noise stream is consumed batch-wise); durations do not depend on the batching. */
+typedef struct sbv2_token_utterance {
+  const int64_t* input_ids;      /* [t_tok] */
+  const int64_t* attention_mask; /* [t_tok], all ones */
+  int64_t t_tok;
+  const int32_t* word2ph;        /* [t_tok], sum == t_x */
+  const int64_t* x_tst;          /* [t_x] */
+  const int64_t* tones;          /* [t_x] */
+  const int64_t* lang_ids;       /* [t_x] */
+  int64_t t_x;
+  int64_t sid;
+  const float* style_vec;        /* [256] */
+  float sdp_ratio, length_scale, noise_scale, noise_scale_w;
+} sbv2_token_utterance;
+int sbv2_synthesize_from_tokens_batch(sbv2_model* synth, sbv2_model* bert, const sbv2_token_utterance* utts, int batch,
+                                      const int64_t* pause_after /* [batch] or NULL */, float** out_samples,
+                                      int64_t* out_total, int64_t* out_n_samples /* [batch] or NULL */);
 
 /* Batched, variable-length extension.  Per-utterance pointer arrays of length `batch`; every
  * utterance's result is bit-identical to its own batch-1 call.  Results land in one pinned block:
@@ -208,6 +242,8 @@ int sbv2_holder_unload(sbv2_holder* h, const char* ident, int* found);
 int sbv2_holder_models(const sbv2_holder* h, char** out);
 /* how many models currently hold device weights (vits2.is_some()). */
 int sbv2_holder_loaded_count(const sbv2_holder* h, int* out);
+/* hidden size of the holder's DeBERTa = rows of every `bert` feature matrix it takes or returns (1024 for deberta-v2-large). */
+int sbv2_holder_bert_hidden_size(const sbv2_holder* h, int* out);
 int sbv2_holder_get_style_vector(sbv2_holder* h, const char* ident, int32_t style_id, float weight,
                                  float* out /* [256] */);
 /* parse_text's device half: BERT over the token ids, then the word2ph row repeat + transpose
@@ -220,7 +256,7 @@ int sbv2_holder_bert_features(sbv2_holder* h, const int64_t* token_ids, const in
  * `line_index[i]` the position of sentence i, so the trailing-silence rule of tts.rs:318-320 is
  * reproduced), then WAV bytes. */
 typedef struct sbv2_sentence {
-  const float* bert;       /* [1024, t_x] */
+  const float* bert;       /* [hidden, t_x], hidden = sbv2_holder_bert_hidden_size (1024 for deberta-v2-large) */
   const int64_t* phones;   /* [t_x] */
   const int64_t* tones;    /* [t_x] */
   const int64_t* lang_ids; /* [t_x] */
@@ -231,6 +267,25 @@ int sbv2_holder_easy_synthesize(sbv2_holder* h, const char* ident, const sbv2_se
                                 int n_sentences, int64_t total_lines, int32_t style_id, int64_t speaker_id,
                                 float sdp_ratio, float length_scale, float style_weight,
                                 void** wav_bytes, size_t* wav_n);
+
+/* The same with bert::predict folded in: sentences carry the tokenizer's output and word2ph instead
+ * of BERT features.  DeBERTa and the synthesizer each run once over all sentences of the request (features stay on the
+ * device), the 22 050-sample pauses are written on the device, the WAV is one header + one copy. */
+typedef struct sbv2_token_sentence {
+  const int64_t* token_ids;      /* [t_tok] */
+  const int64_t* attention_mask; /* [t_tok] */
+  const int32_t* word2ph;        /* [t_tok], sum == t_x */
+  int64_t t_tok;
+  const int64_t* phones;         /* [t_x] */
+  const int64_t* tones;          /* [t_x] */
+  const int64_t* lang_ids;       /* [t_x] */
+  int64_t t_x;
+  int64_t line_index;
+} sbv2_token_sentence;
+int sbv2_holder_easy_synthesize_tokens(sbv2_holder* h, const char* ident, const sbv2_token_sentence* sentences,
+                                       int n_sentences, int64_t total_lines, int32_t style_id, int64_t speaker_id,
+                                       float sdp_ratio, float length_scale, float style_weight,
+                                       void** wav_bytes, size_t* wav_n);
 
 #ifdef __cplusplus
 }

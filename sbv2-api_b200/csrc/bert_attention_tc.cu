@@ -328,11 +328,8 @@ void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __
   const int win0 = span - (T - 1);
   if (win0 < 0 || win0 + W > n_pos) fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention: position window out of range");
   const size_t smem = 3 * QKV_BYTES + 2 * POS_BYTES + P_BYTES + 2 * SKEW_BYTES + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
   dim3 grid(heads, s.n);
   deberta_attention_tc_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, pos_k_p, pos_q_p, n_pos, win0, heads, s);
   CUDA_CHECK(cudaGetLastError());

@@ -3,6 +3,8 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace sbv2 {
@@ -108,17 +110,33 @@ constexpr int BQ = 64, BK = 64, BD = 64, BP = 128;
 // 16-byte loads (3 LDS.128 per 32 FMA instead of 12 LDS.32)
 constexpr int PQ = BQ + 4, PK = BK + 4, PPS = BQ + 4, PPT = BP + 4, PCP = BP + 2;
 
-// pos_k_t / pos_q_t: the position projections transposed to [hidden][n_pos] so that a tile's rows load coalesced
-__global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, const __half* qkv, const float* pos_k_t, const float* pos_q_t,
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ void from_f32(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f32(__half& d, float v) { d = __float2half_rn(v); }
+
+// pos_k_t / pos_q_t: the position projections transposed to [hidden][n_pos] so that a tile's rows load coalesced.
+// F32 = false: q|k|v planar fp16 in, planar fp16 context out, V and the bias tiles staged as fp16 (the fast path's
+// fallback for sequences the tensor-core kernel does not cover).
+// F32 = true ("exact" mode, SBV2_B200_BERT=exact): q|k|v fp32 row-major [rows, 3*heads*64] in, fp32 row-major context
+// [rows, heads*64] out, everything staged in fp32 — the features feed ceil() in the synthesizer (tts_util.rs:120-154 ->
+// model.rs:66-68), and fp16 storage between the GEMMs alone costs 5e-4 relative.
+template <bool F32>
+__global__ void __launch_bounds__(256) deberta_attention_kernel(void* out_v, const void* qkv_v, const float* pos_k_t, const float* pos_q_t,
                                                                 int n_pos, const int* bucket_idx, int max_rel, int heads, PlanarSegs s) {
+  using TS = typename std::conditional<F32, float, __half>::type;
+  __half* out = static_cast<__half*>(out_v);
+  const __half* qkv = static_cast<const __half*>(qkv_v);
+  float* out32 = static_cast<float*>(out_v);
+  const float* qkv32 = static_cast<const float*>(qkv_v);
   extern __shared__ __align__(16) float sm[];
   float* Qt = sm;                     // [BD][PQ]   (scaled)
   float* Kt = Qt + BD * PQ;           // [BD][PK]
   float* Pt = Kt + BD * PK;           // [BD][PPT]  position rows (transposed), posK then posQ
   float* Pst = Pt;                    // [BK][PPS]  probabilities, key-major (Pt is dead once both bias tiles exist)
-  __half* Vs = reinterpret_cast<__half*>(Pt + BD * PPT);  // [BK][BD]
-  __half* C2P = Vs + BK * BD;         // [BQ][PCP]  bias tiles in fp16 (110 KB per CTA: two CTAs per SM overlap each
-  __half* P2C = C2P + BQ * PCP;       // [BK][PCP]   other's synchronous load phases)
+  TS* Vs = reinterpret_cast<TS*>(Pt + BD * PPT);  // [BK][BD]
+  TS* C2P = Vs + BK * BD;             // [BQ][PCP]  bias tiles (fp16: 110 KB per CTA, two CTAs per SM overlap each
+  TS* P2C = C2P + BQ * PCP;           // [BK][PCP]   other's synchronous load phases; fp32: 152 KB, one CTA per SM)
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int len = s.len[b];
@@ -130,6 +148,8 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
   const int HD = heads * BD;
   const float scale = 1.0f / sqrtf(3.0f * BD);
   const int q_plane0 = h * DP, k_plane0 = heads * DP + h * DP, v_plane0 = 2 * heads * DP + h * DP;
+  const size_t ld32 = (size_t)3 * HD;          // F32: row pitch of qkv32
+  const size_t row32 = (size_t)s.start[b];     // F32: first packed row of this sequence
 
   for (int i = tid; i < BQ * DP; i += 256) {
     const int r = i % BQ, pl = i / BQ;
@@ -137,13 +157,20 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = 0.f;
     if (q0 + r < len) {
-      const uint4 u = *reinterpret_cast<const uint4*>(qkv + (size_t)(q_plane0 + pl) * s.plane_stride + (pbase + q0 + r) * 8);
-      const __half2* uh = reinterpret_cast<const __half2*>(&u);
+      if (F32) {
+        const float4* src = reinterpret_cast<const float4*>(qkv32 + (row32 + q0 + r) * ld32 + h * BD + pl * 8);
+        const float4 a = src[0], c = src[1];
+        f[0] = a.x * scale; f[1] = a.y * scale; f[2] = a.z * scale; f[3] = a.w * scale;
+        f[4] = c.x * scale; f[5] = c.y * scale; f[6] = c.z * scale; f[7] = c.w * scale;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(qkv + (size_t)(q_plane0 + pl) * s.plane_stride + (pbase + q0 + r) * 8);
+        const __half2* uh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 y = __half22float2(uh[e]);
-        f[2 * e] = y.x * scale;
-        f[2 * e + 1] = y.y * scale;
+        for (int e = 0; e < 4; ++e) {
+          const float2 y = __half22float2(uh[e]);
+          f[2 * e] = y.x * scale;
+          f[2 * e + 1] = y.y * scale;
+        }
       }
     }
 #pragma unroll
@@ -168,21 +195,29 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
 #pragma unroll
       for (int e = 0; e < 8; ++e) kf[e] = vf[e] = 0.f;
       if (k0 + r < len) {
-        const uint4 uk = *reinterpret_cast<const uint4*>(qkv + (size_t)(k_plane0 + pl) * s.plane_stride + (pbase + k0 + r) * 8);
-        const uint4 uv = *reinterpret_cast<const uint4*>(qkv + (size_t)(v_plane0 + pl) * s.plane_stride + (pbase + k0 + r) * 8);
-        const __half2* kh = reinterpret_cast<const __half2*>(&uk);
-        const __half2* vh = reinterpret_cast<const __half2*>(&uv);
+        if (F32) {
+          const float4* ks = reinterpret_cast<const float4*>(qkv32 + (row32 + k0 + r) * ld32 + HD + h * BD + pl * 8);
+          const float4* vs = reinterpret_cast<const float4*>(qkv32 + (row32 + k0 + r) * ld32 + 2 * HD + h * BD + pl * 8);
+          const float4 a0 = ks[0], a1 = ks[1], c0 = vs[0], c1 = vs[1];
+          kf[0] = a0.x; kf[1] = a0.y; kf[2] = a0.z; kf[3] = a0.w; kf[4] = a1.x; kf[5] = a1.y; kf[6] = a1.z; kf[7] = a1.w;
+          vf[0] = c0.x; vf[1] = c0.y; vf[2] = c0.z; vf[3] = c0.w; vf[4] = c1.x; vf[5] = c1.y; vf[6] = c1.z; vf[7] = c1.w;
+        } else {
+          const uint4 uk = *reinterpret_cast<const uint4*>(qkv + (size_t)(k_plane0 + pl) * s.plane_stride + (pbase + k0 + r) * 8);
+          const uint4 uv = *reinterpret_cast<const uint4*>(qkv + (size_t)(v_plane0 + pl) * s.plane_stride + (pbase + k0 + r) * 8);
+          const __half2* kh = reinterpret_cast<const __half2*>(&uk);
+          const __half2* vh = reinterpret_cast<const __half2*>(&uv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a = __half22float2(kh[e]), c = __half22float2(vh[e]);
-          kf[2 * e] = a.x; kf[2 * e + 1] = a.y;
-          vf[2 * e] = c.x; vf[2 * e + 1] = c.y;
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(kh[e]), c = __half22float2(vh[e]);
+            kf[2 * e] = a.x; kf[2 * e + 1] = a.y;
+            vf[2 * e] = c.x; vf[2 * e + 1] = c.y;
+          }
         }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         Kt[(pl * 8 + e) * PK + r] = kf[e];
-        Vs[r * BD + pl * 8 + e] = __float2half_rn(vf[e]);
+        from_f32(Vs[r * BD + pl * 8 + e], vf[e]);
       }
     }
     // position range of this tile pair: delta = i - j in [q0-k0-63, q0-k0+63]
@@ -217,12 +252,12 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(xr[i], pb[c], acc[i][c]);
       }
-      __half* dst = phase == 0 ? C2P : P2C;
+      TS* dst = phase == 0 ? C2P : P2C;
       const float mul = phase == 0 ? 1.0f : scale;  // Q is pre-scaled, K is not
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[(ty * 4 + i) * PCP + tx * 8 + c] = __float2half_rn(acc[i][c] * mul);
+        for (int c = 0; c < 8; ++c) from_f32(dst[(ty * 4 + i) * PCP + tx * 8 + c], acc[i][c] * mul);
     }
     __syncthreads();
     float sc[4][4];
@@ -252,7 +287,7 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
         delta = delta < -max_rel ? -max_rel : (delta > max_rel ? max_rel : delta);
         int pi = bucket_idx[delta + max_rel] - pmin;
         pi = pi < 0 ? 0 : (pi >= np ? np - 1 : pi);
-        sc[i][j] += __half2float(C2P[(ty * 4 + i) * PCP + pi]) + __half2float(P2C[(tx * 4 + j) * PCP + pi]);
+        sc[i][j] += to_f32(C2P[(ty * 4 + i) * PCP + pi]) + to_f32(P2C[(tx * 4 + j) * PCP + pi]);
         if (kj >= len) sc[i][j] = -CUDART_INF_F;
         mx = fmaxf(mx, sc[i][j]);
       }
@@ -278,10 +313,16 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
 #pragma unroll 4
     for (int j = 0; j < BK; ++j) {
       const float4 p4 = *reinterpret_cast<const float4*>(Pst + j * PPS + ty * 4);
-      const uint2 v4 = *reinterpret_cast<const uint2*>(Vs + j * BD + tx * 4);
-      const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&v4.x)), vb = __half22float2(*reinterpret_cast<const __half2*>(&v4.y));
       const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-      const float vv[4] = {va.x, va.y, vb.x, vb.y};
+      float vv[4];
+      if (F32) {
+        const float4 v4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Vs) + j * BD + tx * 4);
+        vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
+      } else {
+        const uint2 v4 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(Vs) + j * BD + tx * 4);
+        const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&v4.x)), vb = __half22float2(*reinterpret_cast<const __half2*>(&v4.y));
+        vv[0] = va.x; vv[1] = va.y; vv[2] = vb.x; vv[3] = vb.y;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -300,6 +341,13 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(__half* out, con
   for (int i = tid; i < BQ * DP; i += 256) {
     const int r = i % BQ, pl = i / BQ;
     if (q0 + r >= len) continue;
+    if (F32) {
+      float4* dst = reinterpret_cast<float4*>(out32 + (row32 + q0 + r) * (size_t)HD + h * BD + pl * 8);
+      const float* o8 = Os + r * BD + pl * 8;
+      dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+      dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      continue;
+    }
     uint4 u;
     __half2* uh = reinterpret_cast<__half2*>(&u);
 #pragma unroll
@@ -346,13 +394,22 @@ void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __hal
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != BD) fail(SBV2_ERR_UNSUPPORTED, "deberta attention: head_dim must be 64");
   size_t smem = sizeof(float) * (size_t)(BD * PQ + BD * PK + BD * PPT) + sizeof(__half) * (size_t)(BK * BD + BQ * PCP + BK * PCP);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
   dim3 grid((s.max_len + BQ - 1) / BQ, heads, s.n);
-  deberta_attention_kernel<<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s);
+  deberta_attention_kernel<false><<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s);
+  POST_LAUNCH(ctx);
+}
+
+void launch_deberta_attention_f32(const LaunchCtx& ctx, float* ctx_out, const float* qkv, const float* pos_k_t, const float* pos_q_t,
+                                  int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (head_dim != BD) fail(SBV2_ERR_UNSUPPORTED, "deberta attention: head_dim must be 64");
+  size_t smem = sizeof(float) * (size_t)(BD * PQ + BD * PK + BD * PPT) + sizeof(float) * (size_t)(BK * BD + BQ * PCP + BK * PCP);
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
+  dim3 grid((s.max_len + BQ - 1) / BQ, heads, s.n);
+  deberta_attention_kernel<true><<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s);
   POST_LAUNCH(ctx);
 }
 

@@ -2,13 +2,20 @@
 // Replaces the `ort::Session::run` of crates/sbv2_core/src/bert.rs:11-16.  The graph is
 // HF DebertaV2ForMaskedLM up to hidden_states[-3] (scripts/convert/convert_deberta.py:27-35): only
 // encoder layers 0..L-3 are live; the MLM head and the last two layers are never computed.
-// GEMMs / the k=3 ConvLayer run on the tcgen05 kernel (fp16 operands, fp32 accumulate), the residual
-// stream and LayerNorms are fp32, the disentangled attention is an fp32 CUDA-core kernel.
+// Two numerics modes, chosen at model creation (SBV2_B200_BERT):
+//   exact (default)  every GEMM and the k=3 ConvLayer on tcgen05 with two-term fp16 operand splits (~fp32 products, the
+//                    text encoder's scheme, umma_conv.h make_split_conv1d_layer), fp32 row-major activations between
+//                    them, fp32 CUDA-core disentangled attention.  The features feed bert_proj -> enc_p -> ceil() in the
+//                    synthesizer, and durations must match the reference bit for bit: single-term fp16 operands perturb
+//                    the features by 1.4e-3 (relative) and flip ~1 duration in 1000 (tests/test_gpu_fullsize.py chain test).
+//   fp16             single-term fp16 operands and planar fp16 activations (3x fewer tensor FLOPs), tensor-core
+//                    disentangled attention for sequences <= 128 tokens: the throughput mode, feature error ~1e-3.
 #include <algorithm>
 #include <cmath>
 #include <sstream>
 
 #include "model.h"
+#include "onnx_bind.h"
 #include "umma_conv.h"
 
 namespace sbv2 {
@@ -32,8 +39,11 @@ struct BertModel : sbv2_model {
   float *conv_g = nullptr, *conv_b = nullptr;
   int* bucket_idx = nullptr;  // device [2*max_rel+1]
   DBuf ids, h, embp, hp, qkvp, ctxp, f1p, y32, meta, outd;
-  void* qkvp_cleared = nullptr;  // last qkv buffer that was zero-filled (its tail rows must be finite)
+  uint64_t qkvp_cleared_gen = 0;  // DBuf::gen of the qkv buffer that was zero-filled last (its tail rows must be finite)
   bool use_tc_attn = true;       // SBV2_B200_BERT_ATTN=simt (read at model creation) keeps the CUDA-core attention
+  bool exact = true;             // SBV2_B200_BERT=fp16 selects the single-term fp16 path
+  int max_cin = 0;               // widest GEMM input (exact mode: size of the split buffer)
+  DBuf x_emb, x_qkv, x_ctx, x_f1, x_y, x_split;  // exact mode: fp32 row-major activations + the split operand buffer
   PinnedBuf pin_meta, pin_io;
 };
 
@@ -67,8 +77,12 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
   }
   M->metadata = m.metadata;
   const std::string P = find_prefix(m);
+  // real exports keep only biases / embeddings / LayerNorm parameters named: every Linear weight is an anonymous
+  // transposed onnx::MatMul_N initializer, bound here through the Add that applies its bias (onnx_bind.h)
+  WeightBinder binder(m);
+  binder.require_weights_for_biases(P + "encoder.layer.");
   auto get = [&](const std::string& n) -> const OnnxTensor& {
-    const OnnxTensor* t = m.find(P + n);
+    const OnnxTensor* t = binder.find(P + n);
     if (!t) fail(SBV2_ERR_UNSUPPORTED, "DeBERTa graph lacks initializer '" + P + n + "'");
     return *t;
   };
@@ -89,11 +103,15 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
     const char* e = getenv("SBV2_B200_BERT_ATTN");
     M->use_tc_attn = !(e && std::string(e) == "simt");
   }
+  {
+    const char* e = getenv("SBV2_B200_BERT");
+    M->exact = !(e && std::string(e) == "fp16");
+  }
   M->word_emb = M->upload_f32(m.as_f32(we));
   M->emb_g = vec("embeddings.LayerNorm.weight", M->hidden);
   M->emb_b = vec("embeddings.LayerNorm.bias", M->hidden);
   int L = 0;
-  while (m.find(P + "encoder.layer." + std::to_string(L) + ".attention.self.query_proj.weight")) ++L;
+  while (binder.has(P + "encoder.layer." + std::to_string(L) + ".attention.self.query_proj.weight")) ++L;
   if (L < 3) fail(SBV2_ERR_UNSUPPORTED, "DeBERTa graph needs at least 3 encoder layers (output is hidden_states[-3])");
   M->n_layers_total = L;
   M->n_run = L - 2;
@@ -186,22 +204,27 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
       qkv.w.insert(qkv.w.end(), hc->w.begin(), hc->w.end());
       qkv.b.insert(qkv.b.end(), hc->b.begin(), hc->b.end());
     }
-    B.qkv = make_conv1d_layer(M.get(), qkv, 1, 1);
-    B.o = make_conv1d_layer(M.get(), host_linear(lp + ".attention.output.dense"), 1, 1);
+    auto layer = [&](const HostConv& hc) {
+      M->max_cin = std::max(M->max_cin, hc.d1);
+      return M->exact ? make_split_conv1d_layer(M.get(), hc, 1, 1, 2) : make_conv1d_layer(M.get(), hc, 1, 1);
+    };
+    B.qkv = layer(qkv);
+    B.o = layer(host_linear(lp + ".attention.output.dense"));
     HostConv f1 = host_linear(lp + ".intermediate.dense");
     M->inter = f1.d0;
-    B.f1 = make_conv1d_layer(M.get(), f1, 1, 1);
-    B.f2 = make_conv1d_layer(M.get(), host_linear(lp + ".output.dense"), 1, 1);
+    B.f1 = layer(f1);
+    B.f2 = layer(host_linear(lp + ".output.dense"));
     B.ln1_g = vec(lp + ".attention.output.LayerNorm.weight", H);
     B.ln1_b = vec(lp + ".attention.output.LayerNorm.bias", H);
     B.ln2_g = vec(lp + ".output.LayerNorm.weight", H);
     B.ln2_b = vec(lp + ".output.LayerNorm.bias", H);
     M->layers.push_back(B);
   }
-  if (m.find(P + "encoder.conv.conv.weight")) {
+  if (binder.has(P + "encoder.conv.conv.weight")) {
     HostConv c = host_linear("encoder.conv.conv");
     if (c.k % 2 == 0) fail(SBV2_ERR_UNSUPPORTED, "even ConvLayer kernel size");
-    M->conv = make_conv1d_layer(M.get(), c, 1, 1);
+    M->max_cin = std::max(M->max_cin, c.d1);
+    M->conv = M->exact ? make_split_conv1d_layer(M.get(), c, 1, 1, 2) : make_conv1d_layer(M.get(), c, 1, 1);
     M->conv_g = vec("encoder.conv.LayerNorm.weight", H);
     M->conv_b = vec("encoder.conv.LayerNorm.bias", H);
     M->has_conv = true;
@@ -215,11 +238,14 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
     }
     M->bucket_idx = static_cast<int*>(M->upload_bytes(tab.data(), tab.size() * 4));
   }
-  for (DBuf* b : {&M->ids, &M->h, &M->embp, &M->hp, &M->qkvp, &M->ctxp, &M->f1p, &M->y32, &M->meta, &M->outd}) b->stream = M->stream;
+  for (DBuf* b : {&M->ids, &M->h, &M->embp, &M->hp, &M->qkvp, &M->ctxp, &M->f1p, &M->y32, &M->meta, &M->outd, &M->x_emb, &M->x_qkv, &M->x_ctx,
+                  &M->x_f1, &M->x_y, &M->x_split})
+    b->stream = M->stream;
   std::ostringstream js;
   js << "{\"kind\":\"deberta-v2\",\"hidden_size\":" << H << ",\"num_attention_heads\":" << M->heads << ",\"intermediate_size\":" << M->inter
      << ",\"vocab_size\":" << M->vocab << ",\"num_hidden_layers\":" << L << ",\"live_layers\":" << M->n_run
-     << ",\"position_buckets\":" << M->span << ",\"conv_layer\":" << (M->has_conv ? "true" : "false") << "}";
+     << ",\"position_buckets\":" << M->span << ",\"conv_layer\":" << (M->has_conv ? "true" : "false") << ",\"structural_binding\":" << (binder.any_structural() ? "true" : "false") << ",\"numerics\":\""
+     << (M->exact ? "exact" : "fp16") << "\"}";
   M->describe_json = js.str();
   CUDA_CHECK(cudaStreamSynchronize(M->stream));
   return M.release();
@@ -278,6 +304,55 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
   ps.plane_stride = G.rows_tot * 8;
   const size_t R = size_t(G.rows_tot);
   M.h.ensure(size_t(n) * H * 4);
+  if (M.exact) {
+    // ---- exact mode: fp32 row-major activations, two-term fp16 operand splits for every GEMM -------------------------
+    M.x_emb.ensure(size_t(n) * H * 4);
+    M.x_qkv.ensure(size_t(n) * 3 * H * 4);
+    M.x_ctx.ensure(size_t(n) * H * 4);
+    M.x_f1.ensure(size_t(n) * M.inter * 4);
+    M.x_y.ensure(size_t(n) * H * 4);
+    M.x_split.ensure(R * 3 * size_t(M.max_cin) * 2);
+    M.outd.ensure(out_elems * 4);
+    float* h = M.h.as<float>();
+    float* emb = M.x_emb.as<float>();
+    float* qkv = M.x_qkv.as<float>();
+    float* ctxb = M.x_ctx.as<float>();
+    float* f1 = M.x_f1.as<float>();
+    float* y = M.x_y.as<float>();
+    __half* split = M.x_split.as<__half>();
+    launch_zero_gaps(ctx, split, 3 * M.max_cin, G, batch);  // the splits only ever write sequence rows (k = 3 ConvLayer halo)
+    auto gemm = [&](const ConvLayer& L, const float* in, int cin, float* out, int cout, int act) {
+      launch_split_planar(ctx, split, in, cin, cin, bg.d_ystart, G, batch, 2, L.in_scale);
+      ConvCall c;
+      c.in = split;
+      c.rm_out = out;
+      c.rm_ld = cout;
+      c.rm_start = bg.d_ystart;
+      c.act_out = act;
+      launch_umma(ctx, L, G, G, c, batch);
+    };
+    launch_embed_rows(ctx, h, M.word_emb, M.ids.as<int>(), H, M.vocab, n);
+    launch_layernorm(ctx, emb, h, nullptr, nullptr, M.emb_g, M.emb_b, M.eps, ACT_NONE, H, int(n));
+    for (int l = 0; l < M.n_run; ++l) {
+      const BertLayer& B = M.layers[l];
+      const float* in = l == 0 ? emb : h;
+      gemm(B.qkv, in, H, qkv, 3 * H, ACT_NONE);
+      launch_deberta_attention_f32(ctx, ctxb, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+      gemm(B.o, ctxb, H, y, H, ACT_NONE);
+      launch_layernorm(ctx, h, in, y, nullptr, B.ln1_g, B.ln1_b, M.eps, ACT_NONE, H, int(n));
+      gemm(B.f1, h, H, f1, M.inter, ACT_GELU);
+      gemm(B.f2, f1, M.inter, y, H, ACT_NONE);
+      launch_layernorm(ctx, h, h, y, nullptr, B.ln2_g, B.ln2_b, M.eps, ACT_NONE, H, int(n));
+      if (l == 0 && M.has_conv) {
+        // ConvLayer: LN(layer0_out + gelu(conv(embeddings)))
+        gemm(M.conv, emb, H, y, H, ACT_GELU);
+        launch_layernorm(ctx, h, h, y, nullptr, M.conv_g, M.conv_b, M.eps, ACT_NONE, H, int(n));
+      }
+    }
+    launch_scatter_rows(ctx, M.outd.as<float>(), h, H, int(S), ps);
+    M.debug["bert_h"] = DebugView{h, n, H, 4};
+    return M.outd.as<float>();
+  }
   M.embp.ensure(R * H * 2);
   M.hp.ensure(R * H * 2);
   M.qkvp.ensure(R * 3 * H * 2);
@@ -307,10 +382,10 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
   };
   // sequences of at most 128 tokens: disentangled attention on the tensor cores (SBV2_B200_BERT_ATTN=simt: CUDA cores)
   const bool tc_attn = M.use_tc_attn && M.hidden / M.heads == 64 && deberta_attention_tc_supported(64, M.span, max_len);
-  if (tc_attn && M.qkvp.p != M.qkvp_cleared) {
+  if (tc_attn && M.qkvp.gen != M.qkvp_cleared_gen) {
     // rows past an utterance's end are read by the tensor-core attention: they must hold finite values
     CUDA_CHECK(cudaMemsetAsync(M.qkvp.p, 0, M.qkvp.cap, M.stream));
-    M.qkvp_cleared = M.qkvp.p;
+    M.qkvp_cleared_gen = M.qkvp.gen;
   }
   for (int l = 0; l < M.n_run; ++l) {
     const BertLayer& B = M.layers[l];

@@ -2,8 +2,11 @@
 // exception or abort crosses the ABI.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "container.h"
 #include "model.h"
+#include "onnx_bind.h"
 
 namespace sbv2 {
 const char* last_error_cstr();
@@ -20,6 +23,12 @@ void sbv2_free(void* p) { free_out(p); }
 void* sbv2_alloc(size_t bytes) {
   void* p = nullptr;
   guarded([&] { p = alloc_out(bytes, false); });
+  return p;
+}
+
+void* sbv2_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  guarded([&] { p = alloc_out(bytes, true); });
   return p;
 }
 
@@ -42,6 +51,20 @@ int sbv2_device_count(void) {
   }
   if (!ok) set_last_error("no sm_100 (Blackwell) device visible; this backend has no CPU fallback");
   return ok;
+}
+
+// CPU-only diagnostic: how the canonical (PyTorch) weight names of an exported graph bind to its initializers.
+int sbv2_onnx_bind_report(const void* onnx_bytes, size_t n_bytes, int is_bert, char** json) {
+  return guarded([&] {
+    SBV2_REQUIRE(onnx_bytes && n_bytes > 0 && json, "null argument");
+    (void)is_bert;
+    OnnxModel m = parse_onnx(static_cast<const uint8_t*>(onnx_bytes), n_bytes);
+    WeightBinder binder(m);
+    const std::string s = binder.report_json();
+    char* p = static_cast<char*>(alloc_out(s.size() + 1, false));
+    memcpy(p, s.c_str(), s.size() + 1);
+    *json = p;
+  });
 }
 
 int sbv2_model_create(const void* onnx_bytes, size_t n_bytes, int is_bert, int device_ordinal, sbv2_model** out_model) {
@@ -225,6 +248,81 @@ int sbv2_synthesize_from_tokens(sbv2_model* synth, sbv2_model* bert, const int64
   });
 }
 
+int sbv2_synthesize_from_tokens_batch(sbv2_model* synth, sbv2_model* bert, const sbv2_token_utterance* utts, int batch,
+                                      const int64_t* pause_after, float** out_samples, int64_t* out_total, int64_t* out_n_samples) {
+  return guarded([&] {
+    SBV2_REQUIRE(synth && bert && utts && out_samples && out_total, "null argument");
+    SBV2_REQUIRE(!synth->is_bert, "synthesize called on a BERT model");
+    SBV2_REQUIRE(bert->is_bert, "bert_predict called on a synthesizer model");
+    SBV2_REQUIRE(synth->device == bert->device, "the BERT and synthesizer models must live on the same device");
+    SBV2_REQUIRE(batch > 0, "empty batch");
+    *out_samples = nullptr;
+    *out_total = 0;
+    // one right-padded DeBERTa batch over all sentences (bert.rs:6-24 per sentence in the reference)
+    int64_t s_max = 0, nx = 0;
+    for (int i = 0; i < batch; ++i) {
+      SBV2_REQUIRE(utts[i].input_ids && utts[i].attention_mask && utts[i].word2ph && utts[i].t_tok > 0 && utts[i].t_x > 0, "empty input");
+      s_max = std::max(s_max, utts[i].t_tok);
+      nx += utts[i].t_x;
+    }
+    std::vector<int64_t> ids(size_t(batch) * s_max, 0), mask(size_t(batch) * s_max, 0), ph2tok;
+    ph2tok.reserve(size_t(nx));
+    for (int i = 0; i < batch; ++i) {
+      const sbv2_token_utterance& u = utts[i];
+      int64_t n_ph = 0;
+      for (int64_t t = 0; t < u.t_tok; ++t) {
+        SBV2_REQUIRE(u.attention_mask[t] != 0, "attention_mask of a sentence must be all ones (padding is added by the library)");
+        ids[size_t(i) * s_max + t] = u.input_ids[t];
+        mask[size_t(i) * s_max + t] = 1;
+        SBV2_REQUIRE(u.word2ph[t] >= 0, "negative word2ph entry");
+        // tts_util.rs:129-154: token t is repeated word2ph[t] times
+        for (int32_t j = 0; j < u.word2ph[t]; ++j) ph2tok.push_back(int64_t(i) * s_max + t);
+        n_ph += u.word2ph[t];
+      }
+      SBV2_REQUIRE(n_ph == u.t_x, "sum(word2ph) must equal the number of phonemes");
+    }
+    const float* rows = bert_forward_device(bert, ids.data(), mask.data(), batch, s_max);
+    SBV2_REQUIRE(rows != nullptr, "attention_mask selects no token");
+    cudaEvent_t ready = nullptr;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    struct EventGuard {
+      cudaEvent_t e;
+      ~EventGuard() { cudaEventDestroy(e); }
+    } guard{ready};
+    CUDA_CHECK(cudaEventRecord(ready, bert->stream));
+    DeviceBert dev;
+    dev.rows = rows;
+    dev.n_rows = int64_t(batch) * s_max;
+    dev.hidden = bert_hidden(bert);
+    dev.ph2tok = ph2tok.data();
+    dev.ready = ready;
+    std::vector<sbv2_utterance> su;
+    su.resize(size_t(batch));
+    for (int i = 0; i < batch; ++i) {
+      const sbv2_token_utterance& u = utts[i];
+      sbv2_utterance& o = su[size_t(i)];
+      o = sbv2_utterance{};
+      o.x_tst = u.x_tst;
+      o.tones = u.tones;
+      o.lang_ids = u.lang_ids;
+      o.t_x = u.t_x;
+      o.sid = u.sid;
+      o.style_vec = u.style_vec;
+      o.sdp_ratio = u.sdp_ratio;
+      o.length_scale = u.length_scale;
+      o.noise_scale = u.noise_scale;
+      o.noise_scale_w = u.noise_scale_w;
+    }
+    std::unique_ptr<sbv2_device_batch, void (*)(sbv2_device_batch*)> b(synth_upload(synth, su.data(), batch, &dev), synth_batch_free);
+    if (pause_after) synth_set_pauses(b.get(), pause_after);
+    synth_run(synth, b.get());
+    std::vector<int64_t> n(size_t(batch), 0);
+    synth_download(synth, b.get(), out_samples, n.data(), nullptr, nullptr);  // synchronises: the BERT rows are free again
+    *out_total = synth_wave_total(b.get());
+    if (out_n_samples) memcpy(out_n_samples, n.data(), size_t(batch) * 8);
+  });
+}
+
 int sbv2_synthesize(sbv2_model* synth, const float* bert, const int64_t* x_tst, const int64_t* tones, const int64_t* lang_ids,
                     int64_t t_x, int64_t sid, const float* style_vec, float sdp_ratio, float length_scale, float noise_scale,
                     float noise_scale_w, float** out_samples, int64_t* n_samples) {
@@ -236,6 +334,8 @@ int sbv2_batch_upload(sbv2_model* synth, const sbv2_utterance* utts, int batch, 
   return guarded([&] {
     SBV2_REQUIRE(synth && out, "null argument");
     *out = synth_upload(synth, utts, batch);
+    // inputs are borrowed for the duration of the call: copies that read the caller's buffers in place must be done
+    if (synth_borrows_host(*out)) CUDA_CHECK(cudaStreamSynchronize(synth->stream));
   });
 }
 

@@ -53,6 +53,8 @@ int guarded(F&& f) noexcept {
 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
+
+#include <mutex>
 #define CUDA_CHECK(expr)                                                                         \
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \
@@ -60,4 +62,26 @@ int guarded(F&& f) noexcept {
       ::sbv2::fail(SBV2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +  \
                                       __FILE__ + ":" + std::to_string(__LINE__));                \
   } while (0)
+#endif
+
+#ifdef __CUDACC__
+namespace sbv2 {
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize ...) belong to the device/context, not to the
+// process: a call site owns one PerDeviceOnce and runs its opt-in once per device the library is used on.  The mutex
+// also covers two host threads that drive different models on the same device for the first time.
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0;  // bit d: the opt-in ran on device ordinal d (ordinals >= 64 re-run it every time)
+  template <class F>
+  void run(F&& f) {
+    int d = 0;
+    CUDA_CHECK(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned long long bit = d < 64 ? (1ull << d) : 0ull;
+    if (bit && (done & bit)) return;
+    f();
+    done |= bit;
+  }
+};
+}  // namespace sbv2
 #endif

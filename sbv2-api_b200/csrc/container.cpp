@@ -76,7 +76,10 @@ std::vector<uint8_t> zstd_decompress(const uint8_t* p, size_t n) {
   std::vector<uint8_t> chunk(1 << 20);
   ZBuf in{const_cast<uint8_t*>(p), n, 0};
   size_t last = 1;
-  while (in.pos < in.size) {
+  // Keep calling while there is input left OR the last call filled the whole output chunk (the decoder may still hold
+  // data to flush even though every input byte has been consumed); stop when a frame ends exactly at the end of input.
+  bool out_was_full = false;
+  while (in.pos < in.size || out_was_full) {
     ZBuf o{chunk.data(), chunk.size(), 0};
     size_t r = z.decompressStream(ds, &o, &in);
     if (z.isError(r)) {
@@ -85,8 +88,9 @@ std::vector<uint8_t> zstd_decompress(const uint8_t* p, size_t n) {
     }
     out.insert(out.end(), chunk.begin(), chunk.begin() + o.pos);
     last = r;
+    out_was_full = o.pos == o.size;
     if (r == 0 && in.pos >= in.size) break;
-    if (o.pos == 0 && in.pos >= in.size) break;
+    if (o.pos == 0 && in.pos >= in.size) break;  // no progress and nothing left to feed: truncated
   }
   z.freeDStream(ds);
   if (last != 0) fail(SBV2_ERR_PARSE, ".sbv2: truncated zstd frame");
@@ -137,12 +141,13 @@ std::vector<TarEntry> tar_entries(const uint8_t* p, size_t n) {
     }
     char type = char(h[156]);
     off += 512;
-    if (off + size > n) fail(SBV2_ERR_PARSE, ".sbv2: tar entry '" + name + "' exceeds archive");
+    if (size > n - off) fail(SBV2_ERR_PARSE, ".sbv2: tar entry '" + name + "' exceeds archive");  // off <= n here; no wrap-around
     if (type == '0' || type == 0) {
       if (name.rfind("./", 0) == 0) name = name.substr(2);
       out.push_back({name, p + off, size_t(size)});
     }
-    off += (size + 511) / 512 * 512;
+    const uint64_t padded = (size + 511) / 512 * 512;  // size <= n - off, so this cannot wrap
+    off = padded > n - off ? n : off + size_t(padded);
   }
   return out;
 }
@@ -198,12 +203,33 @@ struct Json {
   }
   double number() {
     ws();
-    char* e = nullptr;
-    errno = 0;
-    double v = strtod(p, &e);
-    if (e == p) fail(SBV2_ERR_PARSE, "style json: expected number");
-    p = e;
-    return v;
+    // JSON number grammar only ([-]digits[.digits][(e|E)[+-]digits]); the token is copied into a bounded NUL-terminated
+    // buffer because the input is caller memory of `end - p` bytes, not a C string (strtod would also take nan/inf/hex).
+    const char* q = p;
+    if (q < end && *q == '-') ++q;
+    const char* d0 = q;
+    while (q < end && *q >= '0' && *q <= '9') ++q;
+    if (q == d0) fail(SBV2_ERR_PARSE, "style json: expected number");
+    if (q < end && *q == '.') {
+      ++q;
+      const char* f0 = q;
+      while (q < end && *q >= '0' && *q <= '9') ++q;
+      if (q == f0) fail(SBV2_ERR_PARSE, "style json: malformed number");
+    }
+    if (q < end && (*q == 'e' || *q == 'E')) {
+      ++q;
+      if (q < end && (*q == '+' || *q == '-')) ++q;
+      const char* e0 = q;
+      while (q < end && *q >= '0' && *q <= '9') ++q;
+      if (q == e0) fail(SBV2_ERR_PARSE, "style json: malformed number");
+    }
+    char buf[64];
+    const size_t len = size_t(q - p);
+    if (len >= sizeof(buf)) fail(SBV2_ERR_PARSE, "style json: number token too long");
+    memcpy(buf, p, len);
+    buf[len] = 0;
+    p = q;
+    return strtod(buf, nullptr);
   }
   void skip_value() {
     ws();
@@ -274,7 +300,9 @@ StyleVectors load_style_json(const uint8_t* bytes, size_t n) {
   }
   if (!has_shape || !has_data) fail(SBV2_ERR_PARSE, "style json: missing field 'shape' or 'data'");
   if (shape.size() != 2) fail(SBV2_ERR_PARSE, "style json: shape must have 2 entries");
-  if (shape[0] < 0 || shape[1] < 0 || size_t(shape[0] * shape[1]) != data.size())
+  const bool shape_ok = shape[0] >= 0 && shape[1] >= 0 &&
+                        (shape[1] == 0 ? data.empty() : (data.size() % size_t(shape[1]) == 0 && data.size() / size_t(shape[1]) == size_t(shape[0])));
+  if (!shape_ok)
     fail(SBV2_ERR_INVALID_ARGUMENT, "NDArray error: style data does not match shape");  // ShapeError in the reference
   s.rows = shape[0];
   s.cols = shape[1];
@@ -341,16 +369,23 @@ StyleVectors load_style_npy_base64(const char* b64, size_t n) {
   auto find_after = [&](const std::string& key) -> size_t {
     size_t k = hdr.find(key);
     if (k == std::string::npos) fail(SBV2_ERR_PARSE, "aivmx: .npy header lacks " + key);
-    return hdr.find(':', k) + 1;
+    size_t c = hdr.find(':', k);
+    if (c == std::string::npos) fail(SBV2_ERR_PARSE, "aivmx: malformed .npy header near " + key);
+    return c + 1;
   };
+  const size_t npos = std::string::npos;
   size_t d = find_after("'descr'");
-  size_t q1 = hdr.find('\'', d), q2 = hdr.find('\'', q1 + 1);
+  size_t q1 = hdr.find('\'', d), q2 = q1 == npos ? npos : hdr.find('\'', q1 + 1);
+  if (q1 == npos || q2 == npos) fail(SBV2_ERR_PARSE, "aivmx: malformed .npy header (descr)");
   std::string descr = hdr.substr(q1 + 1, q2 - q1 - 1);
   if (descr != "<f4" && descr != "|f4" && descr != "=f4") fail(SBV2_ERR_UNSUPPORTED, "aivmx: style vectors must be float32, got " + descr);
   size_t f = find_after("'fortran_order'");
-  bool fortran = hdr.compare(hdr.find_first_not_of(' ', f), 4, "True") == 0;
+  const size_t fv = hdr.find_first_not_of(' ', f);
+  if (fv == npos) fail(SBV2_ERR_PARSE, "aivmx: malformed .npy header (fortran_order)");
+  bool fortran = hdr.compare(fv, 4, "True") == 0;
   size_t s = find_after("'shape'");
-  size_t p1 = hdr.find('(', s), p2 = hdr.find(')', p1);
+  size_t p1 = hdr.find('(', s), p2 = p1 == npos ? npos : hdr.find(')', p1);
+  if (p1 == npos || p2 == npos) fail(SBV2_ERR_PARSE, "aivmx: malformed .npy header (shape)");
   std::vector<int64_t> shape;
   {
     std::string inner = hdr.substr(p1 + 1, p2 - p1 - 1);
@@ -368,8 +403,11 @@ StyleVectors load_style_npy_base64(const char* b64, size_t n) {
   StyleVectors out;
   out.rows = shape[0];
   out.cols = shape[1];
-  size_t count = size_t(out.rows * out.cols);
-  if (hoff + hlen + count * 4 > npy.size()) fail(SBV2_ERR_PARSE, "aivmx: .npy payload shorter than shape");
+  if (out.rows < 0 || out.cols < 0) fail(SBV2_ERR_PARSE, "aivmx: negative .npy dimension");
+  // checked arithmetic: the payload bound decides, so neither rows*cols nor count*4 may wrap
+  const size_t avail = (npy.size() - hoff - hlen) / 4;
+  if (out.cols != 0 && size_t(out.rows) > avail / size_t(out.cols)) fail(SBV2_ERR_PARSE, "aivmx: .npy payload shorter than shape");
+  size_t count = size_t(out.rows) * size_t(out.cols);
   const uint8_t* payload = npy.data() + hoff + hlen;
   out.data.resize(count);
   if (!fortran) {

@@ -445,11 +445,8 @@ void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __hal
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != D || window != 4) fail(SBV2_ERR_UNSUPPORTED, "tensor-core attention: head_dim must be 96 and window 4");
   const size_t smem = (1 + 2 * NKV) * TILE_BYTES + P_BYTES + PREL_BYTES + 2 * REL_BYTES + 256 + 2 * QT * 2 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(flow_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(flow_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
   dim3 grid((s.max_len + QT - 1) / QT, heads, s.n);
   launch_pdl(ctx.pdl, flow_attention_tc_kernel, grid, dim3(32 * (NSM_WARPS + 1)), smem, ctx.stream, ctx_out, qkv, rel_k_p, rel_v_p, heads, window, s,
              trace);

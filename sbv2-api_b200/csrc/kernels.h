@@ -184,6 +184,9 @@ void launch_embed_rows(const LaunchCtx& ctx, float* h, const float* table, const
 // bucket_idx: int [2*max_rel+1] = clamp(bucket(delta) + span, 0, 2*span-1) for delta = -max_rel..max_rel.
 void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k_t, const float* pos_q_t,
                               int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
+// "exact" mode: the same kernel on fp32 row-major q|k|v [rows, 3*heads*64] -> fp32 row-major context [rows, heads*64]
+void launch_deberta_attention_f32(const LaunchCtx& ctx, float* ctx_out, const float* qkv, const float* pos_k_t, const float* pos_q_t,
+                                  int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
 // tensor-core version for sequences of at most 128 tokens (bert_attention_tc.cu); pos_*_p: fp16 [heads][D/8][n_pos][8]
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len);
 void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,

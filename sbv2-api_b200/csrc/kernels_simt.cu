@@ -792,11 +792,8 @@ void launch_rel_attention(const LaunchCtx& ctx, float* out, const float* qkv, co
   constexpr int D = 96;
   int R = 2 * window + 1;
   size_t smem = sizeof(float) * (size_t)(D * (AQ + 1) + D * (AK + 1) + AK * D + AQ * (AK + 1) + 2 * R * D + AQ * R);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); });
   dim3 grid((seg.max_len + AQ - 1) / AQ, heads, seg.n);
   rel_attention_kernel<D><<<grid, 256, smem, ctx.stream>>>(out, qkv, rel_k, rel_v, heads, window, seg);
   POST_LAUNCH(ctx);

@@ -1,6 +1,8 @@
 // sbv2_model base: device binding, weight uploads, out-pointer registry.
 #include "model.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -121,7 +123,10 @@ void* sbv2_model::upload_bytes(const void* host, size_t bytes) {
   return d;
 }
 
+// Regions ("text", "flow", "decoder", "bert") are always NVTX ranges (header-only NVTX3: a no-op unless a tool is
+// attached) and, with sbv2_model_enable_timing, CUDA-event pairs on the model's stream.
 void sbv2_model::region_begin(const std::string& name) {
+  nvtxRangePushA(name.c_str());
   if (!timing) return;
   auto it = regions.find(name);
   if (it == regions.end()) {
@@ -134,6 +139,7 @@ void sbv2_model::region_begin(const std::string& name) {
 }
 
 void sbv2_model::region_end(const std::string& name) {
+  nvtxRangePop();
   if (!timing) return;
   auto it = regions.find(name);
   if (it == regions.end()) return;

@@ -12,6 +12,7 @@ namespace sbv2 {
 struct DBuf {
   void* p = nullptr;
   size_t cap = 0;
+  uint64_t gen = 0;  // bumped on every (re)allocation: "was this buffer cleared?" must not rely on pointer identity
   cudaStream_t stream = nullptr;
   DBuf() = default;
   DBuf(const DBuf&) = delete;
@@ -93,7 +94,7 @@ struct DeviceBert {
   const float* rows = nullptr;     // [n_rows, hidden] fp32 on the device
   int64_t n_rows = 0;
   int hidden = 0;
-  const int64_t* ph2tok = nullptr;  // host, [t_x]: BERT row of each phoneme
+  const int64_t* ph2tok = nullptr;  // host, [sum t_x]: BERT row (index into `rows`) of each phoneme of the batch
   cudaEvent_t ready = nullptr;      // recorded on the producer's stream after the rows were written
 };
 sbv2_device_batch* synth_upload(sbv2_model* m, const sbv2_utterance* utts, int batch, const DeviceBert* dev_bert = nullptr);
@@ -101,6 +102,9 @@ void synth_run(sbv2_model* m, sbv2_device_batch* b);
 void synth_download(sbv2_model* m, sbv2_device_batch* b, float** out_samples, int64_t* out_n, int32_t** out_dur,
                     int32_t** out_f2p);
 int64_t synth_total_samples(sbv2_model* m, const sbv2_device_batch* b);
+int64_t synth_wave_total(const sbv2_device_batch* b);                        // samples of the output buffer incl. pauses
+void synth_set_pauses(sbv2_device_batch* b, const int64_t* pause_after);     // before synth_run: zeros after each utterance
+bool synth_borrows_host(const sbv2_device_batch* b);                         // uploads read caller memory in place
 void synth_batch_ty(const sbv2_device_batch* b, int64_t* ty);
 void synth_batch_free(sbv2_device_batch* b);
 void synth_set_seed(sbv2_model* m, uint64_t seed);

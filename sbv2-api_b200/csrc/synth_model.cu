@@ -6,6 +6,7 @@
 #include <sstream>
 
 #include "model.h"
+#include "onnx_bind.h"
 #include "umma_conv.h"
 
 namespace sbv2 {
@@ -124,7 +125,7 @@ struct SynthModel : sbv2_model {
   std::vector<FlowTC> flow_tc;  // tensor-core transformer flow (fp16 operands, fp32 residual stream)
   bool use_tc_flow = true;
   bool use_tc_attn = true;
-  void* fl_qkvp_ptr = nullptr;  // last qkv buffer that was cleared (tails must be finite for the TC attention)
+  uint64_t fl_qkvp_gen = 0;  // DBuf::gen of the qkv buffer that was cleared last (tails must be finite for the TC attention)
   std::vector<std::vector<HostConv>> flow_host;  // consumed at create: per coupling [pre, post, (qkv, o, f1, f2) x L]
   DBuf fl_x0p, fl_hp, fl_qkvp, fl_ctxp, fl_f1p, fl_y32, fl_m32, fl_meta;
   PinnedBuf fl_pin;
@@ -142,7 +143,7 @@ struct SynthModel : sbv2_model {
   DBuf ws[32];
   std::vector<BatchBuffers*> batch_pool;  // idle batch buffer sets
   DecoderHostWeights dec_host;  // original-layout decoder weights, consumed by umma_decoder_create
-  PinnedBuf pin_in, pin_ylen;
+  PinnedBuf pin_in, pin_ylen, pin_ymeta;
   ~SynthModel() override;
 };
 
@@ -170,7 +171,13 @@ struct sbv2_device_batch {
          o_bert_off = 0, o_nsdp_off = 0, o_style = 0, o_bert = 0, o_nsdp = 0, o_zp_off = 0, o_zp_ld = 0;
   bool ran = false;
   bool decode_only = false;
-  // BERT rows already on this device (batch 1): gathered by ph2tok (int64 [t_x] at o_bert) instead of uploaded
+  bool borrowed_host = false;  // some H2D copies read the caller's (pinned) buffers directly: synchronise before returning to it
+  // silence (samples) laid out after each utterance in the waveform buffer (easy_synthesize's 22 050-sample pauses,
+  // tts.rs:318-320, written on the device); empty = none
+  std::vector<int64_t> pause_after;
+  std::vector<long long> wstart;  // sample offset of each utterance in `wave` (filled by synth_run)
+  int64_t wave_total = 0;         // samples in `wave` including pauses
+  // BERT rows already on this device: gathered by ph2tok (int64 [sum t_x] at o_bert) instead of uploaded
   const float* dev_bert_rows = nullptr;
   int64_t dev_bert_n = 0;
   cudaEvent_t dev_bert_ready = nullptr;
@@ -204,12 +211,9 @@ namespace {
 struct Loader {
   const OnnxModel& m;
   SynthModel& M;
-  std::map<std::string, std::string> alias;  // canonical name -> initializer name (structural binding)
+  WeightBinder& binder;  // canonical (PyTorch) name -> initializer, incl. structurally bound anonymous weights (onnx_bind.h)
 
-  const OnnxTensor* find(const std::string& n) const {
-    auto it = alias.find(n);
-    return m.find(it == alias.end() ? n : it->second);
-  }
+  const OnnxTensor* find(const std::string& n) const { return binder.find(n); }
   bool has(const std::string& n) const { return find(n) != nullptr; }
   const OnnxTensor& get(const std::string& n) const {
     const OnnxTensor* t = find(n);
@@ -339,7 +343,7 @@ int attr_first(const OnnxNode& n, const char* name, int dflt) {
 // Bind them by walking Conv / ConvTranspose nodes in graph (= execution) order after conv_pre.
 void bind_decoder_structurally(Loader& L) {
   const OnnxModel& m = L.m;
-  if (m.find("dec.ups.0.weight")) return;
+  if (L.has("dec.ups.0.weight")) return;  // named, or already bound through its bias (onnx_bind.h)
   size_t start = m.nodes.size();
   for (size_t i = 0; i < m.nodes.size(); ++i) {
     const auto& n = m.nodes[i];
@@ -359,8 +363,8 @@ void bind_decoder_structurally(Loader& L) {
     if (n.op_type == "ConvTranspose") {
       if (up >= 0 && n_res_per == 0) n_res_per = (rb + 1);
       ++up;
-      L.alias["dec.ups." + std::to_string(up) + ".weight"] = n.inputs[1];
-      if (n.inputs.size() > 2) L.alias["dec.ups." + std::to_string(up) + ".bias"] = n.inputs[2];
+      L.binder.alias_to("dec.ups." + std::to_string(up) + ".weight", n.inputs[1]);
+      if (n.inputs.size() > 2) L.binder.alias_to("dec.ups." + std::to_string(up) + ".bias", n.inputs[2]);
       pos = 0;
     } else if (n.op_type == "Conv" && up >= 0) {
       if (n.inputs[1] == "dec.conv_post.weight") break;
@@ -371,8 +375,8 @@ void bind_decoder_structurally(Loader& L) {
       if (idx_in_rb == 0) ++rb;
       std::string which = (idx_in_rb % 2 == 0) ? "convs1" : "convs2";
       std::string nm = "dec.resblocks." + std::to_string(rb) + "." + which + "." + std::to_string(idx_in_rb / 2);
-      L.alias[nm + ".weight"] = n.inputs[1];
-      if (n.inputs.size() > 2) L.alias[nm + ".bias"] = n.inputs[2];
+      L.binder.alias_to(nm + ".weight", n.inputs[1]);
+      if (n.inputs.size() > 2) L.binder.alias_to(nm + ".bias", n.inputs[2]);
       ++pos;
     }
   }
@@ -380,11 +384,14 @@ void bind_decoder_structurally(Loader& L) {
 }
 
 void load_weights(SynthModel& M, const OnnxModel& m) {
-  Loader L{m, M, {}};
+  WeightBinder binder(m);
+  Loader L{m, M, binder};
   HParams& hp = M.hp;
   if (!L.has("enc_p.emb.weight") || !L.has("dec.conv_pre.weight"))
     fail(SBV2_ERR_UNSUPPORTED, "not a Style-Bert-VITS2 synthesizer graph (enc_p.emb.weight / dec.conv_pre.weight missing)");
   bind_decoder_structurally(L);
+  // a bias whose weight could not be bound would make has(".weight") probes (spk_emb_linear ...) skip a layer silently
+  binder.require_weights_for_biases("");
 
   auto dims = [&](const std::string& n) { return L.get(n).dims; };
   hp.n_vocab = int(dims("enc_p.emb.weight")[0]);
@@ -476,8 +483,8 @@ void load_weights(SynthModel& M, const OnnxModel& m) {
   for (const auto& n : m.nodes)
     if ((n.op_type == "Conv" || n.op_type == "ConvTranspose") && n.inputs.size() >= 2) node_of_weight[n.inputs[1]] = &n;
   auto node_for = [&](const std::string& canonical) -> const OnnxNode* {
-    auto a = L.alias.find(canonical);
-    auto it = node_of_weight.find(a == L.alias.end() ? canonical : a->second);
+    const OnnxTensor* t = L.find(canonical);
+    auto it = node_of_weight.find(t ? t->name : canonical);
     return it == node_of_weight.end() ? nullptr : it->second;
   };
   static const int default_rates_k16[] = {8, 8, 2, 2, 2};
@@ -651,7 +658,7 @@ void load_weights(SynthModel& M, const OnnxModel& m) {
   for (size_t i = 0; i < hp.up_kernels.size(); ++i) js << (i ? "," : "") << hp.up_kernels[i];
   js << "],\"resblock_kernel_sizes\":[";
   for (size_t i = 0; i < hp.res_kernels.size(); ++i) js << (i ? "," : "") << hp.res_kernels[i];
-  js << "],\"hop\":" << hp.hop << ",\"structural_binding\":" << (L.alias.empty() ? "false" : "true") << "}";
+  js << "],\"hop\":" << hp.hop << ",\"structural_binding\":" << (binder.any_structural() ? "true" : "false") << "}";
   M.describe_json = js.str();
 }
 
@@ -757,6 +764,7 @@ void DBuf::ensure(size_t bytes) {
   size_t want = align_up(bytes + bytes / 4, 1 << 20);
   CUDA_CHECK(cudaMalloc(&p, want));
   cap = want;
+  ++gen;
 }
 
 void PinnedBuf::ensure(size_t bytes) {
@@ -911,7 +919,6 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
   b->has_noise_zp = n_nzp > 0;
   b->Nx = nx;
   if (dev_bert) {
-    SBV2_REQUIRE(batch == 1, "device-resident BERT features are supported for one utterance per call");
     SBV2_REQUIRE(dev_bert->rows && dev_bert->ph2tok && dev_bert->hidden == hp.bert_dim, "BERT hidden size does not match the synthesizer");
     for (int64_t t = 0; t < nx; ++t)
       SBV2_REQUIRE(dev_bert->ph2tok[t] >= 0 && dev_bert->ph2tok[t] < dev_bert->n_rows, "word2ph maps a phoneme past the last token");
@@ -995,9 +1002,19 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
   } else
   for (int i = 0; i < batch; ++i) {
     const size_t off_f = size_t(b->xstart[i]) * hp.bert_dim, cnt = size_t(b->xlen[i]) * hp.bert_dim * 4;
-    memcpy(hbert + off_f, utts[i].bert, cnt);
-    CUDA_CHECK(cudaMemcpyAsync(b->in.as<uint8_t>() + b->o_bert + off_f * 4, reinterpret_cast<uint8_t*>(hbert) + off_f * 4, cnt,
-                               cudaMemcpyHostToDevice, M->stream));
+    // page-locked caller memory (sbv2_alloc_pinned / cudaHostAlloc / cudaHostRegister) is read by the DMA engine in
+    // place; pageable memory goes through the staging block (one memcpy per utterance, pipelined with the copies)
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, utts[i].bert) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    const void* src = utts[i].bert;
+    if (pinned) {
+      b->borrowed_host = true;
+    } else {
+      memcpy(hbert + off_f, utts[i].bert, cnt);
+      src = hbert + off_f;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(b->in.as<uint8_t>() + b->o_bert + off_f * 4, src, cnt, cudaMemcpyHostToDevice, M->stream));
   }
   if (b->has_noise_zp) {
     size_t tot = 0;
@@ -1010,6 +1027,7 @@ sbv2_device_batch* synth_upload(sbv2_model* mm, const sbv2_utterance* utts, int 
       CUDA_CHECK(cudaMemcpyAsync(b->zp.as<float>() + o, utts[i].noise_zp, n * 4, cudaMemcpyHostToDevice, M->stream));
       o += n;
     }
+    b->borrowed_host = true;  // read straight from the caller's buffers (staged by the driver if pageable)
   }
   // no sync here: the copies overlap with the caller's next steps; the staging buffer is protected by
   // the synchronisation at the top of the next upload
@@ -1216,7 +1234,8 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   BatchGeom tbg;
   if (M.use_tc_text && !M.text_tc.empty()) {
     std::vector<int> muls(1, 1);
-    tbg = build_geoms(&M, M.tx_meta, M.tx_pin, b->xstart, b->xlen, muls);
+    // tx_pin was last read by the previous run's text phase, which finished before that run's T_y read-back
+    tbg = build_geoms(&M, M.tx_meta, M.tx_pin, b->xstart, b->xlen, muls, nullptr, /*pin_idle=*/true);
     const Geom& TG = tbg.g[0];
     const int nblk = M.text_terms == 3 ? 6 : 3;
     M.tx_split.ensure(size_t(TG.rows_tot) * nblk * M.text_tc_max_cin * 2);
@@ -1322,9 +1341,14 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   if (ny * hp.hop > (int64_t(1) << 31) - 1) fail(SBV2_ERR_INVALID_ARGUMENT, "batch too long: more than 2^31 samples");
   b->Ny = ny;
   {
-    // ymeta: ystart[B], ylen[B], zp_ld[B] (ints) then zp_off[B] (int64)
-    std::vector<int> meta(size_t(3) * B);
-    std::vector<int64_t> zoff(B);
+    // ymeta: ystart[B], ylen[B], zp_ld[B] (ints) then zp_off[B] (int64); staged in pinned memory — the stream is idle
+    // here (the T_y read-back just synchronised it), so the previous run's copy out of the staging block is complete
+    // and no second synchronisation is needed
+    const size_t ibytes = align_up(size_t(3) * B * 4, 256);
+    const size_t mbytes = ibytes + size_t(B) * 8;
+    M.pin_ymeta.ensure(mbytes);
+    int* meta = M.pin_ymeta.as<int>();
+    int64_t* zoff = reinterpret_cast<int64_t*>(M.pin_ymeta.as<uint8_t>() + ibytes);
     int64_t o = 0;
     for (int i = 0; i < B; ++i) {
       meta[i] = b->ystart[i];
@@ -1333,13 +1357,29 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
       zoff[i] = o;
       o += b->zp_frames[i] * hp.inter;
     }
-    size_t ibytes = align_up(meta.size() * 4, 256);
     b->ymeta.stream = M.stream;
-    b->ymeta.ensure(ibytes + zoff.size() * 8);
-    CUDA_CHECK(cudaMemcpyAsync(b->ymeta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, M.stream));
-    CUDA_CHECK(cudaMemcpyAsync(b->ymeta.as<uint8_t>() + ibytes, zoff.data(), zoff.size() * 8, cudaMemcpyHostToDevice, M.stream));
-    CUDA_CHECK(cudaStreamSynchronize(M.stream));
+    b->ymeta.ensure(mbytes);
+    CUDA_CHECK(cudaMemcpyAsync(b->ymeta.p, M.pin_ymeta.p, mbytes, cudaMemcpyHostToDevice, M.stream));
     b->o_zp_off = ibytes;
+  }
+  // waveform layout: utterances back to back, plus the caller's pauses (written as zeros on the device)
+  {
+    b->wstart.resize(B);
+    long long w = 0;
+    bool any_pause = false;
+    for (int i = 0; i < B; ++i) {
+      b->wstart[i] = w;
+      w += (long long)b->ylen[i] * hp.hop;
+      if (!b->pause_after.empty() && b->pause_after[i] > 0) {
+        w += b->pause_after[i];
+        any_pause = true;
+      }
+    }
+    if (w > (int64_t(1) << 31) - 1) fail(SBV2_ERR_INVALID_ARGUMENT, "batch too long: more than 2^31 samples");
+    b->wave_total = w;
+    b->wave.stream = M.stream;
+    b->wave.ensure(size_t(std::max<long long>(w, 1)) * 4);
+    if (any_pause) CUDA_CHECK(cudaMemsetAsync(b->wave.p, 0, size_t(w) * 4, M.stream));
   }
   Segs yseg;
   yseg.start = b->ymeta.as<int>();
@@ -1377,7 +1417,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   if (M.use_tc_flow) {
     // tensor-core path: fp16 planar operands, fp32 residual stream hf
     std::vector<int> muls(1, 1);
-    BatchGeom bg = build_geoms(&M, M.fl_meta, M.fl_pin, b->ystart, b->ylen, muls);
+    BatchGeom bg = build_geoms(&M, M.fl_meta, M.fl_pin, b->ystart, b->ylen, muls, nullptr, /*pin_idle=*/true);  // stream idle since the T_y read-back
     const Geom& G = bg.g[0];
     PlanarSegs ps;
     ps.start = bg.d_ystart;
@@ -1391,10 +1431,10 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     M.fl_x0p.ensure(size_t(G.rows_tot) * (C / 2) * 2);
     M.fl_hp.ensure(size_t(G.rows_tot) * H * 2);
     M.fl_qkvp.ensure(size_t(G.rows_tot) * 3 * H * 2);
-    if (M.fl_qkvp.p != M.fl_qkvp_ptr) {
+    if (M.fl_qkvp.gen != M.fl_qkvp_gen) {
       // rows past an utterance's end are read (and masked) by the attention: they must hold finite values
       CUDA_CHECK(cudaMemsetAsync(M.fl_qkvp.p, 0, M.fl_qkvp.cap, M.stream));
-      M.fl_qkvp_ptr = M.fl_qkvp.p;
+      M.fl_qkvp_gen = M.fl_qkvp.gen;
     }
     M.fl_ctxp.ensure(size_t(G.rows_tot) * H * 2);
     M.fl_f1p.ensure(size_t(G.rows_tot) * filt * 2);
@@ -1481,12 +1521,11 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   M.region_end("flow");
 
   // ---- decoder ---------------------------------------------------------------------------------------
-  b->wave.stream = M.stream;
-  b->wave.ensure(size_t(ny) * hp.hop * 4);
   M.region_begin("decoder");
   if (M.use_umma && M.umma) {
-    umma_decoder_run(M.umma, &M, zc, g, B, b->ystart, b->ylen, b->wave.as<float>());
+    umma_decoder_run(M.umma, &M, zc, g, B, b->ystart, b->ylen, b->wave.as<float>(), &b->wstart);
   } else {
+    if (b->wave_total != ny * hp.hop) fail(SBV2_ERR_UNSUPPORTED, "pauses between utterances need the tensor-core decoder");
     decoder_fp32(M, zc, g, yseg, bseg, b->ystart, b->ylen, b->wave.as<float>(), M.ws[W_META]);
   }
   M.region_end("decoder");
@@ -1494,6 +1533,12 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
 }
 
 int64_t synth_total_samples(sbv2_model* m, const sbv2_device_batch* b) { return b->Ny * static_cast<SynthModel*>(m)->hp.hop; }
+int64_t synth_wave_total(const sbv2_device_batch* b) { return b->wave_total; }
+void synth_set_pauses(sbv2_device_batch* b, const int64_t* pause_after) {
+  b->pause_after.assign(pause_after, pause_after + b->B);
+  for (int64_t v : b->pause_after) SBV2_REQUIRE(v >= 0 && v < (int64_t(1) << 28), "pause length out of range");
+}
+bool synth_borrows_host(const sbv2_device_batch* b) { return b->borrowed_host; }
 
 void synth_batch_ty(const sbv2_device_batch* b, int64_t* ty) {
   for (int i = 0; i < b->B; ++i) ty[i] = b->ylen[i];
@@ -1503,7 +1548,7 @@ void synth_download(sbv2_model* mm, sbv2_device_batch* b, float** out_samples, i
   auto* M = static_cast<SynthModel*>(mm);
   SBV2_REQUIRE(b->ran, "batch has not been run");
   M->bind_device();
-  const int64_t total = b->Ny * M->hp.hop;
+  const int64_t total = b->wave_total;
   float* host = static_cast<float*>(alloc_out(size_t(std::max<int64_t>(total, 1)) * 4, true));
   int32_t* hdur = nullptr;
   int32_t* hf2p = nullptr;
@@ -1612,6 +1657,7 @@ void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, con
   launch_gather_rows(ctx, g, M.emb_g, reinterpret_cast<const int64_t*>(in + o_sid), batch, hp.gin, hp.n_speakers);
   b.wave.stream = M.stream;
   b.wave.ensure(size_t(ny) * hp.hop * 4);
+  b.wave_total = ny * hp.hop;
   M.region_begin("decoder");
   if (M.use_umma && M.umma) {
     umma_decoder_run(M.umma, &M, zr, g, batch, b.ystart, b.ylen, b.wave.as<float>());

@@ -561,11 +561,8 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_group
 int mt_slot(int mt) { return mt == 1 ? 0 : (mt == 2 ? 1 : (mt == 4 ? 2 : (mt == 8 ? 3 : 4))); }
 
 void set_smem_attr() {
-  static bool done = false;
-  if (!done) {
-    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    done = true;
-  }
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); });
 }
 
 }  // namespace
@@ -720,7 +717,8 @@ void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, i
 }
 
 BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::vector<int>& ystart, const std::vector<int>& ylen,
-                      const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights) {
+                      const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights, bool pin_idle,
+                      const std::vector<long long>* wstart) {
   const int B = int(ylen.size());
   BatchGeom bg;
   bg.g.resize(muls.size());
@@ -732,7 +730,7 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
   }
   const size_t total = goff.back() + size_t(3) * B;  // + ystart, wstart, order
   // the pinned blob of the previous run may still be in flight on the stream
-  CUDA_CHECK(cudaStreamSynchronize(owner->stream));
+  if (!pin_idle) CUDA_CHECK(cudaStreamSynchronize(owner->stream));
   pin.ensure(total * 4);
   int* h = pin.as<int>();
   for (size_t s = 0; s < muls.size(); ++s) {
@@ -775,7 +773,9 @@ BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::v
   long long hop = muls.back();
   for (int b = 0; b < B; ++b) {
     tail[b] = ystart[b];
-    tail[B + b] = int((long long)ystart[b] * hop);
+    const long long ws = wstart ? (*wstart)[size_t(b)] : (long long)ystart[b] * hop;
+    if (ws < 0 || ws > 2000000000LL) fail(SBV2_ERR_INVALID_ARGUMENT, "waveform offset exceeds the 32-bit sample index");
+    tail[B + b] = int(ws);
   }
   {
     // utterances by decreasing length: kernels with one CTA per (utterance, tile) start the long ones first

@@ -82,8 +82,11 @@ struct BatchGeom {
 };
 struct DBuf;
 struct PinnedBuf;
+// The tables are staged in `pin` and copied to `dev` asynchronously.  `pin_idle`: the caller guarantees that the previous
+// copy out of `pin` has completed (it synchronised the stream since); otherwise build_geoms synchronises the stream itself.
 BatchGeom build_geoms(sbv2_model* owner, DBuf& dev, PinnedBuf& pin, const std::vector<int>& ystart, const std::vector<int>& ylen,
-                      const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights = nullptr);
+                      const std::vector<int>& muls, const std::vector<std::vector<int>>* extra_heights = nullptr, bool pin_idle = false,
+                      const std::vector<long long>* wstart = nullptr /* sample offset of each utterance in the waveform buffer */);
 
 // Conv1d evaluated to ~fp32 accuracy on the fp16 tensor cores by splitting both operands into fp16 terms
 // (x = h0 + h1 [+ h2], w = w0 + w1 [+ w2]) and stacking the cross products along K:
@@ -154,8 +157,11 @@ void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, c
 struct UmmaDecoder;
 UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner);
 void umma_decoder_free(UmmaDecoder* d);
-// z: packed [Ny, Cin] fp32 (time-major), g: [B, gin] fp32, wave: [Ny*hop] fp32 (all device).
+// z: packed [Ny, Cin] fp32 (time-major), g: [B, gin] fp32, wave: fp32 (all device).  Utterance b's samples start at
+// wave[wstart[b]] (null: back to back, ystart[b] * hop).  The caller must have synchronised the owner's stream since the
+// previous umma_decoder_run of this decoder (its pinned geometry blob is rewritten without a further synchronisation).
 void umma_decoder_run(UmmaDecoder* d, sbv2_model* owner, const float* z, const float* g, int B,
-                      const std::vector<int>& ystart, const std::vector<int>& ylen, float* wave);
+                      const std::vector<int>& ystart, const std::vector<int>& ylen, float* wave,
+                      const std::vector<long long>* wstart = nullptr);
 
 }  // namespace sbv2

@@ -189,11 +189,11 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
 void umma_decoder_free(UmmaDecoder* d) { delete d; }
 
 void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const float* g, int B, const std::vector<int>& ystart,
-                      const std::vector<int>& ylen, float* wave) {
+                      const std::vector<int>& ylen, float* wave, const std::vector<long long>* wstart) {
   LaunchCtx ctx = owner->ctx();
   std::vector<int> muls(1, 1);
   for (int s = 0; s < D->n_stages; ++s) muls.push_back(muls.back() * D->up_u[s]);
-  BatchGeom bg = build_geoms(owner, D->meta, D->pin_meta, ystart, ylen, muls, &D->pair_heights);
+  BatchGeom bg = build_geoms(owner, D->meta, D->pin_meta, ystart, ylen, muls, &D->pair_heights, /*pin_idle=*/true, wstart);
   // buffer sizes
   size_t max_half = size_t(bg.g[0].rows_tot) * D->c0;
   for (int s = 0; s < D->n_stages; ++s) max_half = std::max(max_half, size_t(bg.g[s + 1].rows_tot) * D->stage_c[s]);

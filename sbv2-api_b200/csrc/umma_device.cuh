@@ -251,7 +251,7 @@ __device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, 
   tc_wait_ld();
   if (!valid) return;
   float* dst = p.rm_out + rm_row * p.rm_ld + co0_global;
-  const bool relu = p.act_out == ACT_RELU;
+  const bool relu = p.act_out == ACT_RELU, gelu = p.act_out == ACT_GELU;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
@@ -259,6 +259,7 @@ __device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, 
     float4 f = make_float4(__uint_as_float(v[4 * q]) * sc + b.x, __uint_as_float(v[4 * q + 1]) * sc + b.y,
                            __uint_as_float(v[4 * q + 2]) * sc + b.z, __uint_as_float(v[4 * q + 3]) * sc + b.w);
     if (relu) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
+    if (gelu) f = make_float4(act_apply(f.x, ACT_GELU), act_apply(f.y, ACT_GELU), act_apply(f.z, ACT_GELU), act_apply(f.w, ACT_GELU));
     *reinterpret_cast<float4*>(dst + 4 * q) = f;
   }
 }

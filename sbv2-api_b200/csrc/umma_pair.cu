@@ -504,14 +504,13 @@ bool make_pair_layer(sbv2_model* owner, const HostConv& c1, int dil, const HostC
 }
 
 void launch_umma_pair(const LaunchCtx& ctx, const PairLayer& L, const Geom& g, const PairCall& c, int n_utt) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] {
     CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_LIMIT));
-    attr = true;
-  }
+  });
   auto it = g.extra.find(L.out_rows);
   if (it == g.extra.end()) fail(SBV2_ERR_INTERNAL, "geometry lacks the tile table for a fused ResBlock pair");
   PairArgs a;

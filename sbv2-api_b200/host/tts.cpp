@@ -298,8 +298,9 @@ std::vector<uint8_t> TTSModelHolder::easy_synthesize(const std::string& ident, c
       utts.push_back(u);
       line_of.push_back(i);
     }
-    if (utts.empty() && lines.empty()) throw Error(ErrorKind::NdArrayError, "NDArray error: nothing to concatenate");
-    if (!utts.empty()) {
+    // tts.rs:321-324: `concatenate` of an empty list is an error (a text of empty lines only)
+    if (utts.empty()) throw Error(ErrorKind::NdArrayError, "NDArray error: nothing to concatenate");
+    {
       float* samples = nullptr;
       std::vector<int64_t> n(utts.size(), 0);
       check(sbv2_synthesize_batch(m->vits2->get(), utts.data(), int(utts.size()), &samples, n.data(), nullptr, nullptr));
@@ -319,6 +320,59 @@ std::vector<uint8_t> TTSModelHolder::easy_synthesize(const std::string& ident, c
     audio = synth_one(*lines[0]);
   }
   return tts_util::array_to_vec(audio);
+}
+
+std::vector<uint8_t> TTSModelHolder::easy_synthesize_tokens(const std::string& ident,
+                                                            const std::vector<std::optional<ParsedTokens>>& lines, int32_t style_id,
+                                                            int64_t speaker_id, const SynthesizeOptions& options) {
+  find_and_load_model(ident);
+  std::vector<float> style_vector = get_style_vector(ident, style_id, options.style_weight);
+  TTSModel* m = find_model(ident);
+  if (!m || !m->vits2) throw Error(ErrorKind::ModelNotFoundError, "model not found error: " + ident);
+  if (!options.split_sentences && (lines.size() != 1 || !lines[0]))
+    throw Error(ErrorKind::ValueError, "split_sentences=false expects exactly one parsed text");
+  std::vector<sbv2_token_utterance> utts;
+  std::vector<int64_t> pause;
+  for (size_t i = 0; i < lines.size(); ++i) {
+    if (!lines[i]) continue;  // empty line (tts.rs:293-295)
+    const ParsedTokens& t = *lines[i];
+    const int64_t t_x = int64_t(t.phones.size());
+    if (int64_t(t.tones.size()) != t_x || int64_t(t.lang_ids.size()) != t_x)
+      throw Error(ErrorKind::OrtError, "x_tst, tones and language must agree on x_tst_max_length");
+    if (t.token_ids.size() != t.attention_masks.size() || t.word2ph.size() != t.token_ids.size())
+      throw Error(ErrorKind::OtherError, "word2ph length must equal the number of BERT rows");
+    sbv2_token_utterance u{};
+    u.input_ids = t.token_ids.data();
+    u.attention_mask = t.attention_masks.data();
+    u.t_tok = int64_t(t.token_ids.size());
+    u.word2ph = t.word2ph.data();
+    u.x_tst = t.phones.data();
+    u.tones = t.tones.data();
+    u.lang_ids = t.lang_ids.data();
+    u.t_x = t_x;
+    u.sid = speaker_id;
+    u.style_vec = style_vector.data();
+    u.sdp_ratio = options.sdp_ratio;
+    u.length_scale = options.length_scale;
+    u.noise_scale = 0.677f;
+    u.noise_scale_w = 0.8f;
+    utts.push_back(u);
+    // tts.rs:318-320: half a second of silence after every line but the last one of the text
+    pause.push_back(options.split_sentences && i != lines.size() - 1 ? 22050 : 0);
+  }
+  if (utts.empty()) throw Error(ErrorKind::NdArrayError, "NDArray error: nothing to concatenate");
+  float* samples = nullptr;
+  int64_t total = 0;
+  check(sbv2_synthesize_from_tokens_batch(m->vits2->get(), bert_.get(), utts.data(), int(utts.size()), pause.data(), &samples, &total,
+                                          nullptr));
+  void* wav = nullptr;
+  size_t wav_n = 0;
+  const int st = sbv2_wav_from_f32(samples, total, &wav, &wav_n);
+  sbv2_free(samples);
+  check(st);
+  std::vector<uint8_t> out(static_cast<uint8_t*>(wav), static_cast<uint8_t*>(wav) + wav_n);
+  sbv2_free(wav);
+  return out;
 }
 
 }  // namespace host
@@ -376,8 +430,15 @@ int sbv2_holder_new(const void* bert_onnx, size_t bert_n, const void* tokenizer,
 
 void sbv2_holder_free(sbv2_holder* h) { delete h; }
 
+namespace {
+void need(const void* p, const char* what) {
+  if (!p) throw sbv2::host::Error(sbv2::host::ErrorKind::ValueError, std::string("null argument: ") + what);
+}
+}  // namespace
+
 int sbv2_holder_load_sbv2file(sbv2_holder* h, const char* ident, const void* bytes, size_t n) {
   return holder_guard([&] {
+    need(h, "holder"), need(ident, "ident"), need(bytes, "bytes");
     std::vector<uint8_t> b(static_cast<const uint8_t*>(bytes), static_cast<const uint8_t*>(bytes) + n);
     h->impl.load_sbv2file(ident, b);
   });
@@ -385,6 +446,7 @@ int sbv2_holder_load_sbv2file(sbv2_holder* h, const char* ident, const void* byt
 
 int sbv2_holder_load(sbv2_holder* h, const char* ident, const void* style_json, size_t style_n, const void* onnx, size_t onnx_n) {
   return holder_guard([&] {
+    need(h, "holder"), need(ident, "ident"), need(style_json, "style_json"), need(onnx, "onnx");
     std::vector<uint8_t> s(static_cast<const uint8_t*>(style_json), static_cast<const uint8_t*>(style_json) + style_n);
     std::vector<uint8_t> o(static_cast<const uint8_t*>(onnx), static_cast<const uint8_t*>(onnx) + onnx_n);
     h->impl.load(ident, s, o);
@@ -393,6 +455,7 @@ int sbv2_holder_load(sbv2_holder* h, const char* ident, const void* style_json, 
 
 int sbv2_holder_load_aivmx(sbv2_holder* h, const char* ident, const void* bytes, size_t n) {
   return holder_guard([&] {
+    need(h, "holder"), need(ident, "ident"), need(bytes, "bytes");
     std::vector<uint8_t> b(static_cast<const uint8_t*>(bytes), static_cast<const uint8_t*>(bytes) + n);
     h->impl.load_aivmx(ident, b);
   });
@@ -400,6 +463,7 @@ int sbv2_holder_load_aivmx(sbv2_holder* h, const char* ident, const void* bytes,
 
 int sbv2_holder_unload(sbv2_holder* h, const char* ident, int* found) {
   return holder_guard([&] {
+    need(h, "holder"), need(ident, "ident");
     bool f = h->impl.unload(ident);
     if (found) *found = f ? 1 : 0;
   });
@@ -407,6 +471,7 @@ int sbv2_holder_unload(sbv2_holder* h, const char* ident, int* found) {
 
 int sbv2_holder_models(const sbv2_holder* h, char** out) {
   return holder_guard([&] {
+    need(h, "holder"), need(out, "out");
     std::string s;
     for (auto& m : h->impl.models()) {
       if (!s.empty()) s += "\n";
@@ -419,11 +484,23 @@ int sbv2_holder_models(const sbv2_holder* h, char** out) {
 }
 
 int sbv2_holder_loaded_count(const sbv2_holder* h, int* out) {
-  return holder_guard([&] { *out = int(h->impl.loaded_count()); });
+  return holder_guard([&] {
+    need(h, "holder"), need(out, "out");
+    *out = int(h->impl.loaded_count());
+  });
+}
+
+int sbv2_holder_bert_hidden_size(const sbv2_holder* h, int* out) {
+  return holder_guard([&] {
+    need(h, "holder"), need(out, "out");
+    if (sbv2_bert_hidden_size(const_cast<sbv2_holder*>(h)->impl.bert_session().get(), out) != SBV2_OK)
+      throw sbv2::host::Error(sbv2::host::ErrorKind::OrtError, sbv2_last_error());
+  });
 }
 
 int sbv2_holder_get_style_vector(sbv2_holder* h, const char* ident, int32_t style_id, float weight, float* out) {
   return holder_guard([&] {
+    need(h, "holder"), need(ident, "ident"), need(out, "out");
     auto v = h->impl.get_style_vector(ident, style_id, weight);
     memcpy(out, v.data(), v.size() * 4);
   });
@@ -432,6 +509,9 @@ int sbv2_holder_get_style_vector(sbv2_holder* h, const char* ident, int32_t styl
 int sbv2_holder_bert_features(sbv2_holder* h, const int64_t* token_ids, const int64_t* attention_mask, int64_t t_tok,
                               const int32_t* word2ph, float** out, int64_t* t_x) {
   return holder_guard([&] {
+    need(h, "holder"), need(token_ids, "token_ids"), need(attention_mask, "attention_mask"), need(word2ph, "word2ph"), need(out, "out"),
+        need(t_x, "t_x");
+    if (t_tok <= 0) throw sbv2::host::Error(sbv2::host::ErrorKind::ValueError, "t_tok must be positive");
     std::vector<int64_t> ids(token_ids, token_ids + t_tok), mask(attention_mask, attention_mask + t_tok);
     std::vector<int32_t> w(word2ph, word2ph + t_tok);
     auto a = h->impl.bert_features(ids, mask, w);
@@ -447,14 +527,21 @@ int sbv2_holder_easy_synthesize(sbv2_holder* h, const char* ident, const sbv2_se
                                 float style_weight, void** wav_bytes, size_t* wav_n) {
   return holder_guard([&] {
     using namespace sbv2::host;
+    need(h, "holder"), need(ident, "ident"), need(wav_bytes, "wav_bytes"), need(wav_n, "wav_n");
+    if (n_sentences > 0) need(sentences, "sentences");
+    // rows of bert_ori = hidden size of the holder's DeBERTa (1024 for deberta-v2-large; model.rs:66-68 feeds what bert.rs returns)
+    int hidden = 0;
+    if (sbv2_bert_hidden_size(h->impl.bert_session().get(), &hidden) != SBV2_OK || hidden <= 0)
+      throw Error(ErrorKind::OrtError, "cannot determine the BERT hidden size");
     std::vector<std::optional<ParsedText>> lines(size_t(total_lines > 0 ? total_lines : 0));
     for (int i = 0; i < n_sentences; ++i) {
       const sbv2_sentence& s = sentences[i];
       if (s.line_index < 0 || s.line_index >= total_lines) throw Error(ErrorKind::ValueError, "line_index out of range");
+      if (!s.bert || !s.phones || !s.tones || !s.lang_ids || s.t_x <= 0) throw Error(ErrorKind::ValueError, "sentence with null or empty input");
       ParsedText t;
-      t.bert_ori.rows = 1024;
+      t.bert_ori.rows = hidden;
       t.bert_ori.cols = s.t_x;
-      t.bert_ori.data.assign(s.bert, s.bert + 1024 * s.t_x);
+      t.bert_ori.data.assign(s.bert, s.bert + size_t(hidden) * size_t(s.t_x));
       t.phones.assign(s.phones, s.phones + s.t_x);
       t.tones.assign(s.tones, s.tones + s.t_x);
       t.lang_ids.assign(s.lang_ids, s.lang_ids + s.t_x);
@@ -466,6 +553,41 @@ int sbv2_holder_easy_synthesize(sbv2_holder* h, const char* ident, const sbv2_se
     opt.style_weight = style_weight;
     opt.split_sentences = true;
     auto wav = h->impl.easy_synthesize(ident, lines, style_id, speaker_id, opt);
+    void* p = sbv2_alloc(wav.size());
+    memcpy(p, wav.data(), wav.size());
+    *wav_bytes = p;
+    *wav_n = wav.size();
+  });
+}
+
+int sbv2_holder_easy_synthesize_tokens(sbv2_holder* h, const char* ident, const sbv2_token_sentence* sentences, int n_sentences,
+                                       int64_t total_lines, int32_t style_id, int64_t speaker_id, float sdp_ratio, float length_scale,
+                                       float style_weight, void** wav_bytes, size_t* wav_n) {
+  return holder_guard([&] {
+    using namespace sbv2::host;
+    need(h, "holder"), need(ident, "ident"), need(wav_bytes, "wav_bytes"), need(wav_n, "wav_n");
+    if (n_sentences > 0) need(sentences, "sentences");
+    std::vector<std::optional<ParsedTokens>> lines(size_t(total_lines > 0 ? total_lines : 0));
+    for (int i = 0; i < n_sentences; ++i) {
+      const sbv2_token_sentence& s = sentences[i];
+      if (s.line_index < 0 || s.line_index >= total_lines) throw Error(ErrorKind::ValueError, "line_index out of range");
+      if (!s.token_ids || !s.attention_mask || !s.word2ph || !s.phones || !s.tones || !s.lang_ids || s.t_tok <= 0 || s.t_x <= 0)
+        throw Error(ErrorKind::ValueError, "sentence with null or empty input");
+      ParsedTokens t;
+      t.token_ids.assign(s.token_ids, s.token_ids + s.t_tok);
+      t.attention_masks.assign(s.attention_mask, s.attention_mask + s.t_tok);
+      t.word2ph.assign(s.word2ph, s.word2ph + s.t_tok);
+      t.phones.assign(s.phones, s.phones + s.t_x);
+      t.tones.assign(s.tones, s.tones + s.t_x);
+      t.lang_ids.assign(s.lang_ids, s.lang_ids + s.t_x);
+      lines[size_t(s.line_index)] = std::move(t);
+    }
+    SynthesizeOptions opt;
+    opt.sdp_ratio = sdp_ratio;
+    opt.length_scale = length_scale;
+    opt.style_weight = style_weight;
+    opt.split_sentences = true;
+    auto wav = h->impl.easy_synthesize_tokens(ident, lines, style_id, speaker_id, opt);
     void* p = sbv2_alloc(wav.size());
     memcpy(p, wav.data(), wav.size());
     *wav_bytes = p;

@@ -89,6 +89,14 @@ struct ParsedText {
   std::vector<int64_t> phones, tones, lang_ids;
 };
 
+// The same for the device-resident chain: the tokenizer's ids / mask and word2ph instead of
+// BERT features; DeBERTa then runs inside easy_synthesize_tokens, batched over the lines of the request.
+struct ParsedTokens {
+  std::vector<int64_t> token_ids, attention_masks;
+  std::vector<int32_t> word2ph;
+  std::vector<int64_t> phones, tones, lang_ids;
+};
+
 struct TTSModel {
   std::optional<Session> vits2;
   Array2 style_vectors;
@@ -113,6 +121,11 @@ class TTSModelHolder {
   // it still counts for the "not the last line" silence rule, tts.rs:293-320).
   std::vector<uint8_t> easy_synthesize(const std::string& ident, const std::vector<std::optional<ParsedText>>& lines, int32_t style_id,
                                        int64_t speaker_id, const SynthesizeOptions& options);
+  // easy_synthesize with bert::predict folded in: every non-empty line of the request goes through DeBERTa as ONE
+  // right-padded batch and through the synthesizer as ONE batch (features never leave the device), the 22 050-sample
+  // pauses of tts.rs:318-320 are written on the device, and the WAV is one header + one copy of the pinned result.
+  std::vector<uint8_t> easy_synthesize_tokens(const std::string& ident, const std::vector<std::optional<ParsedTokens>>& lines,
+                                              int32_t style_id, int64_t speaker_id, const SynthesizeOptions& options);
   size_t loaded_count() const;
   Session& bert_session() { return bert_; }
 

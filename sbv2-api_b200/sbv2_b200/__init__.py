@@ -34,6 +34,19 @@ class Utterance(C.Structure):
                 ("noise_zp", C.POINTER(C.c_float)), ("noise_zp_frames", C.c_int64)]
 
 
+class TokenUtterance(C.Structure):
+    _fields_ = [("input_ids", C.POINTER(C.c_int64)), ("attention_mask", C.POINTER(C.c_int64)), ("t_tok", C.c_int64),
+                ("word2ph", C.POINTER(C.c_int32)), ("x_tst", C.POINTER(C.c_int64)), ("tones", C.POINTER(C.c_int64)),
+                ("lang_ids", C.POINTER(C.c_int64)), ("t_x", C.c_int64), ("sid", C.c_int64), ("style_vec", C.POINTER(C.c_float)),
+                ("sdp_ratio", C.c_float), ("length_scale", C.c_float), ("noise_scale", C.c_float), ("noise_scale_w", C.c_float)]
+
+
+class TokenSentence(C.Structure):
+    _fields_ = [("token_ids", C.POINTER(C.c_int64)), ("attention_mask", C.POINTER(C.c_int64)), ("word2ph", C.POINTER(C.c_int32)),
+                ("t_tok", C.c_int64), ("phones", C.POINTER(C.c_int64)), ("tones", C.POINTER(C.c_int64)),
+                ("lang_ids", C.POINTER(C.c_int64)), ("t_x", C.c_int64), ("line_index", C.c_int64)]
+
+
 class Sentence(C.Structure):
     _fields_ = [("bert", C.POINTER(C.c_float)), ("phones", C.POINTER(C.c_int64)), ("tones", C.POINTER(C.c_int64)),
                 ("lang_ids", C.POINTER(C.c_int64)), ("t_x", C.c_int64), ("line_index", C.c_int64)]
@@ -50,6 +63,7 @@ def _load() -> C.CDLL:
         "sbv2_last_error": (C.c_char_p, []),
         "sbv2_free": (None, [vp]),
         "sbv2_alloc": (vp, [sz]),
+        "sbv2_alloc_pinned": (vp, [sz]),
         "sbv2_set_last_error": (None, [C.c_char_p]),
         "sbv2_version": (C.c_char_p, []),
         "sbv2_device_count": (C.c_int, []),
@@ -63,6 +77,10 @@ def _load() -> C.CDLL:
         "sbv2_synthesize": (C.c_int, [vp, pf, pi64, pi64, pi64, i64, i64, pf, f32, f32, f32, f32, C.POINTER(pf), pi64]),
         "sbv2_synthesize_from_tokens": (C.c_int, [vp, vp, pi64, pi64, i64, pi32, pi64, pi64, pi64, i64, i64, pf, f32, f32, f32, f32,
                                                   C.POINTER(pf), pi64]),
+        "sbv2_synthesize_from_tokens_batch": (C.c_int, [vp, vp, C.POINTER(TokenUtterance), C.c_int, pi64, C.POINTER(pf), pi64, pi64]),
+        "sbv2_holder_easy_synthesize_tokens": (C.c_int, [vp, C.c_char_p, C.POINTER(TokenSentence), C.c_int, i64, i32, i64, f32, f32, f32,
+                                                         C.POINTER(vp), C.POINTER(sz)]),
+        "sbv2_onnx_bind_report": (C.c_int, [vp, sz, C.c_int, C.POINTER(vp)]),
         "sbv2_model_seed": (C.c_int, [vp, C.c_uint64]),
         "sbv2_synthesize_with_noise": (C.c_int, [vp, pf, pi64, pi64, pi64, i64, i64, pf, f32, f32, f32, f32, pf, pf, i64,
                                                  C.POINTER(pf), pi64, pi32, C.POINTER(pi32), pi64]),
@@ -91,6 +109,7 @@ def _load() -> C.CDLL:
         "sbv2_holder_unload": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_int)]),
         "sbv2_holder_models": (C.c_int, [vp, C.POINTER(vp)]),
         "sbv2_holder_loaded_count": (C.c_int, [vp, C.POINTER(C.c_int)]),
+        "sbv2_holder_bert_hidden_size": (C.c_int, [vp, C.POINTER(C.c_int)]),
         "sbv2_holder_get_style_vector": (C.c_int, [vp, C.c_char_p, i32, f32, pf]),
         "sbv2_holder_bert_features": (C.c_int, [vp, pi64, pi64, i64, pi32, C.POINTER(pf), pi64]),
         "sbv2_holder_easy_synthesize": (C.c_int, [vp, C.c_char_p, C.POINTER(Sentence), C.c_int, i64, i32, i64, f32, f32, f32,
@@ -163,6 +182,33 @@ def _take(ptr, n: int, dtype, copy: bool = True) -> np.ndarray:
 
 
 _OWNERS = {}
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """Uninitialised array in page-locked host memory (sbv2_alloc_pinned): inputs that live here are read by the copy
+    engine in place instead of being staged."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    p = lib.sbv2_alloc_pinned(max(1, n * np.dtype(dtype).itemsize))
+    if not p:
+        raise MemoryError("sbv2_alloc_pinned failed")
+    return _take(C.cast(p, C.POINTER(C.c_byte)), n * np.dtype(dtype).itemsize, np.uint8, copy=False).view(dtype).reshape(shape)
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
+def onnx_bind_report(onnx_bytes: bytes, bert: bool) -> dict:
+    """Which initializer every canonical weight name binds to (structural binding of anonymous exports); CPU only."""
+    p = C.c_void_p()
+    _check(lib.sbv2_onnx_bind_report(onnx_bytes, len(onnx_bytes), 1 if bert else 0, C.byref(p)))
+    s = C.string_at(p).decode()
+    lib.sbv2_free(p)
+    return json.loads(s)
 
 
 def device_count() -> int:
@@ -331,6 +377,30 @@ class Model:
                                                _pf(sv), sdp_ratio, length_scale, noise_scale, noise_scale_w, C.byref(p), C.byref(n)))
         return _take(p, n.value, np.float32)
 
+    def synthesize_from_tokens_batch(self, bert_model: "Model", sentences: Sequence[dict], pause_after: Optional[Sequence[int]] = None):
+        """sentences[i]: dict(token_ids, word2ph, x_tst, tones, lang_ids, style_vec[, sid, sdp_ratio, length_scale,
+        noise_scale, noise_scale_w]).  -> (audio [total] incl. the pauses, samples per sentence int64 [batch])"""
+        B = len(sentences)
+        arr = (TokenUtterance * B)()
+        keep = []
+        for i, u in enumerate(sentences):
+            ids, w2p = _i64(u["token_ids"]), np.ascontiguousarray(u["word2ph"], dtype=np.int32)
+            mask = _i64(u.get("attention_mask", np.ones_like(ids)))
+            x, t, l, sv = _i64(u["x_tst"]), _i64(u["tones"]), _i64(u["lang_ids"]), _f32(u["style_vec"])
+            keep += [ids, mask, w2p, x, t, l, sv]
+            a = arr[i]
+            a.input_ids, a.attention_mask, a.t_tok, a.word2ph = _pi64(ids), _pi64(mask), ids.size, w2p.ctypes.data_as(C.POINTER(C.c_int32))
+            a.x_tst, a.tones, a.lang_ids, a.t_x = _pi64(x), _pi64(t), _pi64(l), x.size
+            a.sid, a.style_vec = int(u.get("sid", 0)), _pf(sv)
+            a.sdp_ratio, a.length_scale = float(u.get("sdp_ratio", 0.0)), float(u.get("length_scale", 1.0))
+            a.noise_scale, a.noise_scale_w = float(u.get("noise_scale", 0.677)), float(u.get("noise_scale_w", 0.8))
+        pa = _i64(pause_after) if pause_after is not None else None
+        p, total = C.POINTER(C.c_float)(), C.c_int64()
+        ns = np.zeros(B, dtype=np.int64)
+        _check(lib.sbv2_synthesize_from_tokens_batch(self._h, bert_model._h, arr, B, _pi64(pa) if pa is not None else None, C.byref(p),
+                                                     C.byref(total), _pi64(ns)))
+        return _take(p, total.value, np.float32), ns
+
     def synthesize_with_noise(self, bert_ori, x_tst, sid: int, tones, lang_ids, style_vector, sdp_ratio, length_scale,
                               noise_scale, noise_scale_w, noise_sdp, noise_zp):
         """-> (audio [N], durations int32 [T_x], frame2ph int32 [T_y])."""
@@ -457,6 +527,9 @@ class TTSModelHolder:
         self._h = C.c_void_p()
         _check(lib.sbv2_holder_new(bert_model_bytes, len(bert_model_bytes), tokenizer_bytes, len(tokenizer_bytes),
                                    -1 if max_loaded_models is None else int(max_loaded_models), device, C.byref(self._h)))
+        h = C.c_int()
+        _check(lib.sbv2_holder_bert_hidden_size(self._h, C.byref(h)))
+        self._bert_hidden = h.value
 
     def close(self):
         if self._h:
@@ -507,7 +580,31 @@ class TTSModelHolder:
         p, tx = C.POINTER(C.c_float)(), C.c_int64()
         _check(lib.sbv2_holder_bert_features(self._h, _pi64(ids), _pi64(mask), ids.size,
                                              w.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(p), C.byref(tx)))
-        return _take(p, 1024 * tx.value, np.float32).reshape(1024, tx.value)
+        n = C.c_int64()  # rows = hidden size of the holder's DeBERTa: the library returns rows * t_x floats
+        rows = self._bert_hidden
+        return _take(p, rows * tx.value, np.float32).reshape(rows, tx.value)
+
+    def easy_synthesize_tokens(self, ident: str, lines: Sequence[Optional[dict]], style_id: int, speaker_id: int,
+                               sdp_ratio: float = 0.0, length_scale: float = 1.0, style_weight: float = 1.0) -> bytes:
+        """``lines[i]`` is None for an empty line, else dict(token_ids, word2ph, phones, tones, lang_ids): the request's
+        sentences run through DeBERTa and the synthesizer as one batch each, silences are written on the device."""
+        sent = [(i, l) for i, l in enumerate(lines) if l is not None]
+        arr = (TokenSentence * max(len(sent), 1))()
+        keep = []
+        for j, (i, l) in enumerate(sent):
+            ids, w2p = _i64(l["token_ids"]), np.ascontiguousarray(l["word2ph"], dtype=np.int32)
+            mask = _i64(l.get("attention_mask", np.ones_like(ids)))
+            ph, t, lg = _i64(l["phones"]), _i64(l["tones"]), _i64(l["lang_ids"])
+            keep += [ids, mask, w2p, ph, t, lg]
+            a = arr[j]
+            a.token_ids, a.attention_mask, a.word2ph, a.t_tok = _pi64(ids), _pi64(mask), w2p.ctypes.data_as(C.POINTER(C.c_int32)), ids.size
+            a.phones, a.tones, a.lang_ids, a.t_x, a.line_index = _pi64(ph), _pi64(t), _pi64(lg), ph.size, i
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib.sbv2_holder_easy_synthesize_tokens(self._h, ident.encode(), arr, len(sent), len(lines), style_id, speaker_id,
+                                                      sdp_ratio, length_scale, style_weight, C.byref(p), C.byref(n)))
+        out = C.string_at(p, n.value)
+        lib.sbv2_free(p)
+        return out
 
     def easy_synthesize(self, ident: str, lines: Sequence[Optional[dict]], style_id: int, speaker_id: int,
                         sdp_ratio: float = 0.0, length_scale: float = 1.0, style_weight: float = 1.0) -> bytes:

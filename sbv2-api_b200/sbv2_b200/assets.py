@@ -116,14 +116,19 @@ SYNTH_INPUTS = ["x_tst", "x_tst_lengths", "sid", "tones", "language", "bert", "s
 
 
 def synth_onnx(state: Dict[str, np.ndarray], upsample_rates: Sequence[int], resblock_dilations: Sequence[Sequence[int]],
-               anonymize_weight_norm: bool = False, metadata: Optional[Dict[str, str]] = None) -> bytes:
+               anonymize_weight_norm: bool = False, metadata: Optional[Dict[str, str]] = None,
+               anonymize_linear: bool = False) -> bytes:
     """ModelProto for a JP-Extra synthesizer whose initializers are ``state`` (upstream state_dict
     names, weight-norm folded).  The decoder's Conv / ConvTranspose nodes are emitted in execution
     order with their strides / dilations, as a traced export carries them; with
-    ``anonymize_weight_norm`` the weight-normed decoder convs get ``onnx::Conv_N`` names like a real
-    export after constant folding."""
+    ``anonymize_weight_norm`` the weight-normed convs (decoder ups / resblocks, WN flow layers) get
+    ``onnx::Conv_N`` names like a real export after constant folding, and with ``anonymize_linear``
+    every nn.Linear the graph applies to a 3-D input (``spk_emb_linear`` of the encoders) becomes a
+    TRANSPOSED ``onnx::MatMul_N`` initializer feeding MatMul -> Add with the still-named bias
+    (scripts/convert/convert_model.py:115-156)."""
     inits: Dict[str, np.ndarray] = {}
     rename: Dict[str, str] = {}
+    transposed: set = set()
     counter = [1000]
 
     def reg(name: str) -> str:
@@ -136,6 +141,28 @@ def synth_onnx(state: Dict[str, np.ndarray], upsample_rates: Sequence[int], resb
         return name
 
     nodes: List[bytes] = []
+    if anonymize_weight_norm:
+        # WN flow variant: in_layers / res_skip_layers / cond_layer are weight-normed Conv1d
+        for k_ in sorted(state):
+            if k_.startswith("flow.flows.") and ".enc." in k_ and k_.endswith(".weight") and \
+                    any(t in k_ for t in (".in_layers.", ".res_skip_layers.", ".cond_layer.")):
+                counter[0] += 1
+                rename[k_] = f"onnx::Conv_{counter[0]}"
+                kk = state[k_].shape[2]
+                nodes.append(node_proto("Conv", ["wn_in", rename[k_], k_[:-7] + ".bias"], [k_ + "_out"], "/" + k_[:-7].replace(".", "/") + "/Conv",
+                                        [attribute_ints("kernel_shape", [kk]), attribute_ints("strides", [1]), attribute_int("group", 1)]))
+    if anonymize_linear:
+        for k_ in sorted(state):
+            if k_.endswith(".spk_emb_linear.weight"):
+                counter[0] += 1
+                rename[k_] = f"onnx::MatMul_{counter[0]}"
+                transposed.add(k_)
+                base = k_[:-7]
+                nodes.append(node_proto("MatMul", ["g_t", rename[k_]], [base + "_mm"], "/" + base.replace(".", "/") + "/MatMul"))
+                nodes.append(node_proto("Add", [base + ".bias", base + "_mm"], [base + "_out"], "/" + base.replace(".", "/") + "/Add"))
+        if "enc_p.style_proj.weight" in state:  # Linear on a 2-D input exports as Gemm(transB=1) and keeps its name
+            nodes.append(node_proto("Gemm", ["style_vec", "enc_p.style_proj.weight", "enc_p.style_proj.bias"], ["style_emb"],
+                                    "/enc_p/style_proj/Gemm", [attribute_int("transB", 1)]))
     n_ups = sum(1 for k in state if k.startswith("dec.ups.") and k.endswith(".weight"))
     n_res_per = len(resblock_dilations)
     cur = "dec_in"
@@ -167,15 +194,38 @@ def synth_onnx(state: Dict[str, np.ndarray], upsample_rates: Sequence[int], resb
                                              attribute_int("group", 1)]))
                     x = nm + "_out"
     for k_, v in state.items():
-        inits[rename.get(k_, k_)] = np.asarray(v)
+        v = np.asarray(v)
+        inits[rename.get(k_, k_)] = np.ascontiguousarray(v.T) if k_ in transposed else v
     return model_proto(inits, nodes, SYNTH_INPUTS, ["output"], metadata)
 
 
-def deberta_onnx(state: Dict[str, np.ndarray], metadata: Optional[Dict[str, str]] = None) -> bytes:
+def deberta_onnx(state: Dict[str, np.ndarray], metadata: Optional[Dict[str, str]] = None,
+                 anonymize_linear: bool = False) -> bytes:
     """ModelProto for the DeBERTa-v2 feature encoder; initializers keep HF ``state_dict`` names
-    (``deberta.embeddings.word_embeddings.weight`` ...). scripts/convert/convert_deberta.py:47-48."""
-    return model_proto({k: np.asarray(v) for k, v in state.items()}, (), ["input_ids", "token_type_ids", "attention_mask"],
-                       ["output"], metadata)
+    (``deberta.embeddings.word_embeddings.weight`` ...). scripts/convert/convert_deberta.py:47-48.
+
+    ``anonymize_linear`` reproduces what the TorchScript export + onnxsim of convert_deberta.py:36-52 does to the
+    graph: every encoder Linear (query/key/value_proj, attention.output.dense, intermediate.dense, output.dense) is
+    constant-folded into a TRANSPOSED [in, out] ``onnx::MatMul_N`` initializer consumed by MatMul -> Add(bias), only
+    the biases / embeddings / LayerNorm parameters / the ConvLayer weight keep their names."""
+    inits: Dict[str, np.ndarray] = {}
+    nodes: List[bytes] = []
+    counter = 2000
+    linear = (".attention.self.query_proj", ".attention.self.key_proj", ".attention.self.value_proj",
+              ".attention.output.dense", ".intermediate.dense", ".output.dense")
+    for k, v in state.items():
+        v = np.asarray(v)
+        if anonymize_linear and k.endswith(".weight") and ".encoder.layer." in k and k[:-7].endswith(linear) and v.ndim == 2:
+            counter += 1
+            anon = f"onnx::MatMul_{counter}"
+            base = k[:-7]
+            inits[anon] = np.ascontiguousarray(v.T)
+            nodes.append(node_proto("MatMul", [base + "_in", anon], [base + "_mm"], "/" + base.replace(".", "/") + "/MatMul"))
+            # TorchScript emits Add(bias, matmul) for Linear on 3-D inputs
+            nodes.append(node_proto("Add", [base + ".bias", base + "_mm"], [base + "_out"], "/" + base.replace(".", "/") + "/Add"))
+        else:
+            inits[k] = v
+    return model_proto(inits, nodes, ["input_ids", "token_type_ids", "attention_mask"], ["output"], metadata)
 
 
 # ---- containers --------------------------------------------------------------------------------

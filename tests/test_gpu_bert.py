@@ -1,7 +1,9 @@
 """GPU parity of the DeBERTa-v2 feature encoder (bert::predict, crates/sbv2_core/src/bert.rs:6-24)
-against the HF model the reference exports (oracle/deberta.py).  GEMM operands are fp16 (fp32
-accumulate, fp32 residual stream): tolerance 3e-2 max-abs on activations of magnitude ~4 and a
-relative Frobenius error below 5e-3."""
+against the HF model the reference exports (oracle/deberta.py).
+
+Two numerics modes (bert_model.cu): "exact" (default; two-term fp16 operand splits, fp32 activations and attention) must
+match HF fp32 to max-abs 2e-4 / relative Frobenius 2e-5 — the features feed ceil() downstream; "fp16"
+(SBV2_B200_BERT=fp16; single-term fp16 operands, tensor-core attention) to 3e-2 / 5e-3 on activations of magnitude ~4."""
 import os
 
 import numpy as np
@@ -29,13 +31,37 @@ def tiny(S):
     cfg = od.tiny_config()
     hf = od.build_model(cfg, seed=1)
     model = S.Model(assets.deberta_onnx(od.state_dict_numpy(hf)), bert=True)
+    assert model.describe()["numerics"] == "exact"
     return cfg, hf, model
 
 
-def close(got, ref):
+@pytest.fixture(scope="module")
+def tiny_fp16(S):
+    from sbv2_b200 import assets
+    cfg = od.tiny_config()
+    hf = od.build_model(cfg, seed=1)
+    model = make_model(S, assets.deberta_onnx(od.state_dict_numpy(hf)), "fp16")
+    assert model.describe()["numerics"] == "fp16"
+    return cfg, hf, model
+
+
+TOL = {"exact": (2e-4, 2e-5), "fp16": (3e-2, 5e-3)}
+
+
+def close(got, ref, mode="exact"):
     err = np.abs(got - ref).max()
     rel = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30)
-    assert err <= 3e-2 and rel <= 5e-3, f"max-abs {err:.3e}, rel-fro {rel:.3e} (|ref| max {np.abs(ref).max():.2f})"
+    assert err <= TOL[mode][0] and rel <= TOL[mode][1], f"[{mode}] max-abs {err:.3e}, rel-fro {rel:.3e} (|ref| max {np.abs(ref).max():.2f})"
+
+
+def make_model(S, onnx, mode):
+    if mode == "exact":
+        return S.Model(onnx, bert=True)
+    os.environ["SBV2_B200_BERT"] = "fp16"
+    try:
+        return S.Model(onnx, bert=True)
+    finally:
+        del os.environ["SBV2_B200_BERT"]
 
 
 def test_describe_and_live_layers(tiny):
@@ -56,6 +82,17 @@ def test_predict_matches_hf(tiny, s):
     got = model.predict(ids[0].numpy(), np.ones(s, np.int64))
     assert got.shape == (s, cfg.hidden_size)
     close(got, ref)
+
+
+@pytest.mark.parametrize("s", [1, 7, 64, 128, 129, 300])
+def test_predict_matches_hf_fp16_mode(tiny_fp16, s):
+    """The throughput mode: tensor-core attention up to 128 tokens, CUDA-core kernel beyond."""
+    cfg, hf, model = tiny_fp16
+    g = torch.Generator().manual_seed(100 + s)
+    ids = torch.randint(3, cfg.vocab_size, (1, s), generator=g)
+    ref = od.predict(hf, ids, torch.ones_like(ids))[0].numpy()
+    got = model.predict(ids[0].numpy(), np.ones(s, np.int64))
+    close(got, ref, "fp16")
 
 
 def test_golden_fixture(tiny):
@@ -101,10 +138,10 @@ def test_tensor_core_attention_matches_cuda_core_attention(S):
     from sbv2_b200 import assets
     cfg = od.tiny_config()
     onnx = assets.deberta_onnx(od.state_dict_numpy(od.build_model(cfg, seed=1)))
-    tc = S.Model(onnx, bert=True)
+    tc = make_model(S, onnx, "fp16")
     os.environ["SBV2_B200_BERT_ATTN"] = "simt"
     try:
-        simt = S.Model(onnx, bert=True)
+        simt = make_model(S, onnx, "fp16")
     finally:
         del os.environ["SBV2_B200_BERT_ATTN"]
     g = torch.Generator().manual_seed(9)
@@ -119,4 +156,4 @@ def test_tensor_core_attention_matches_cuda_core_attention(S):
     assert np.isfinite(a).all()
     for i, n in enumerate(lens):
         assert not a[i, n:].any()
-        close(a[i, :n], b_[i, :n])
+        close(a[i, :n], b_[i, :n], "fp16")
