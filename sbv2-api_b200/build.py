@@ -43,18 +43,40 @@ def _digest(path: str) -> str:
     return h.hexdigest()
 
 
+# Debug hooks (sbv2_debug_conv_compare / _conv_trace / _pair_compare / _attn_trace, the MMA micro-benchmarks) are compiled
+# only with -DSBV2_DEBUG_HOOKS and linked only into libsbv2_b200_debug.so, which the kernel unit tests and tools/ load.
+# The product library libsbv2_b200.so carries the C ABI of include/sbv2_b200.h and nothing else.
+DEBUG_ONLY = {"umma_microbench.cu"}                         # whole file is a debug facility
+DEBUG_VARIANT = {"umma_decoder.cu", "flow_attention_tc.cu"}  # contain #ifdef SBV2_DEBUG_HOOKS sections
+DEBUG_LIB = os.path.join(OUT_DIR, "libsbv2_b200_debug.so")
+
+
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
-    objs, jobs = [], []
-    for src in sources():
-        obj = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
+    os.makedirs(os.path.join(OBJ_DIR, "debug"), exist_ok=True)
+    objs, dbg_objs, jobs = [], [], []
+
+    def plan(src, obj, flags):
         stamp = obj + ".sha1"
-        dig = _digest(src)
-        objs.append(obj)
+        dig = _digest(src) + " " + " ".join(flags)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
-            continue
+            return
         extra = ["-x", "cu"] if src.endswith(".cpp") else []
-        jobs.append((src, obj, stamp, dig, [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + extra + ["-c", src, "-o", obj]))
+        jobs.append((src, obj, stamp, dig, [NVCC] + FLAGS + flags + (["-Xptxas", "-v"] if verbose else []) + extra + ["-c", src, "-o", obj]))
+
+    for src in sources():
+        base = os.path.basename(src)
+        obj = os.path.join(OBJ_DIR, base + ".o")
+        if base in DEBUG_ONLY or base in DEBUG_VARIANT:
+            dobj = os.path.join(OBJ_DIR, "debug", base + ".o")
+            plan(src, dobj, ["-DSBV2_DEBUG_HOOKS"])
+            dbg_objs.append(dobj)
+            if base in DEBUG_ONLY:
+                continue
+        else:
+            dbg_objs.append(obj)
+        plan(src, obj, [])
+        objs.append(obj)
 
     def run(job):
         src, obj, stamp, dig, cmd = job
@@ -68,11 +90,12 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
-    if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    for lib, lst in ((LIB, objs), (DEBUG_LIB, dbg_objs)):
+        if jobs or not os.path.exists(lib):
+            cmd = [NVCC, "-shared", "-o", lib] + lst + ["-lcudart", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

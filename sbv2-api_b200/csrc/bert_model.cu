@@ -304,6 +304,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
   ps.plane_stride = G.rows_tot * 8;
   const size_t R = size_t(G.rows_tot);
   M.h.ensure(size_t(n) * H * 4);
+  M.region_begin("bert");
   if (M.exact) {
     // ---- exact mode: fp32 row-major activations, two-term fp16 operand splits for every GEMM -------------------------
     M.x_emb.ensure(size_t(n) * H * 4);
@@ -350,6 +351,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
       }
     }
     launch_scatter_rows(ctx, M.outd.as<float>(), h, H, int(S), ps);
+    M.region_end("bert");
     M.debug["bert_h"] = DebugView{h, n, H, 4};
     return M.outd.as<float>();
   }
@@ -405,6 +407,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     }
   }
   launch_scatter_rows(ctx, M.outd.as<float>(), h, H, int(S), ps);
+  M.region_end("bert");
   M.debug["bert_h"] = DebugView{h, n, H, 4};
   return M.outd.as<float>();
 }

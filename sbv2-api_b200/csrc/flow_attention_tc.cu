@@ -455,6 +455,7 @@ void launch_flow_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __hal
 
 }  // namespace sbv2
 
+#ifdef SBV2_DEBUG_HOOKS  // only in libsbv2_b200_debug.so (build.py)
 // ---- test hook: timeline + timing of the attention kernel on a synthetic batch ------------------------------------
 #include "model.h"
 #include "umma_conv.h"
@@ -510,3 +511,4 @@ extern "C" int sbv2_debug_attn_trace(int T, int n_utt, int heads, long long* out
     if (out_trace) CUDA_CHECK(cudaMemcpy(out_trace, tr.p, 64 * 8 * 8, cudaMemcpyDeviceToHost));
   });
 }
+#endif  // SBV2_DEBUG_HOOKS

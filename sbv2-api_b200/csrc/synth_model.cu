@@ -84,6 +84,14 @@ struct FlowTC {
   ConvLayer pre, post;
   std::vector<FlowTCLayer> layers;
 };
+// WN residual-coupling layer on the tensor cores: in_layers with the tanh * sigmoid gate fused into the epilogue
+// (channels permuted per N block), res/skip 1x1 convs accumulating into the fp32 [x | skip] stream
+struct WnTC {
+  ConvLayer pre, post;
+  std::vector<ConvLayer> in_layers, res_skip;
+  ConvW cond_perm;    // cond_layer with every layer's 2H slice in the gated layers' channel order
+  int gate_half = 0;
+};
 
 struct HParams {
   int n_vocab = 0, n_tones = 0, n_lang = 0, hidden = 0, inter = 0, gin = 0, n_speakers = 0, bert_dim = 0, style_dim = 0;
@@ -127,6 +135,9 @@ struct SynthModel : sbv2_model {
   bool use_tc_attn = true;
   uint64_t fl_qkvp_gen = 0;  // DBuf::gen of the qkv buffer that was cleared last (tails must be finite for the TC attention)
   std::vector<std::vector<HostConv>> flow_host;  // consumed at create: per coupling [pre, post, (qkv, o, f1, f2) x L]
+  std::vector<std::vector<HostConv>> wn_host;    // consumed at create: per coupling [pre, post, cond, (in, res_skip) x L]
+  std::vector<WnTC> wn_tc;
+  bool use_tc_wn = false;
   DBuf fl_x0p, fl_hp, fl_qkvp, fl_ctxp, fl_f1p, fl_y32, fl_m32, fl_meta;
   PinnedBuf fl_pin;
   // text encoder / duration predictor convs on the tensor cores with two-term fp16 splits (~fp32 accuracy)
@@ -622,6 +633,20 @@ void load_weights(SynthModel& M, const OnnxModel& m) {
       M.flow_host.push_back(std::move(v));
     }
   }
+  if (!hp.transformer_flow) {
+    for (int i = 0; i < hp.n_flows; ++i) {
+      std::string p = "flow.flows." + std::to_string(2 * i);
+      std::vector<HostConv> v;
+      v.push_back(host_conv(p + ".pre", true));
+      v.push_back(host_conv(p + ".post", true));
+      v.push_back(host_conv(p + ".enc.cond_layer", true));
+      for (int l = 0; l < hp.wn_layers; ++l) {
+        v.push_back(host_conv(p + ".enc.in_layers." + std::to_string(l), true));
+        v.push_back(host_conv(p + ".enc.res_skip_layers." + std::to_string(l), true));
+      }
+      M.wn_host.push_back(std::move(v));
+    }
+  }
   {
     DecoderHostWeights& D = M.dec_host;
     D.pre = host_conv("dec.conv_pre", true);
@@ -847,6 +872,41 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
     }
   }
   M->flow_host.clear();
+  // WN variant on the tensor cores (SBV2_B200_FLOW=fp32 keeps the CUDA-core kernels): dilation_rate of the coupling
+  // layers' WN is 1 (oracle/vits.py ResidualCouplingLayer), so every in_layer is a plain k-tap "same" convolution
+  M->use_tc_wn = !M->hp.transformer_flow && !(fenv && std::string(fenv) == "fp32") && M->hp.hidden % 16 == 0 && (M->hp.inter / 2) % 16 == 0 &&
+                 M->hp.gin > 0;
+  if (M->use_tc_wn) {
+    const int H = M->hp.hidden, nl = M->hp.wn_layers;
+    for (auto& v : M->wn_host) {
+      WnTC w;
+      w.pre = make_conv1d_layer(M.get(), v[0], 1, 2, flow_nb);
+      w.post = make_conv1d_layer(M.get(), v[1], 1, 2, flow_nb);
+      std::vector<int> perm;
+      for (int l = 0; l < nl; ++l) {
+        w.in_layers.push_back(make_gated_conv1d_layer(M.get(), v[3 + 2 * l], 1, 2, &w.gate_half, &perm));
+        w.res_skip.push_back(make_conv1d_layer(M.get(), v[4 + 2 * l], 1, 2, flow_nb));
+      }
+      // cond_layer (gin -> 2H * nl, k = 1) with each layer's slice permuted like the gated conv's output channels
+      const HostConv& c = v[2];
+      if (c.d0 != 2 * H * nl || c.k != 1) fail(SBV2_ERR_UNSUPPORTED, "WN cond_layer shape does not match the in_layers");
+      std::vector<float> wp(size_t(c.d1) * c.d0), bp(size_t(c.d0));
+      for (int l = 0; l < nl; ++l)
+        for (int i = 0; i < 2 * H; ++i) {
+          const int src = l * 2 * H + perm[size_t(i)], dst = l * 2 * H + i;
+          bp[size_t(dst)] = c.b[size_t(src)];
+          for (int ci = 0; ci < c.d1; ++ci) wp[size_t(ci) * c.d0 + dst] = c.w[size_t(src) * c.d1 + ci];  // [k=1][Cin][Cout]
+        }
+      w.cond_perm.w = M->upload_f32(wp);
+      w.cond_perm.b = M->upload_f32(bp);
+      w.cond_perm.cin = c.d1;
+      w.cond_perm.cout = c.d0;
+      w.cond_perm.k = 1;
+      M->wn_tc.push_back(std::move(w));
+    }
+    for (DBuf* b : {&M->fl_x0p, &M->fl_hp, &M->fl_qkvp, &M->fl_ctxp, &M->fl_f1p, &M->fl_y32, &M->fl_m32, &M->fl_meta}) b->stream = M->stream;
+  }
+  M->wn_host.clear();
   // SBV2_B200_TEXT=fp32 keeps the text encoder / duration predictor convs on the CUDA-core fp32 kernel; =split3 uses
   // three fp16 terms per operand.  Measured against the oracle both splits give the same error (enc_x 1e-5 relative,
   // 3x the CUDA-core kernel's): the tensor core's fp32 accumulation, not the operand split, sets it.
@@ -1485,6 +1545,75 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
         launch_ln_planar(ctx, hf, hp16, y32, Lw.n2.g, Lw.n2.b, 1e-5f, H, ps);
       }
       umma(T.post, hp16, nullptr, m32, ACT_NONE);
+      launch_coupling_sub_planar(ctx, zc, m32, C, ps);
+    }
+  } else if (M.use_tc_wn) {
+    // WN coupling layers on the tensor cores: fp16 planar operands, fp32 planar [x | skip] stream
+    std::vector<int> muls(1, 1);
+    BatchGeom bg = build_geoms(&M, M.fl_meta, M.fl_pin, b->ystart, b->ylen, muls, nullptr, /*pin_idle=*/true);
+    const Geom& G = bg.g[0];
+    PlanarSegs ps;
+    ps.start = bg.d_ystart;
+    ps.pstart = G.d_pstart;
+    ps.len = G.d_len;
+    ps.order = bg.d_order;
+    ps.n = B;
+    ps.max_len = ymax;
+    ps.plane_stride = G.rows_tot * 8;
+    const int nl = hp.wn_layers;
+    M.fl_x0p.ensure(size_t(G.rows_tot) * (C / 2) * 2);
+    M.fl_hp.ensure(size_t(G.rows_tot) * H * 2);
+    M.fl_ctxp.ensure(size_t(G.rows_tot) * H * 2);
+    M.fl_y32.ensure(size_t(G.rows_tot) * 2 * H * 4);
+    M.fl_m32.ensure(size_t(G.rows_tot) * (C / 2) * 4);
+    __half* x0p = M.fl_x0p.as<__half>();
+    __half* xp = M.fl_hp.as<__half>();
+    __half* actp = M.fl_ctxp.as<__half>();
+    float* acc = M.fl_y32.as<float>();                            // planes [0, H/8): x, [H/8, 2H/8): skip
+    float* acc_skip = acc + size_t(H / 8) * size_t(ps.plane_stride);
+    float* m32 = M.fl_m32.as<float>();
+    launch_zero_gaps(ctx, xp, H, G, B);
+    launch_zero_gaps(ctx, actp, H, G, B);
+    float* gcond = ens(W_STYLE, size_t(B) * 2 * H * nl);
+    for (int i = hp.n_flows - 1; i >= 0; --i) {
+      const WnTC& T = M.wn_tc[size_t(i)];
+      launch_flip_channels(ctx, zn, zc, C, ny);
+      std::swap(zc, zn);
+      launch_to_planar(ctx, x0p, zc, C, C / 2, bg.d_ystart, G, B, ACT_NONE);
+      CUDA_CHECK(cudaMemsetAsync(acc_skip, 0, size_t(H / 8) * size_t(ps.plane_stride) * 4, M.stream));  // output = zeros_like(x)
+      {
+        ConvCall c;
+        c.in = x0p;
+        c.accum = acc;
+        c.accum_mode = UACC_SET;
+        launch_umma(ctx, T.pre, G, G, c, B);
+      }
+      F.conv(T.cond_perm, g, hp.gin, gcond, 2 * H * nl, bseg);
+      for (int l = 0; l < nl; ++l) {
+        launch_planar_cast(ctx, xp, acc, H, G, B);
+        {
+          ConvCall c;
+          c.in = xp;
+          c.out = actp;
+          c.gate_half = T.gate_half;
+          c.bias_utt = gcond + size_t(l) * 2 * H;
+          c.bias_utt_ld = 2 * H * nl;
+          launch_umma(ctx, T.in_layers[size_t(l)], G, G, c, B);
+        }
+        ConvCall c;
+        c.in = actp;
+        c.accum = l == nl - 1 ? acc_skip : acc;  // last layer: all of res_skip goes to the output sum
+        c.accum_mode = UACC_ADD;
+        launch_umma(ctx, T.res_skip[size_t(l)], G, G, c, B);
+      }
+      launch_planar_cast(ctx, xp, acc_skip, H, G, B);
+      {
+        ConvCall c;
+        c.in = xp;
+        c.accum = m32;
+        c.accum_mode = UACC_SET;
+        launch_umma(ctx, T.post, G, G, c, B);
+      }
       launch_coupling_sub_planar(ctx, zc, m32, C, ps);
     }
   } else

@@ -54,7 +54,9 @@ struct UmmaConvArgs {
   float* accum;                // fp32 planar, geometry of `out`
   const __half* w;             // packed [nblk][kc][tap][KC/8][NB][8]
   const float* bias;           // [n_nblk*NB]
-  const float* bias_utt;       // [n_utt][n_nblk*NB] or null
+  const float* bias_utt;       // [n_utt][bias_utt_ld] or null
+  int bias_utt_ld;
+  int gate_half;               // > 0: WaveNet gate epilogue (N block = [tanh half | sigmoid half])
   const int* tile_prefix;      // [n_utt+1]
   const int* pstart_in;        // [n_utt] first planar row of each utterance in `in`
   const int* pstart_out;
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         // happen after the last read)
         for (int i = etid; i < p.nb; i += NUM_EPI_WARPS * 32) {
           float v = p.bias[(size_t)ti.nblk * p.nb + i];
-          if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.n_nblk * p.nb + (size_t)ti.nblk * p.nb + i];
+          if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.bias_utt_ld + (size_t)ti.nblk * p.nb + i];
           bias[i] = v;
         }
         asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");
@@ -312,6 +314,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       tc_fence_after();
       if (threadIdx.x == 64) TRACE(5, it);
       const uint32_t tmem_acc = tmem_base + buf * acc_cols;
+      if (p.gate_half > 0) {
+        const int per_acc = p.gate_half / 16;
+        for (int sub = part; sub < p.mt * per_acc; sub += NUM_EPI_WARPS / 4) {
+          const int a = sub / per_acc;
+          const int c0 = (sub - a * per_acc) * 16;
+          const int t = ti.t0 + a * 128 + wq * 32 + lane;
+          const long long orow = (long long)p.pstart_out[ti.b] + t;
+          const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
+          epilogue_gate(p, taddr, taddr + (uint32_t)p.gate_half, t < ti.len, orow, ti.nblk * p.gate_half + c0, bias + c0,
+                        bias + p.gate_half + c0);
+        }
+      } else
       for (int sub = part; sub < n_sub; sub += NUM_EPI_WARPS / 4) {
         const int a = sub / items_per_acc;
         const int c0 = (sub - a * items_per_acc) * nch;
@@ -394,6 +408,23 @@ __global__ void split_planar_kernel(__half* out, long long plane_stride, const f
     }
   }
 }
+// planar fp32 -> planar fp16, utterance rows only: one 16-byte item (8 channels of one row) per thread; consecutive
+// threads take consecutive rows of a plane, so a warp reads 1 KB and writes 512 B contiguous
+__global__ void planar_cast_kernel(__half* out, const float* in, long long plane_stride, const int* pstart, const int* len) {
+  const int b = blockIdx.z, pl = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len[b]) return;
+  const size_t o = (size_t)pl * plane_stride + (size_t)(pstart[b] + t) * 8;
+  const float4 x0 = *reinterpret_cast<const float4*>(in + o), x1 = *reinterpret_cast<const float4*>(in + o + 4);
+  uint4 v;
+  __half2* vh = reinterpret_cast<__half2*>(&v);
+  vh[0] = __floats2half2_rn(x0.x, x0.y);
+  vh[1] = __floats2half2_rn(x0.z, x0.w);
+  vh[2] = __floats2half2_rn(x1.x, x1.y);
+  vh[3] = __floats2half2_rn(x1.z, x1.w);
+  *reinterpret_cast<uint4*>(out + o) = v;
+}
+
 // packed fp32 [rows, in_ld] (utterance b at rows start[b]..) -> planar fp16 with gaps
 __global__ void to_planar_kernel(__half* out, long long plane_stride, const float* in, int in_ld, int C, const int* start,
                                  const int* pstart, const int* len, int act) {
@@ -578,6 +609,34 @@ ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int m
                     [=](int, int co, int ci, int tap) { return w[(size_t(co) * cin + ci) * k + tap]; }, mt_pref, nb_max);
 }
 
+ConvLayer make_gated_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int* gate_half, std::vector<int>* perm) {
+  const int H = c.d0 / 2;
+  if (c.d0 % 2 != 0 || H % 16 != 0) fail(SBV2_ERR_UNSUPPORTED, "gated conv: output channels must be 2 * (multiple of 16)");
+  int hb = 0;
+  for (int v = std::min(H, 128) / 16 * 16; v >= 16; v -= 16)
+    if (H % v == 0) {
+      hb = v;
+      break;
+    }
+  if (hb == 0) fail(SBV2_ERR_UNSUPPORTED, "gated conv: no N block divides the hidden size");
+  perm->resize(size_t(2) * H);
+  for (int j = 0; j < H / hb; ++j)
+    for (int i = 0; i < hb; ++i) {
+      (*perm)[size_t(j) * 2 * hb + i] = j * hb + i;           // tanh half
+      (*perm)[size_t(j) * 2 * hb + hb + i] = H + j * hb + i;  // sigmoid half
+    }
+  HostConv p = c;
+  const size_t per_out = size_t(c.d1) * c.k;
+  for (int i = 0; i < 2 * H; ++i) {
+    std::copy(c.w.begin() + size_t((*perm)[size_t(i)]) * per_out, c.w.begin() + size_t((*perm)[size_t(i)] + 1) * per_out, p.w.begin() + size_t(i) * per_out);
+    if (!c.b.empty()) p.b[size_t(i)] = c.b[size_t((*perm)[size_t(i)])];
+  }
+  ConvLayer L = make_conv1d_layer(owner, p, dil, mt_pref, 2 * hb);
+  if (L.nb != 2 * hb) fail(SBV2_ERR_INTERNAL, "gated conv: unexpected N block");
+  *gate_half = hb;
+  return L;
+}
+
 ConvLayer make_split_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int terms, int nb_max) {
   // [Cout][n*Cin][k]: terms = 2: input planes [h0 | h1 | h0] meet weights [w0 | w0 | w1];
   // terms = 3: [h0 | h1 | h2 | h0 | h1 | h0] meet [w0 | w0 | w0 | w1 | w1 | w2]
@@ -652,6 +711,10 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.w = L.w;
   a.bias = L.bias;
   a.bias_utt = c.bias_utt;
+  a.bias_utt_ld = c.bias_utt_ld > 0 ? c.bias_utt_ld : L.n_nblk * L.nb;
+  a.gate_half = c.gate_half;
+  if (c.gate_half > 0 && (2 * c.gate_half != L.nb || c.residual || c.accum || c.rm_out || !c.out || c.out_mul != 1 || L.n_groups != 1))
+    fail(SBV2_ERR_INTERNAL, "gated conv: unsupported epilogue combination");
   const int slot = mt_slot(L.mt);
   a.tile_prefix = gi.d_prefix[slot];
   a.pstart_in = gi.d_pstart;
@@ -808,6 +871,14 @@ void launch_to_planar(const LaunchCtx& ctx, __half* out, const float* in, int in
   dim3 block(std::min(32, C / 8), 8);
   dim3 grid((g.max_len + 7) / 8, n_utt);
   to_planar_kernel<<<grid, block, 0, ctx.stream>>>(out, g.rows_tot * 8, in, in_ld, C, d_start, g.d_pstart, g.d_len, act);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+void launch_planar_cast(const LaunchCtx& ctx, __half* out, const float* in, int C, const Geom& g, int n_utt) {
+  if (g.max_len <= 0 || n_utt <= 0) return;
+  dim3 grid((g.max_len + 255) / 256, C / 8, n_utt);
+  planar_cast_kernel<<<grid, 256, 0, ctx.stream>>>(out, in, g.rows_tot * 8, g.d_pstart, g.d_len);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -57,6 +57,11 @@ struct ConvLayer {
 // item streams its N block's weights once, so few-row problems (flow, text encoder) want nb_max = 128 and mt_pref = 2:
 // twice the rows per weight byte read from L2.
 ConvLayer make_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int nb_max = 256);
+// Conv1d(C -> 2H) of a WaveNet layer whose output feeds tanh(first H) * sigmoid(last H): output channels are permuted so
+// that every N block of 2 * hb channels holds [tanh j*hb .. | sigmoid j*hb ..] and the gate is fused into the epilogue
+// (ConvCall::gate_half = *gate_half).  perm (size 2H) receives the permutation: packed channel i = original perm[i]
+// (apply it to the conditioning vector that goes in as ConvCall::bias_utt).
+ConvLayer make_gated_conv1d_layer(sbv2_model* owner, const HostConv& c, int dil, int mt_pref, int* gate_half, std::vector<int>* perm);
 // ConvTranspose1d weight [Cin][Cout][k], stride u, pad (k-u)/2 as u polyphase groups of k/u taps (one launch;
 // launch with ConvCall::out_mul = u)
 ConvLayer make_upsample_layer(sbv2_model* owner, const HostConv& c, int u, int mt_pref);
@@ -114,6 +119,10 @@ struct ConvCall {
   int act_out = ACT_NONE;         // ACT_NONE / ACT_RELU / ACT_LRELU / ACT_LRELU01 / ACT_GELU
   bool act_on_accum = false;      // apply act_out before the fp32 accumulate/store instead of on the fp16 output
   const float* bias_utt = nullptr;
+  int bias_utt_ld = 0;            // floats between consecutive utterances of bias_utt (0: the layer's cout)
+  // WaveNet gate (make_gated_conv1d_layer): every N block holds [tanh half | sigmoid half] of gate_half channels each;
+  // out (planar fp16, cout / 2 channels) = tanh(.) * sigmoid(.); no residual / accumulate / row-major output
+  int gate_half = 0;
   int out_mul = 1, out_off = 0;
   // fp32 row-major output [packed rows, rm_ld] instead of the planar ones (text encoder): packed row = rm_start[b] + t;
   // act_out ACT_NONE / ACT_RELU only
@@ -123,6 +132,8 @@ struct ConvCall {
 };
 void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt);
 void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, int n_utt);
+// planar fp32 -> planar fp16 over the first C channels (utterance rows only; 32-byte loads, 16-byte stores)
+void launch_planar_cast(const LaunchCtx& ctx, __half* out, const float* in, int C, const Geom& g, int n_utt);
 // packed fp32 [rows, in_ld] (first C columns) -> planar fp16
 void launch_to_planar(const LaunchCtx& ctx, __half* out, const float* in, int in_ld, int C, const int* d_start, const Geom& g,
                       int n_utt, int act);

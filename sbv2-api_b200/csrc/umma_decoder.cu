@@ -375,6 +375,7 @@ void umma_decoder_run(UmmaDecoder* D, sbv2_model* owner, const float* z, const f
 
 }  // namespace sbv2
 
+#ifdef SBV2_DEBUG_HOOKS  // kernel unit-test / tracing entry points: only in libsbv2_b200_debug.so (build.py)
 // ---- test hook: one convolution through both the fp32 kernel and the tensor-core kernel -------------------
 extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const float* w, const float* bias, int cout, int k,
                                        int dil, int mt_pref, int with_residual, float* out_umma, float* out_ref) {
@@ -642,3 +643,4 @@ extern "C" int sbv2_debug_pair_compare(const float* x, const int* lens, int n_ut
     }
   });
 }
+#endif  // SBV2_DEBUG_HOOKS

@@ -242,6 +242,35 @@ __device__ __forceinline__ void epilogue_item(const Args& p, uint32_t taddr, boo
   }
 }
 
+// WaveNet gate epilogue (WN coupling layers, oracle/vits.py WN.forward): the N block holds [tanh half | sigmoid half];
+// 16 output channels of one row = tanh(a_t + b_t) * sigmoid(a_s + b_s), stored as planar fp16.  bias_* already include the
+// per-utterance conditioning slice cond_layer(g).
+template <class Args>
+__device__ __forceinline__ void epilogue_gate(const Args& p, uint32_t taddr_t, uint32_t taddr_s, bool valid, long long orow,
+                                              int co_global, const float* bias_t, const float* bias_s) {
+  uint32_t vt[16], vs[16];
+  tc_ld16(taddr_t, vt);
+  tc_ld16(taddr_s, vs);
+  tc_wait_ld();
+  if (!valid) return;
+  const long long eoff0 = ((long long)co_global >> 3) * p.out_plane_stride + orow * 8;
+#pragma unroll
+  for (int pl = 0; pl < 2; ++pl) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = __uint_as_float(vt[8 * pl + e]) + bias_t[8 * pl + e];
+      const float b = __uint_as_float(vs[8 * pl + e]) + bias_s[8 * pl + e];
+      f[e] = tanhf(a) * (1.0f / (1.0f + __expf(-b)));
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p.out + eoff0 + pl * p.out_plane_stride) = o;
+  }
+}
+
 // fp32 row-major epilogue of 16 accumulator columns of one row: out[row][co0 .. co0+15] = act(acc + bias)
 template <class Args>
 __device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, bool valid, long long rm_row, int co0_global,

@@ -126,6 +126,21 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTED_SYMBOLS = sorted(lib._sbv2_signatures)
 
+_debug_lib = None
+
+
+def debug_lib() -> C.CDLL:
+    """libsbv2_b200_debug.so: the same objects plus the kernel unit-test / tracing hooks (sbv2_debug_conv_compare,
+    _conv_trace, _pair_compare, _attn_trace, _mma_rate*), which the product library does not export."""
+    global _debug_lib
+    if _debug_lib is None:
+        path = os.path.join(_HERE, "libsbv2_b200_debug.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build it with `python sbv2-api_b200/build.py`")
+        _debug_lib = C.CDLL(path)
+        _debug_lib.sbv2_last_error.restype = C.c_char_p
+    return _debug_lib
+
 
 def _check(status: int) -> None:
     if status != OK:

@@ -174,3 +174,151 @@ def test_synthesize_from_tokens_matches_host_expansion(S):
         synth.synthesize_from_tokens(bert, ids, mask, word2ph[::-1].copy() * 0 + 1, x, 0, tone, lang, style, 0.2, 1.0, 0.677, 0.8)
     with pytest.raises(S.Sbv2Error):
         bert.synthesize_from_tokens(synth, ids, mask, word2ph, x, 0, tone, lang, style, 0.2, 1.0, 0.677, 0.8)
+
+
+def _token_setup(S):
+    from sbv2_b200 import assets
+    hp = ov.tiny_hparams(bert_dim=128)
+    oracle, onnx = util.synth_assets(hp, seed=0)
+    cfg = od.tiny_config()
+    bert_onnx = assets.deberta_onnx(od.state_dict_numpy(od.build_model(cfg, seed=1)))
+    return hp, oracle, onnx, cfg, bert_onnx
+
+
+def _sentence(hp, cfg, t_x, seed):
+    w2p = util.word2ph_for(t_x, seed)
+    ids = np.random.default_rng(seed).integers(3, cfg.vocab_size, size=w2p.size).astype(np.int64)
+    x, tone, lang, _, style = ov.synthetic_inputs(hp, t_x, seed=seed)
+    return dict(token_ids=ids, word2ph=w2p, x_tst=x[0].numpy(), tones=tone[0].numpy(), lang_ids=lang[0].numpy(), style_vec=style[0].numpy())
+
+
+def test_synthesize_from_tokens_batch_matches_singles_and_writes_pauses(S):
+    """sbv2_synthesize_from_tokens_batch: one DeBERTa batch + one synthesizer batch for the sentences of a request
+    (SURVEY §8f row 2), pauses written on the device.  sdp_ratio = 0 so that durations do not depend on the noise: every
+    sentence must have exactly the length of its own sbv2_synthesize_from_tokens call, the pauses must be exact zeros, and
+    with batch 1 the audio is bit-identical to the single call (same generator state)."""
+    hp, oracle, onnx, cfg, bert_onnx = _token_setup(S)
+    synth, bert = S.Model(onnx, bert=False), S.Model(bert_onnx, bert=True)
+    sents = [_sentence(hp, cfg, t, 40 + i) for i, t in enumerate((19, 7, 33, 11))]
+    singles = []
+    for s in sents:
+        synth.seed(5)
+        singles.append(synth.synthesize_from_tokens(bert, s["token_ids"], np.ones_like(s["token_ids"]), s["word2ph"], s["x_tst"], 0,
+                                                    s["tones"], s["lang_ids"], s["style_vec"], 0.0, 1.0, 0.677, 0.8))
+    pauses = [22050, 0, 22050, 100]
+    synth.seed(5)
+    audio, ns = synth.synthesize_from_tokens_batch(bert, sents, pauses)
+    assert [int(n) for n in ns] == [a.size for a in singles]
+    assert audio.size == int(ns.sum()) + sum(pauses)
+    off = 0
+    for i, n in enumerate(ns):
+        seg = audio[off:off + n]
+        assert np.isfinite(seg).all() and np.abs(seg).max() > 1e-4
+        off += int(n)
+        assert not audio[off:off + pauses[i]].any()      # silence written on the device
+        off += pauses[i]
+    synth.seed(5)
+    one, n1 = synth.synthesize_from_tokens_batch(bert, sents[:1], [7])
+    assert np.array_equal(one[:n1[0]], singles[0]) and not one[n1[0]:].any() and one.size == n1[0] + 7
+    with pytest.raises(S.Sbv2Error):
+        synth.synthesize_from_tokens_batch(bert, [dict(sents[0], word2ph=sents[0]["word2ph"] + 1)])
+
+
+def test_easy_synthesize_tokens_matches_feature_path_lengths(S):
+    hp, oracle, onnx, cfg, bert_onnx = _token_setup(S)
+    from sbv2_b200 import assets
+    sv = np.random.default_rng(3).standard_normal((2, 256)).astype(np.float32) * 0.1
+    h = S.TTSModelHolder(bert_onnx, b"")
+    h.load("m", assets.style_json(sv), onnx)
+    sents = [_sentence(hp, cfg, t, 60 + i) for i, t in enumerate((15, 9))]
+    lines_tok = [dict(token_ids=s["token_ids"], word2ph=s["word2ph"], phones=s["x_tst"], tones=s["tones"], lang_ids=s["lang_ids"]) for s in sents]
+    # the reference-shaped path: bert_features per line on the host, then easy_synthesize
+    lines_feat = []
+    for s in sents:
+        f = h.bert_features(s["token_ids"], np.ones_like(s["token_ids"]), s["word2ph"])
+        assert f.shape == (128, s["x_tst"].size)     # rows follow the holder's DeBERTa hidden size, not a constant 1024
+        lines_feat.append(dict(bert=f, phones=s["x_tst"], tones=s["tones"], lang_ids=s["lang_ids"]))
+    a = wav_samples(h.easy_synthesize("m", [lines_feat[0], None, lines_feat[1]], 1, 0))
+    b = wav_samples(h.easy_synthesize_tokens("m", [lines_tok[0], None, lines_tok[1]], 1, 0))
+    assert a.size == b.size                              # same durations (sdp_ratio 0), same pause layout
+    n0 = (a.size - 22050 - 0) // 1
+    # locate the pause: identical position in both
+    za = np.flatnonzero(np.convolve((a == 0).astype(np.int32), np.ones(22050, np.int32), "valid") == 22050)
+    zb = np.flatnonzero(np.convolve((b == 0).astype(np.int32), np.ones(22050, np.int32), "valid") == 22050)
+    assert za.size and zb.size and za[0] == zb[0]
+    with pytest.raises(S.Sbv2Error) as e:
+        h.easy_synthesize_tokens("m", [None, None], 1, 0)  # only empty lines: concatenate of nothing (tts.rs:321-324)
+    assert e.value.status == S.ERR_INVALID_ARGUMENT
+    with pytest.raises(S.Sbv2Error) as e:
+        h.easy_synthesize("m", [None], 1, 0)
+    assert e.value.status == S.ERR_INVALID_ARGUMENT
+    h.close()
+
+
+def test_pinned_inputs_give_identical_results(S):
+    """Inputs in page-locked memory (sbv2_alloc_pinned) are copied by the DMA engine in place; results are bit-identical
+    to the staged path."""
+    hp = ov.tiny_hparams()
+    oracle, onnx = util.synth_assets(hp, seed=0)
+    model = S.Model(onnx, bert=False)
+    us = [util.to_api(util.make_utterance(hp, t, seed=70 + i, sdp_ratio=0.3)) for i, t in enumerate((23, 5, 41))]
+    a = model.synthesize_batch(us)
+    pinned = [dict(u, bert=S.pinned_copy(u["bert"])) for u in us]
+    b = model.synthesize_batch(pinned)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    db = S.DeviceBatch(model, pinned)
+    for p in pinned:
+        p["bert"][...] = 0                               # upload has finished with the caller's buffers when it returns
+    db.run()
+    for x, y in zip(a, db.download()):
+        assert np.array_equal(x, y)
+
+
+def test_anonymous_exports_load_and_match(S):
+    """Models written the way TorchScript + onnxsim leave them (anonymous transposed Linear weights, anonymous
+    weight-normed convs; convert_model.py:115-156, convert_deberta.py:36-52) load through the structural binder and give
+    bit-identical results; a Linear whose weight is missing is a load error, not a silently skipped layer."""
+    from sbv2_b200 import assets
+    for flow in (True, False):
+        hp = ov.tiny_hparams(use_transformer_flow=flow)
+        sd = ov.state_dict_numpy(ov.build_model(hp, seed=2))
+        named = S.Model(assets.synth_onnx(sd, hp.upsample_rates, hp.resblock_dilation_sizes), bert=False)
+        anon = S.Model(assets.synth_onnx(sd, hp.upsample_rates, hp.resblock_dilation_sizes, anonymize_weight_norm=True,
+                                         anonymize_linear=True), bert=False)
+        assert anon.describe()["structural_binding"] is True
+        u = util.make_utterance(hp, 27, seed=9, sdp_ratio=0.3, sid=1)
+        args = (u["bert"][0].numpy(), u["x"][0].numpy(), u["sid"], u["tone"][0].numpy(), u["lang"][0].numpy(), u["style"][0].numpy(),
+                u["sdp_ratio"], u["length_scale"], u["noise_scale"], u["noise_scale_w"], u["noise_sdp"][0].numpy(), u["noise_zp"][0].numpy())
+        a, b = named.synthesize_with_noise(*args), anon.synthesize_with_noise(*args)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    broken = {k: v for k, v in sd.items() if k != "enc_p.encoder.spk_emb_linear.weight"}
+    with pytest.raises(S.Sbv2Error) as e:
+        S.Model(assets.synth_onnx(broken, hp.upsample_rates, hp.resblock_dilation_sizes), bert=False)
+    assert e.value.status == S.ERR_UNSUPPORTED and "spk_emb_linear" in e.value.message
+    cfg = od.tiny_config()
+    bsd = od.state_dict_numpy(od.build_model(cfg, seed=1))
+    bn, ba = S.Model(assets.deberta_onnx(bsd), bert=True), S.Model(assets.deberta_onnx(bsd, anonymize_linear=True), bert=True)
+    assert ba.describe()["structural_binding"] is True and bn.describe()["structural_binding"] is False
+    ids = np.arange(3, 40, dtype=np.int64)
+    assert np.array_equal(bn.predict(ids, np.ones_like(ids)), ba.predict(ids, np.ones_like(ids)))
+    with pytest.raises(S.Sbv2Error) as e:
+        S.Model(assets.deberta_onnx({k: v for k, v in bsd.items() if k != "deberta.encoder.layer.0.output.dense.weight"}), bert=True)
+    assert e.value.status == S.ERR_UNSUPPORTED
+
+
+def test_second_device_in_one_process(S):
+    """Function attributes (dynamic shared memory opt-in) are per device: a model on device 1 must work after device 0
+    was used in the same process.  Needs two GPUs; on a one-GPU box only the error path is checked."""
+    hp = ov.tiny_hparams()
+    oracle, onnx = util.synth_assets(hp, seed=0)
+    u = util.to_api(util.make_utterance(hp, 23, seed=12, sdp_ratio=0.4))
+    m0 = S.Model(onnx, bert=False, device=0)
+    a = m0.synthesize_batch([u])[0]
+    if S.device_count() < 2:
+        with pytest.raises(S.Sbv2Error):
+            S.Model(onnx, bert=False, device=1)
+        return
+    m1 = S.Model(onnx, bert=False, device=1)
+    b = m1.synthesize_batch([u])[0]
+    assert np.array_equal(a, b)

@@ -25,7 +25,7 @@ def S(lib_built):
     import sbv2_b200
     if sbv2_b200.device_count() < 1:
         pytest.fail("GPU tests selected but no B200 is visible: " + sbv2_b200.lib.sbv2_last_error().decode())
-    fn = sbv2_b200.lib.sbv2_debug_pair_compare
+    fn = sbv2_b200.debug_lib().sbv2_debug_pair_compare   # unit-test hooks live in libsbv2_b200_debug.so only
     fn.restype = C.c_int
     fn.argtypes = [pf, pi, C.c_int, C.c_int, C.c_int, C.c_int, pf, pf, pf, pf, C.c_int, C.c_int, pf, pf, pf, pi, C.POINTER(C.c_longlong)]
     return sbv2_b200
@@ -66,11 +66,11 @@ def test_fused_resblock_pair(S, c, k, dil, mrf):
     unfused = np.zeros((tot, c), np.float32)
     ms = np.zeros(2, np.float32)
     cfg = np.zeros(8, np.int32)
-    st = S.lib.sbv2_debug_pair_compare(x.ctypes.data_as(pf), lens.ctypes.data_as(pi), len(lens), c, k, dil, w1.ctypes.data_as(pf),
+    st = S.debug_lib().sbv2_debug_pair_compare(x.ctypes.data_as(pf), lens.ctypes.data_as(pi), len(lens), c, k, dil, w1.ctypes.data_as(pf),
                                        b1.ctypes.data_as(pf), w2.ctypes.data_as(pf), b2.ctypes.data_as(pf), mrf, 0,
                                        fused.ctypes.data_as(pf), unfused.ctypes.data_as(pf), ms.ctypes.data_as(pf),
                                        cfg.ctypes.data_as(pi), None)
-    assert st == 0, S.lib.sbv2_last_error().decode()
+    assert st == 0, S.debug_lib().sbv2_last_error().decode()
     assert np.array_equal(fused, unfused), "fused pair differs from the two unfused tensor-core convs"
     # numpy evaluation with the kernels' rounding points: stored activations and the intermediate are fp16
     y = f16(lrelu(x))

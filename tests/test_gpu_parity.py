@@ -178,11 +178,32 @@ def test_wn_flow_variant(S):
     oracle, onnx = util.synth_assets(hp, seed=3)
     model = S.Model(onnx, bert=False)
     assert model.describe()["use_transformer_flow"] is False and model.describe()["wn_layers"] == 4
-    u = util.make_utterance(hp, 45, seed=5, sdp_ratio=0.3)
-    ref, inter = util.oracle_run(oracle, u)
-    audio, dur, f2p = run_gpu(model, u)
-    check_alignment(oracle, u, inter, dur, f2p)
-    assert np.abs(audio - ref[0, 0].numpy()).max() <= WAVE_TOL
+    for t_x, seed in ((45, 5), (241, 6)):
+        u = util.make_utterance(hp, t_x, seed=seed, sdp_ratio=0.3)
+        ref, inter = util.oracle_run(oracle, u)
+        audio, dur, f2p = run_gpu(model, u)
+        check_alignment(oracle, u, inter, dur, f2p)
+        err = np.abs(audio - ref[0, 0].numpy()).max()
+        assert err <= WAVE_TOL, f"WN flow, T_x={t_x}: waveform max-abs {err:.3e}"
+        # the flow output itself: z after the four coupling layers, against the oracle's
+        z = model.debug_fetch("z")
+        zr = inter["z"][0].numpy().T
+        assert z.shape == zr.shape and np.abs(z - zr).max() <= 2e-2 and np.linalg.norm(z - zr) / np.linalg.norm(zr) <= 2e-3
+    # tensor-core WN (gate fused into the in_layer conv's epilogue) vs the CUDA-core fp32 kernels of the same model, ragged batch
+    os.environ["SBV2_B200_FLOW"] = "fp32"
+    try:
+        simt = S.Model(onnx, bert=False)
+    finally:
+        del os.environ["SBV2_B200_FLOW"]
+    us = [util.to_api(util.make_utterance(hp, t, seed=40 + i, sdp_ratio=0.0)) for i, t in enumerate((33, 1, 130, 77))]
+    a, da, fa = model.synthesize_batch(us, want_alignment=True)
+    b, db_, fb = simt.synthesize_batch(us, want_alignment=True)
+    for i in range(len(us)):
+        assert np.array_equal(da[i], db_[i]) and np.array_equal(fa[i], fb[i])
+        assert np.abs(a[i] - b[i]).max() <= WAVE_TOL
+    singles = [model.synthesize_batch([u])[0] for u in us]
+    for i in range(len(us)):
+        assert np.array_equal(a[i], singles[i])          # batched == batch-1, bit for bit
 
 
 def test_structural_binding_of_anonymous_weights(S):

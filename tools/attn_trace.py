@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sbv2-api_b200"))
 import sbv2_b200 as S  # noqa: E402
 
-fn = S.lib.sbv2_debug_attn_trace
+fn = S.debug_lib().sbv2_debug_attn_trace
 fn.restype = C.c_int
 fn.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
 
@@ -19,7 +19,7 @@ def run(T, n, heads, show=True):
     ms = C.c_float()
     st = fn(T, n, heads, tr.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(ms))
     if st:
-        print("ERROR", S.lib.sbv2_last_error().decode())
+        print("ERROR", S.debug_lib().sbv2_last_error().decode())
         return
     nkt = (T + 127) // 128
     flops = 4.0 * T * T * 96 * heads * n * 1.5  # pass A recomputes QK^T

@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sbv2-api_b200"))
 import sbv2_b200 as S  # noqa: E402
 
-fn = S.lib.sbv2_debug_conv_trace
+fn = S.debug_lib().sbv2_debug_conv_trace
 fn.restype = C.c_int
 fn.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int,
                C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -22,7 +22,7 @@ def run(T, cin, cout, k, dil, res=0, acc=0, mt=16, show=True):
     cfg = (C.c_int * 8)()
     st = fn(T, cin, cout, k, dil, mt, res, acc, tr.ctypes.data_as(C.POINTER(C.c_longlong)), nb, C.byref(ms), cfg)
     if st != 0:
-        print("ERROR", S.lib.sbv2_last_error().decode())
+        print("ERROR", S.debug_lib().sbv2_last_error().decode())
         return
     mtv, nbv, aslots, nst, sps, resid, smem, nkc = list(cfg)
     flops = 2.0 * T * cin * cout * k

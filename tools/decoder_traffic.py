@@ -1,6 +1,18 @@
 """Sums ncu dram bytes + durations over the decoder's umma_conv launches of one bench step.
 Usage: python tools/decoder_traffic.py gpurun_out/traffic.csv  -> writes profiles/decoder_traffic.json"""
-import csv, json, os, sys
+import csv, hashlib, json, os, sys
+
+
+def sources_digest():
+    """Same digest as bench.py: the traffic figure is only valid for the kernel sources it was measured on."""
+    h = hashlib.sha1()
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sbv2-api_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith("umma_") and f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 per = {}
 order = []
@@ -24,7 +36,7 @@ dec = [per[k] for i, k in enumerate(order) if i > last_tp and ("umma_conv" in pe
 rd = sum(k.get("dram__bytes_read.sum", 0) for k in dec)
 wr = sum(k.get("dram__bytes_write.sum", 0) for k in dec)
 us = sum(k.get("us", 0) for k in dec)
-out = {"launches": len(dec), "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr, "dram_bytes_per_step": rd + wr,
+out = {"sources_sha1": sources_digest(), "launches": len(dec), "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr, "dram_bytes_per_step": rd + wr,
        "kernel_time_us_under_ncu": us, "note": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum, cold-cache serialised replays; bench workload (32 x ~8 s)"}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "decoder_traffic.json"), "w"), indent=1)
 print(out)

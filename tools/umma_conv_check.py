@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sbv2-api_b200"))
 import sbv2_b200 as S  # noqa: E402
 
-fn = S.lib.sbv2_debug_conv_compare
+fn = S.debug_lib().sbv2_debug_conv_compare
 pf = C.POINTER(C.c_float)
 fn.restype = C.c_int
 fn.argtypes = [pf, C.c_int64, C.c_int, pf, pf, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, pf, pf]
@@ -31,7 +31,7 @@ def run(T, cin, cout, k, dil, mt=4, res=0, swap=0, identity=False, seed=0):
     st = fn(x.ctypes.data_as(pf), T, cin, w.ctypes.data_as(pf), b.ctypes.data_as(pf), cout, k, dil, mt, res,
             ou.ctypes.data_as(pf), orf.ctypes.data_as(pf))
     if st != 0:
-        print(f"T={T} cin={cin} cout={cout} k={k} d={dil} mt={mt}: ERROR {S.lib.sbv2_last_error().decode()}")
+        print(f"T={T} cin={cin} cout={cout} k={k} d={dil} mt={mt}: ERROR {S.debug_lib().sbv2_last_error().decode()}")
         return None
     ref = orf.copy()
     if res:

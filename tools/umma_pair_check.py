@@ -10,7 +10,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sbv2-api_b200"))
 import sbv2_b200 as S  # noqa: E402
 
-fn = S.lib.sbv2_debug_pair_compare
+fn = S.debug_lib().sbv2_debug_pair_compare
 pf = C.POINTER(C.c_float)
 pi = C.POINTER(C.c_int)
 fn.restype = C.c_int
@@ -52,7 +52,7 @@ def run(lens, c, k, dil, mrf=0, iters=0, seed=0, check_np=True, trace=False):
             ms.ctypes.data_as(pf), cfg.ctypes.data_as(pi), tr.ctypes.data_as(C.POINTER(C.c_longlong)) if trace else None)
     tag = f"C={c} k={k} d={dil} mrf={mrf} n={len(lens)} rows={tot}"
     if st != 0:
-        print(f"ERROR {tag}: {S.lib.sbv2_last_error().decode()}")
+        print(f"ERROR {tag}: {S.debug_lib().sbv2_last_error().decode()}")
         return False
     err_u = float(np.abs(of - orf).max())
     msg = f"{tag} cfg(mt,rows,aslots,nst,sps,res,smem,nkc)={cfg.tolist()} |fused-unfused| {err_u:.3g}"
