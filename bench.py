@@ -10,7 +10,7 @@ per-GPU shard: T_x odd in U{201..281}, BERT features given, sdp_ratio 0, device-
 Weak scaling: every rank owns a model replica and its own batch, no collective on the data path.
 
   value : audio-seconds per second with the step's inputs already resident in HBM, timed with CUDA
-          events on the models' streams, max over ranks (two model replicas per GPU on their own
+          events on the models' streams, max over ranks (--e2e-replicas model replicas per GPU on their own
           streams; `single_stream` repeats it with ONE replica / ONE stream).
   e2e   : the same metric through the C-ABI call a user makes (`sbv2_synthesize_batch`): host
           buffers in (page-locked, as the bench contract prescribes), waveforms in pinned host
@@ -270,8 +270,10 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs", default="cfg1,cfg2,cfg3,cfg5", help="other BASELINE configs measured on rank 0 ('' = none)")
-    ap.add_argument("--e2e-replicas", type=int, default=2,
-                    help="model replicas per GPU driven by separate host threads (copies of one overlap compute of the other)")
+    ap.add_argument("--e2e-replicas", type=int, default=3,
+                    help="model replicas per GPU driven by separate host threads: the synchronous call's H2D / T_y read-back / D2H "
+                         "phases of one replica overlap the kernels of the others (measured 1/2/3 replicas: 8.2k/8.3k/8.9k audio-s/s, "
+                         "profiles/r2_e2e_replicas.log)")
     ap.add_argument("--tiny", action="store_true", help="reduced model (tests only; not a benchmark configuration)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -501,7 +503,7 @@ def main():
                        "region_ms_per_step_rank0": {"text": text_ms, "flow": flow_ms, "decoder": dec_ms}},
             "single_stream": {"value": audio_s_step * single_steps * world / (ms_single_max * 1e-3), "unit": "audio-s/s",
                               "ms_per_step": ms_single_max / single_steps,
-                              "what": "kernel-only, ONE replica on ONE stream per GPU (value above: two replicas / streams per GPU)"},
+                              "what": f"kernel-only, ONE replica on ONE stream per GPU (value above: {R} replicas / streams per GPU)"},
             "e2e": {"value": e2e_audio_total / (e2e_ms_max * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": d2h, "replicas_per_gpu": R, "single_replica_rank0": e2e_single,
                     "single_replica_pageable_inputs_rank0": e2e_pageable,

@@ -23,6 +23,9 @@ namespace {
 
 struct BertLayer {
   ConvLayer qkv, o, f1, f2;
+  // the same GEMMs packed with 64-wide N blocks: a call with few tokens (one sentence, bert.rs:6-24 as the reference
+  // calls it) is a pure weight stream, and 256-wide blocks would leave it to 4-16 CTAs (f2: 4 CTAs x 6 MB each)
+  ConvLayer qkv_s, o_s, f1_s, f2_s;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   float *pos_k = nullptr, *pos_q = nullptr;  // [hidden, 2*span] (transposed) projections of LN(rel_embeddings)
   __half *pos_k_p = nullptr, *pos_q_p = nullptr;  // the same as fp16 [heads][64/8][2*span][8] (tensor-core attention operands)
@@ -35,7 +38,7 @@ struct BertModel : sbv2_model {
   float *emb_g = nullptr, *emb_b = nullptr;
   std::vector<BertLayer> layers;
   bool has_conv = false;
-  ConvLayer conv;
+  ConvLayer conv, conv_s;
   float *conv_g = nullptr, *conv_b = nullptr;
   int* bucket_idx = nullptr;  // device [2*max_rel+1]
   DBuf ids, h, embp, hp, qkvp, ctxp, f1p, y32, meta, outd;
@@ -54,6 +57,9 @@ std::string find_prefix(const OnnxModel& m) {
 }
 
 // HF make_log_bucket_position in float32, as torch evaluates it
+constexpr int kSmallNb = 64;         // N block of the few-token weight packing
+constexpr int64_t kSmallTokens = 256;  // calls with at most this many tokens use it
+
 int log_bucket(int rel, int bucket_size, int max_position) {
   const int mid = bucket_size / 2;
   const int sign = (rel > 0) - (rel < 0);
@@ -204,16 +210,21 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
       qkv.w.insert(qkv.w.end(), hc->w.begin(), hc->w.end());
       qkv.b.insert(qkv.b.end(), hc->b.begin(), hc->b.end());
     }
-    auto layer = [&](const HostConv& hc) {
+    auto layer = [&](const HostConv& hc, int nb_max) {
       M->max_cin = std::max(M->max_cin, hc.d1);
-      return M->exact ? make_split_conv1d_layer(M.get(), hc, 1, 1, 2) : make_conv1d_layer(M.get(), hc, 1, 1);
+      return M->exact ? make_split_conv1d_layer(M.get(), hc, 1, 1, 2, nb_max) : make_conv1d_layer(M.get(), hc, 1, 1, nb_max);
     };
-    B.qkv = layer(qkv);
-    B.o = layer(host_linear(lp + ".attention.output.dense"));
+    const HostConv od = host_linear(lp + ".attention.output.dense"), f2 = host_linear(lp + ".output.dense");
     HostConv f1 = host_linear(lp + ".intermediate.dense");
     M->inter = f1.d0;
-    B.f1 = layer(f1);
-    B.f2 = layer(host_linear(lp + ".output.dense"));
+    B.qkv = layer(qkv, 256);
+    B.o = layer(od, 256);
+    B.f1 = layer(f1, 256);
+    B.f2 = layer(f2, 256);
+    B.qkv_s = layer(qkv, kSmallNb);
+    B.o_s = layer(od, kSmallNb);
+    B.f1_s = layer(f1, kSmallNb);
+    B.f2_s = layer(f2, kSmallNb);
     B.ln1_g = vec(lp + ".attention.output.LayerNorm.weight", H);
     B.ln1_b = vec(lp + ".attention.output.LayerNorm.bias", H);
     B.ln2_g = vec(lp + ".output.LayerNorm.weight", H);
@@ -225,6 +236,7 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
     if (c.k % 2 == 0) fail(SBV2_ERR_UNSUPPORTED, "even ConvLayer kernel size");
     M->max_cin = std::max(M->max_cin, c.d1);
     M->conv = M->exact ? make_split_conv1d_layer(M.get(), c, 1, 1, 2) : make_conv1d_layer(M.get(), c, 1, 1);
+    M->conv_s = M->exact ? make_split_conv1d_layer(M.get(), c, 1, 1, 2, kSmallNb) : make_conv1d_layer(M.get(), c, 1, 1, kSmallNb);
     M->conv_g = vec("encoder.conv.LayerNorm.weight", H);
     M->conv_b = vec("encoder.conv.LayerNorm.bias", H);
     M->has_conv = true;
@@ -334,19 +346,20 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     };
     launch_embed_rows(ctx, h, M.word_emb, M.ids.as<int>(), H, M.vocab, n);
     launch_layernorm(ctx, emb, h, nullptr, nullptr, M.emb_g, M.emb_b, M.eps, ACT_NONE, H, int(n));
+    const bool small = n <= kSmallTokens;
     for (int l = 0; l < M.n_run; ++l) {
       const BertLayer& B = M.layers[l];
       const float* in = l == 0 ? emb : h;
-      gemm(B.qkv, in, H, qkv, 3 * H, ACT_NONE);
+      gemm(small ? B.qkv_s : B.qkv, in, H, qkv, 3 * H, ACT_NONE);
       launch_deberta_attention_f32(ctx, ctxb, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
-      gemm(B.o, ctxb, H, y, H, ACT_NONE);
+      gemm(small ? B.o_s : B.o, ctxb, H, y, H, ACT_NONE);
       launch_layernorm(ctx, h, in, y, nullptr, B.ln1_g, B.ln1_b, M.eps, ACT_NONE, H, int(n));
-      gemm(B.f1, h, H, f1, M.inter, ACT_GELU);
-      gemm(B.f2, f1, M.inter, y, H, ACT_NONE);
+      gemm(small ? B.f1_s : B.f1, h, H, f1, M.inter, ACT_GELU);
+      gemm(small ? B.f2_s : B.f2, f1, M.inter, y, H, ACT_NONE);
       launch_layernorm(ctx, h, h, y, nullptr, B.ln2_g, B.ln2_b, M.eps, ACT_NONE, H, int(n));
       if (l == 0 && M.has_conv) {
         // ConvLayer: LN(layer0_out + gelu(conv(embeddings)))
-        gemm(M.conv, emb, H, y, H, ACT_GELU);
+        gemm(small ? M.conv_s : M.conv, emb, H, y, H, ACT_GELU);
         launch_layernorm(ctx, h, h, y, nullptr, M.conv_g, M.conv_b, M.eps, ACT_NONE, H, int(n));
       }
     }
@@ -389,20 +402,21 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     CUDA_CHECK(cudaMemsetAsync(M.qkvp.p, 0, M.qkvp.cap, M.stream));
     M.qkvp_cleared_gen = M.qkvp.gen;
   }
+  const bool small = n <= kSmallTokens;
   for (int l = 0; l < M.n_run; ++l) {
     const BertLayer& B = M.layers[l];
     const __half* in = l == 0 ? embp : hp;
-    umma(B.qkv, in, qkvp, nullptr, ACT_NONE);
+    umma(small ? B.qkv_s : B.qkv, in, qkvp, nullptr, ACT_NONE);
     if (tc_attn) launch_deberta_attention_tc(ctx, ctxp, qkvp, B.pos_k_p, B.pos_q_p, 2 * M.span, M.span, M.heads, ps);
     else launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
-    umma(B.o, ctxp, nullptr, y32, ACT_NONE);
+    umma(small ? B.o_s : B.o, ctxp, nullptr, y32, ACT_NONE);
     launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln1_g, B.ln1_b, M.eps, H, ps);
-    umma(B.f1, hp, f1p, nullptr, ACT_GELU);
-    umma(B.f2, f1p, nullptr, y32, ACT_NONE);
+    umma(small ? B.f1_s : B.f1, hp, f1p, nullptr, ACT_GELU);
+    umma(small ? B.f2_s : B.f2, f1p, nullptr, y32, ACT_NONE);
     launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln2_g, B.ln2_b, M.eps, H, ps);
     if (l == 0 && M.has_conv) {
       // ConvLayer: LN(layer0_out + gelu(conv(embeddings)))
-      umma(M.conv, embp, nullptr, y32, ACT_GELU);
+      umma(small ? M.conv_s : M.conv, embp, nullptr, y32, ACT_GELU);
       launch_ln_planar_wide(ctx, h, hp, nullptr, y32, M.conv_g, M.conv_b, M.eps, H, ps);
     }
   }

@@ -75,13 +75,19 @@ struct CouplingW {
   WNW wn;        // WN variant
 };
 
+// Every flow / text layer is packed twice: [0] for batches (N blocks up to 256 channels, 256-row work items: fewest weight
+// bytes per row) and [1] for few rows (64-channel N blocks, 128-row items): a batch-1 call is latency-bound, its layers
+// are weight streams, and the wide packing would leave each of them to 2-12 CTAs (profiles/r2_latency_*).  Both give
+// bit-identical results: the K order of every output element is the same.
+constexpr int kSmallNb = 64;
+constexpr int64_t kSmallFlowRows = 1024, kSmallTextRows = 512;
 struct FlowTCLayer {
-  ConvLayer qkv, o, f1, f2;
+  ConvLayer qkv[2], o[2], f1[2], f2[2];
   __half* rel_k_p = nullptr;  // fp16 [D/8][16][8] packing of emb_rel_k for the tensor-core attention
   __half* rel_v_p = nullptr;
 };
 struct FlowTC {
-  ConvLayer pre, post;
+  ConvLayer pre[2], post[2];
   std::vector<FlowTCLayer> layers;
 };
 // WN residual-coupling layer on the tensor cores: in_layers with the tanh * sigmoid gate fused into the epilogue
@@ -141,7 +147,7 @@ struct SynthModel : sbv2_model {
   DBuf fl_x0p, fl_hp, fl_qkvp, fl_ctxp, fl_f1p, fl_y32, fl_m32, fl_meta;
   PinnedBuf fl_pin;
   // text encoder / duration predictor convs on the tensor cores with two-term fp16 splits (~fp32 accuracy)
-  std::vector<ConvLayer> text_tc;
+  std::vector<ConvLayer> text_tc, text_tc_small;  // same index; see kSmallNb
   std::vector<std::pair<ConvW*, HostConv>> text_host;  // consumed at create
   bool use_tc_text = true;
   int text_terms = 2;  // fp16 terms per operand (2: 3 cross products, 3: 6 cross products)
@@ -702,12 +708,14 @@ struct Fwd {
   const int* tg_seg_start = nullptr;  // the Segs::start the geometry was built for
   __half* tg_split = nullptr;
   int tg_n = 0;
+  bool tg_small = false;  // few phoneme rows: use the 64-wide packing of the text layers
 
   void conv(const ConvW& c, const float* in, int in_ld, float* out, int out_ld, const Segs& seg, int dil = 1, int act_in = ACT_NONE,
             int act_out = ACT_NONE, const float* residual = nullptr, const float* bias_utt = nullptr) {
     if (c.tc >= 0 && tg != nullptr && seg.start == tg_seg_start && residual == nullptr && act_in == ACT_NONE && dil == 1 &&
         (act_out == ACT_NONE || act_out == ACT_RELU) && out_ld % 4 == 0) {
-      launch_split_planar(ctx, tg_split, in, in_ld, c.cin, tg_start, *tg, tg_n, M.text_terms, M.text_tc[c.tc].in_scale);
+      const ConvLayer& TL = (tg_small ? M.text_tc_small : M.text_tc)[size_t(c.tc)];
+      launch_split_planar(ctx, tg_split, in, in_ld, c.cin, tg_start, *tg, tg_n, M.text_terms, TL.in_scale);
       ConvCall cc;
       cc.in = tg_split;
       cc.rm_out = out;
@@ -715,7 +723,7 @@ struct Fwd {
       cc.rm_start = tg_start;
       cc.act_out = act_out;
       cc.bias_utt = bias_utt;
-      launch_umma(ctx, M.text_tc[c.tc], *tg, *tg, cc, tg_n);
+      launch_umma(ctx, TL, *tg, *tg, cc, tg_n);
       return;
     }
     ConvArgs a;
@@ -834,14 +842,20 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
   if (M->use_tc_flow) {
     for (auto& v : M->flow_host) {
       FlowTC f;
-      f.pre = make_conv1d_layer(M.get(), v[0], 1, 2, flow_nb);
-      f.post = make_conv1d_layer(M.get(), v[1], 1, 2, flow_nb);
+      for (int sm = 0; sm < 2; ++sm) {
+        const int mtp = sm ? 1 : 2, nbm = sm ? kSmallNb : flow_nb;
+        f.pre[sm] = make_conv1d_layer(M.get(), v[0], 1, mtp, nbm);
+        f.post[sm] = make_conv1d_layer(M.get(), v[1], 1, mtp, nbm);
+      }
       for (size_t l = 0; 2 + 4 * l + 3 < v.size(); ++l) {
         FlowTCLayer fl;
-        fl.qkv = make_conv1d_layer(M.get(), v[2 + 4 * l], 1, 2, flow_nb);
-        fl.o = make_conv1d_layer(M.get(), v[3 + 4 * l], 1, 2, flow_nb);
-        fl.f1 = make_conv1d_layer(M.get(), v[4 + 4 * l], 1, 2, flow_nb);
-        fl.f2 = make_conv1d_layer(M.get(), v[5 + 4 * l], 1, 2, flow_nb);
+        for (int sm = 0; sm < 2; ++sm) {
+          const int mtp = sm ? 1 : 2, nbm = sm ? kSmallNb : flow_nb;
+          fl.qkv[sm] = make_conv1d_layer(M.get(), v[2 + 4 * l], 1, mtp, nbm);
+          fl.o[sm] = make_conv1d_layer(M.get(), v[3 + 4 * l], 1, mtp, nbm);
+          fl.f1[sm] = make_conv1d_layer(M.get(), v[4 + 4 * l], 1, mtp, nbm);
+          fl.f2[sm] = make_conv1d_layer(M.get(), v[5 + 4 * l], 1, mtp, nbm);
+        }
         f.layers.push_back(fl);
       }
       M->flow_tc.push_back(std::move(f));
@@ -917,6 +931,7 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
     for (auto& e : M->text_host) {
       e.first->tc = int(M->text_tc.size());
       M->text_tc.push_back(make_split_conv1d_layer(M.get(), e.second, 1, 2, M->text_terms, flow_nb));
+      M->text_tc_small.push_back(make_split_conv1d_layer(M.get(), e.second, 1, 1, M->text_terms, kSmallNb));
       M->text_tc_max_cin = std::max(M->text_tc_max_cin, e.second.d1);
     }
     M->tx_split.stream = M->stream;
@@ -1304,6 +1319,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     F.tg_seg_start = xseg.start;
     F.tg_split = M.tx_split.as<__half>();
     F.tg_n = B;
+    F.tg_small = Nx <= kSmallTextRows;
     launch_zero_gaps(ctx, F.tg_split, nblk * M.text_tc_max_cin, TG, B);  // the splits only ever write utterance rows
   }
   launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
@@ -1509,6 +1525,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     float* m32 = M.fl_m32.as<float>();
     launch_zero_gaps(ctx, hp16, H, G, B);
     launch_zero_gaps(ctx, f1p, filt, G, B);
+    const int sm = ny <= kSmallFlowRows ? 1 : 0;  // few frames: the 64-wide packing (more CTAs per weight stream)
     auto umma = [&](const ConvLayer& L, const __half* in, __half* out, float* acc32, int act) {
       ConvCall c;
       c.in = in;
@@ -1524,7 +1541,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
       launch_flip_channels(ctx, zn, zc, C, ny);
       std::swap(zc, zn);
       launch_to_planar(ctx, x0p, zc, C, C / 2, bg.d_ystart, G, B, ACT_NONE);
-      umma(T.pre, x0p, nullptr, y32, ACT_NONE);
+      umma(T.pre[sm], x0p, nullptr, y32, ACT_NONE);
       launch_flow_mix(ctx, hf, hp16, nullptr, y32, nullptr, 0, H, ps);
       const EncoderW& E = cp.enc;
       for (size_t l = 0; l < E.layers.size(); ++l) {
@@ -1535,16 +1552,16 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
           F.conv(E.spk, g, hp.gin, gg, H, bseg);
           launch_flow_mix(ctx, hf, hp16, hf, nullptr, gg, H, H, ps);
         }
-        umma(Lt.qkv, hp16, qkvp, nullptr, ACT_NONE);
+        umma(Lt.qkv[sm], hp16, qkvp, nullptr, ACT_NONE);
         if (M.use_tc_attn) launch_flow_attention_tc(ctx, ctxp, qkvp, Lt.rel_k_p, Lt.rel_v_p, E.heads, E.head_dim, E.window, ps);
         else launch_rel_attention_planar(ctx, ctxp, qkvp, Lw.rel_k, Lw.rel_v, E.heads, E.head_dim, E.window, ps);
-        umma(Lt.o, ctxp, nullptr, y32, ACT_NONE);
+        umma(Lt.o[sm], ctxp, nullptr, y32, ACT_NONE);
         launch_ln_planar(ctx, hf, hp16, y32, Lw.n1.g, Lw.n1.b, 1e-5f, H, ps);
-        umma(Lt.f1, hp16, f1p, nullptr, ACT_RELU);
-        umma(Lt.f2, f1p, nullptr, y32, ACT_NONE);
+        umma(Lt.f1[sm], hp16, f1p, nullptr, ACT_RELU);
+        umma(Lt.f2[sm], f1p, nullptr, y32, ACT_NONE);
         launch_ln_planar(ctx, hf, hp16, y32, Lw.n2.g, Lw.n2.b, 1e-5f, H, ps);
       }
-      umma(T.post, hp16, nullptr, m32, ACT_NONE);
+      umma(T.post[sm], hp16, nullptr, m32, ACT_NONE);
       launch_coupling_sub_planar(ctx, zc, m32, C, ps);
     }
   } else if (M.use_tc_wn) {

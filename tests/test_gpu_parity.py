@@ -195,7 +195,7 @@ def test_wn_flow_variant(S):
         simt = S.Model(onnx, bert=False)
     finally:
         del os.environ["SBV2_B200_FLOW"]
-    us = [util.to_api(util.make_utterance(hp, t, seed=40 + i, sdp_ratio=0.0)) for i, t in enumerate((33, 1, 130, 77))]
+    us = [util.to_api(util.make_utterance(hp, t, seed=40 + i, sdp_ratio=0.0)) for i, t in enumerate((33, 1, 131, 77))]
     a, da, fa = model.synthesize_batch(us, want_alignment=True)
     b, db_, fb = simt.synthesize_batch(us, want_alignment=True)
     for i in range(len(us)):
