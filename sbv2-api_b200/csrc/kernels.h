@@ -35,20 +35,37 @@ struct LaunchCtx {
 // Measured on the bench workload: -0.65 ms of 29 on a single stream (batch-1 latency 5.3 -> 4.9 ms) and neutral for two
 // replicas per GPU once the mbarrier waits sleep instead of polling; on by default, SBV2_B200_PDL=0 disables it.
 #ifdef __CUDACC__
+// cluster > 1 launches thread-block clusters of that many CTAs along x (grid.x must be a multiple of it)
 template <class... KArgs, class... Args>
-inline void launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline void launch_pdl_cluster(bool pdl, int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = unsigned(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = unsigned(n);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) fail(SBV2_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e));
+}
+template <class... KArgs, class... Args>
+inline void launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  launch_pdl_cluster(pdl, 1, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -57,6 +57,11 @@ struct UmmaConvArgs {
   const float* bias_utt;       // [n_utt][bias_utt_ld] or null
   int bias_utt_ld;
   int gate_half;               // > 0: WaveNet gate epilogue (N block = [tanh half | sigmoid half])
+  // Thread-block cluster of `cluster` CTAs (1 = none): the CTAs of a cluster work on `cluster` consecutive row tiles of
+  // the SAME (N block, group), so they consume the same weight stages; every CTA fetches 1/cluster of each stage and
+  // multicasts it to all of them (L2 -> SM weight traffic and L2 request pressure divided by `cluster`)
+  int cluster;
+  int n_tiles;                 // row tiles of this launch (tile_prefix[n_utt])
   const int* tile_prefix;      // [n_utt+1]
   const int* pstart_in;        // [n_utt] first planar row of each utterance in `in`
   const int* pstart_out;
@@ -94,13 +99,23 @@ struct TileInfo {
     if (p.trace && (itv) < 64) p.trace[((size_t)blockIdx.x * 64 + (itv)) * 8 + (ev)] = clock64(); \
   } while (0)
 
-__device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item) {
+// Work item `item` of this CTA.  Without clusters: item = tile * per_tile + (grp, nblk).  With clusters the unit is a
+// cluster item = (group of `cluster` consecutive tiles, (grp, nblk)) and CTA `rank` takes tile group * cluster + rank; a
+// tile past the end is a dummy (no valid rows) that still runs the K loop, so the cluster's weight pipeline stays in step.
+__device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item, int rank) {
   TileInfo ti;
   const int per_tile = p.n_nblk * p.n_groups;
-  const int tile = item / per_tile;
-  const int rem = item - tile * per_tile;
+  const int tgroup = item / per_tile;
+  const int rem = item - tgroup * per_tile;
+  const int tile = tgroup * p.cluster + rank;
   ti.grp = rem / p.n_nblk;
   ti.nblk = rem - ti.grp * p.n_nblk;
+  if (tile >= p.n_tiles) {
+    ti.b = p.n_utt - 1;
+    ti.len = p.len[ti.b];
+    ti.t0 = ti.len;  // every row invalid; the A tile is read from the (zero, allocated) rows after the last utterance
+    return ti;
+  }
   int lo = 0, hi = p.n_utt;  // largest b with tile_prefix[b] <= tile
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -134,6 +149,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sA));
   float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 320);  // [2][NB] (after 36 barriers + the TMEM slot)
   const int acc_cols = p.mt * p.nb;  // TMEM columns of one accumulator set
+  const int nc = p.cluster;
+  const int rank = nc > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / nc, unit_step = (int)gridDim.x / nc;  // this CTA's (cluster's) first item and stride
+  const uint16_t cta_mask = (uint16_t)((1u << nc) - 1u);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) {
@@ -142,7 +161,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     }
     for (int i = 0; i < p.nstages; ++i) {
       mbar_init(bar_bf + 8 * i, 1);
-      mbar_init(bar_be + 8 * i, 1);
+      mbar_init(bar_be + 8 * i, nc);  // a weight stage is free again when every CTA of the cluster has consumed it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accf + 8 * i, 1);
@@ -156,6 +175,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (nc > 1) cluster_sync_all();  // every CTA's barriers are initialised before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // PDL: everything above overlapped the previous kernel's tail; its results are visible after the wait
@@ -168,8 +188,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       uint32_t a_it = 0, b_it = 0;  // running ring counters
       bool first = true;
       uint32_t pit = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, first = false, ++pit) {
-        const TileInfo ti = locate_item(p, item);
+      for (int item = unit0; item < p.n_items; item += unit_step, first = false, ++pit) {
+        const TileInfo ti = locate_item(p, item, rank);
         TRACE(0, pit);
         const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
@@ -191,7 +211,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           const int nsteps = min(p.sps, p.total_steps - first_step);
           const uint32_t bytes = step_bytes * nsteps;
           mbar_expect_tx(bar_bf + 8 * st, bytes);
-          bulk_g2s(sB + stage_bytes * st, wbase + (size_t)first_step * (step_bytes / 2), bytes, bar_bf + 8 * st);
+          if (nc > 1) {
+            // this CTA's 1/nc of the stage goes to every CTA of the cluster (all of them expect the whole stage)
+            const uint32_t slice = bytes / (uint32_t)nc;
+            bulk_g2s_multicast(sB + stage_bytes * st + (uint32_t)rank * slice,
+                               reinterpret_cast<const uint8_t*>(wbase + (size_t)first_step * (step_bytes / 2)) + (size_t)rank * slice, slice,
+                               bar_bf + 8 * st, cta_mask);
+          } else {
+            bulk_g2s(sB + stage_bytes * st, wbase + (size_t)first_step * (step_bytes / 2), bytes, bar_bf + 8 * st);
+          }
           ++b_it;
         };
         const bool load_w = !p.b_resident || first;
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       auto run = [&](auto mtk) {
         constexpr int MT = decltype(mtk)::mt, K16 = decltype(mtk)::k16;
         uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0, it = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
           const uint32_t buf = it & 1;
           mbar_wait(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
           tc_fence_after();
@@ -251,7 +279,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
               if (!p.b_resident) {
                 ++si;
                 if (si == p.sps || step == p.total_steps - 1) {
-                  if (leader) tc_commit(bar_be + 8 * b_st);
+                  if (leader) {
+                    if (nc > 1) tc_commit_multicast(bar_be + 8 * b_st, cta_mask);
+                    else tc_commit(bar_be + 8 * b_st);
+                  }
                   si = 0;
                   if (++b_st == (uint32_t)p.nstages) {
                     b_st = 0;
@@ -296,9 +327,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     const int n_sub = p.mt * items_per_acc;
     const bool bias_per_item = p.n_nblk > 1 || p.bias_utt != nullptr;
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
       const uint32_t buf = it & 1;
-      const TileInfo ti = locate_item(p, item);
+      const TileInfo ti = locate_item(p, item, rank);
       float* bias = bias_s + (bias_per_item ? buf * p.nb : 0);
       if (bias_per_item || it == 0) {
         // (per item: the set used two items ago has been fully consumed — its acc_empty arrivals
@@ -358,6 +389,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (nc > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -760,15 +792,28 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.rm_start = c.rm_start;
   a.trace = g_trace;
   if (gi.n_tiles[slot] <= 0) return;
-  a.n_items = gi.n_tiles[slot] * L.n_nblk * L.n_groups;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  dim3 grid(std::min(a.n_items, num_sms));
-  launch_pdl(ctx.pdl, umma_conv_kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
+  // Thread-block clusters with multicast weight stages (SBV2_B200_CLUSTER = 1 / 2 / 4, default 2: a cluster of 2 is one
+  // TPC, so all 148 SMs stay usable; 4 halves the weight traffic again but strands the SMs of a GPC that do not fill a
+  // cluster).  Streaming layers only: resident weights are fetched once per CTA anyway.
+  static int cluster_pref = -1;
+  if (cluster_pref < 0) {
+    const char* e = getenv("SBV2_B200_CLUSTER");
+    cluster_pref = e ? atoi(e) : 2;
+    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 2;
+  }
+  int nc = L.b_resident ? 1 : cluster_pref;
+  while (nc > 1 && (gi.n_tiles[slot] < nc || (size_t(L.nb) * L.kc * 2) % (size_t(16) * nc) != 0)) nc >>= 1;
+  a.cluster = nc;
+  a.n_tiles = gi.n_tiles[slot];
+  a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * L.n_nblk * L.n_groups;  // cluster items
+  dim3 grid(std::min(a.n_items, num_sms / nc) * nc);
+  launch_pdl_cluster(ctx.pdl, nc, umma_conv_kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
   ctx.count();
 }
 

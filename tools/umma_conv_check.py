@@ -68,3 +68,11 @@ if __name__ == "__main__":
     run(300, 192, 512, 7, 1, mt=2, swap=swap)
     run(700, 128, 128, 3, 1, mt=4, res=1, swap=swap)
     run(900, 512, 256, 3, 1, mt=1, swap=swap)
+    # cluster-multicast coverage (SBV2_B200_CLUSTER=2/4): many tiles, odd tile counts (dummy tiles), streaming weights
+    run(647, 192, 768, 3, 1, mt=1, swap=swap)
+    run(5000, 192, 768, 3, 1, mt=2, swap=swap)
+    run(3000, 768, 192, 3, 1, mt=2, swap=swap)
+    run(4096 + 128 * 3 + 5, 1024, 1024, 1, 1, mt=1, swap=swap)
+    run(129, 1024, 1024, 1, 1, mt=1, swap=swap)
+    run(9000, 128, 128, 11, 5, mt=2, res=1, swap=swap)
+    run(9000, 256, 256, 7, 3, mt=1, swap=swap)
