@@ -275,6 +275,9 @@ def main():
                          "phases of one replica overlap the kernels of the others (measured 1/2/3 replicas: 8.2k/8.3k/8.9k audio-s/s, "
                          "profiles/r2_e2e_replicas.log)")
     ap.add_argument("--tiny", action="store_true", help="reduced model (tests only; not a benchmark configuration)")
+    ap.add_argument("--flow", default="transformer", choices=["transformer", "wn"],
+                    help="flow variant of the synthetic model: JP-Extra's transformer coupling layers (the headline) or the WN "
+                         "residual-coupling layers north_star names (non-JP-Extra Style-Bert-VITS2 models)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -286,9 +289,11 @@ def main():
     import torch
     from oracle import vits as ov
 
-    hp = ov.tiny_hparams() if args.tiny else ov.HParams()
+    flow_kw = {} if args.flow == "transformer" else {"use_transformer_flow": False}
+    hp = ov.tiny_hparams(**flow_kw) if args.tiny else ov.HParams(**flow_kw)
     workload = f"cfg4 shard: full JP-Extra pipeline, {args.batch} synthetic ~8 s utterances per GPU per step " \
-               f"(T_x odd U{{201..281}}, BERT features given, sdp_ratio 0, transformer flow L=6)"
+               f"(T_x odd U{{201..281}}, BERT features given, sdp_ratio 0, " + \
+               ("transformer flow L=6)" if args.flow == "transformer" else "WN residual-coupling flow, 4 x 4 layers)")
 
     # ------------------------------------------------------------------ reference arm (the reference's CPU path)
     if args.impl == "reference":

@@ -149,6 +149,7 @@ struct SynthModel : sbv2_model {
   // text encoder / duration predictor convs on the tensor cores with two-term fp16 splits (~fp32 accuracy)
   std::vector<ConvLayer> text_tc, text_tc_small;  // same index; see kSmallNb
   std::vector<std::pair<ConvW*, HostConv>> text_host;  // consumed at create
+  int64_t small_text_rows = kSmallTextRows, small_flow_rows = kSmallFlowRows;  // SBV2_B200_SMALL_ROWS="text,flow" overrides
   bool use_tc_text = true;
   int text_terms = 2;  // fp16 terms per operand (2: 3 cross products, 3: 6 cross products)
   int text_tc_max_cin = 0;
@@ -885,6 +886,13 @@ sbv2_model* create_synth_model(const OnnxModel& m, int device) {
         }
     }
   }
+  if (const char* e = getenv("SBV2_B200_SMALL_ROWS")) {
+    long long a = 0, b = 0;
+    if (sscanf(e, "%lld,%lld", &a, &b) == 2) {
+      M->small_text_rows = a;
+      M->small_flow_rows = b;
+    }
+  }
   M->flow_host.clear();
   // WN variant on the tensor cores (SBV2_B200_FLOW=fp32 keeps the CUDA-core kernels): dilation_rate of the coupling
   // layers' WN is 1 (oracle/vits.py ResidualCouplingLayer), so every in_layer is a plain k-tap "same" convolution
@@ -1319,7 +1327,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     F.tg_seg_start = xseg.start;
     F.tg_split = M.tx_split.as<__half>();
     F.tg_n = B;
-    F.tg_small = Nx <= kSmallTextRows;
+    F.tg_small = Nx <= M.small_text_rows;
     launch_zero_gaps(ctx, F.tg_split, nblk * M.text_tc_max_cin, TG, B);  // the splits only ever write utterance rows
   }
   launch_gather_rows(ctx, g, M.emb_g, d_sid, B, hp.gin, hp.n_speakers);
@@ -1525,7 +1533,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
     float* m32 = M.fl_m32.as<float>();
     launch_zero_gaps(ctx, hp16, H, G, B);
     launch_zero_gaps(ctx, f1p, filt, G, B);
-    const int sm = ny <= kSmallFlowRows ? 1 : 0;  // few frames: the 64-wide packing (more CTAs per weight stream)
+    const int sm = ny <= M.small_flow_rows ? 1 : 0;  // few frames: the 64-wide packing (more CTAs per weight stream)
     auto umma = [&](const ConvLayer& L, const __half* in, __half* out, float* acc32, int act) {
       ConvCall c;
       c.in = in;

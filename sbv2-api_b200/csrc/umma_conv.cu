@@ -102,15 +102,16 @@ struct TileInfo {
 // Work item `item` of this CTA.  Without clusters: item = tile * per_tile + (grp, nblk).  With clusters the unit is a
 // cluster item = (group of `cluster` consecutive tiles, (grp, nblk)) and CTA `rank` takes tile group * cluster + rank; a
 // tile past the end is a dummy (no valid rows) that still runs the K loop, so the cluster's weight pipeline stays in step.
+template <bool CLUSTER>
 __device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item, int rank) {
   TileInfo ti;
   const int per_tile = p.n_nblk * p.n_groups;
   const int tgroup = item / per_tile;
   const int rem = item - tgroup * per_tile;
-  const int tile = tgroup * p.cluster + rank;
+  const int tile = CLUSTER ? tgroup * p.cluster + rank : tgroup;
   ti.grp = rem / p.n_nblk;
   ti.nblk = rem - ti.grp * p.n_nblk;
-  if (tile >= p.n_tiles) {
+  if (CLUSTER && tile >= p.n_tiles) {
     ti.b = p.n_utt - 1;
     ti.len = p.len[ti.b];
     ti.t0 = ti.len;  // every row invalid; the A tile is read from the (zero, allocated) rows after the last utterance
@@ -128,7 +129,13 @@ __device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item,
   return ti;
 }
 
+// VARIANT bit 0: WaveNet gate epilogue; bit 1: thread-block clusters with multicast weight stages; bit 2: fp32 row-major
+// epilogue (text encoder, exact-mode DeBERTa: bias + ReLU / GELU).  The plain kernel (VARIANT 0: every decoder and
+// transformer-flow launch) is compiled with the planar epilogue only, so the other paths cost it no registers (96
+// registers per thread at 576 threads: the epilogue is the part that spills first).
+template <int VARIANT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvArgs p) {
+  constexpr bool GATE = (VARIANT & 1) != 0, CLUSTER = (VARIANT & 2) != 0, ROWMAJOR = (VARIANT & 4) != 0;
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index made provably warp-uniform so that role branches are uniform and the MMA
   // descriptors stay in uniform registers (UTCHMMA takes UR operands; R2UR per MMA is slow)
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sA));
   float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 320);  // [2][NB] (after 36 barriers + the TMEM slot)
   const int acc_cols = p.mt * p.nb;  // TMEM columns of one accumulator set
-  const int nc = p.cluster;
-  const int rank = nc > 1 ? (int)cluster_ctarank() : 0;
+  const int nc = CLUSTER ? p.cluster : 1;
+  const int rank = CLUSTER ? (int)cluster_ctarank() : 0;
   const int unit0 = (int)blockIdx.x / nc, unit_step = (int)gridDim.x / nc;  // this CTA's (cluster's) first item and stride
   const uint16_t cta_mask = (uint16_t)((1u << nc) - 1u);
 
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (nc > 1) cluster_sync_all();  // every CTA's barriers are initialised before a peer multicasts into them
+  if (CLUSTER) cluster_sync_all();  // every CTA's barriers are initialised before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // PDL: everything above overlapped the previous kernel's tail; its results are visible after the wait
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       bool first = true;
       uint32_t pit = 0;
       for (int item = unit0; item < p.n_items; item += unit_step, first = false, ++pit) {
-        const TileInfo ti = locate_item(p, item, rank);
+        const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
         TRACE(0, pit);
         const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           const int nsteps = min(p.sps, p.total_steps - first_step);
           const uint32_t bytes = step_bytes * nsteps;
           mbar_expect_tx(bar_bf + 8 * st, bytes);
-          if (nc > 1) {
+          if (CLUSTER) {
             // this CTA's 1/nc of the stage goes to every CTA of the cluster (all of them expect the whole stage)
             const uint32_t slice = bytes / (uint32_t)nc;
             bulk_g2s_multicast(sB + stage_bytes * st + (uint32_t)rank * slice,
@@ -245,6 +252,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       const uint64_t b_desc0 = desc_hi | ((uint64_t)((uint32_t)p.nb & 0x3FFF) << 16);  // LBO = NB*16 B
       const uint32_t a_kstep = 2u * (uint32_t)RA, b_kstep = 2u * (uint32_t)p.nb;       // two planes per K=16 step (16-B units)
       const uint32_t nb_u = (uint32_t)p.nb, idesc = p.idesc;
+      // In a cluster launch the shared-window address of CTA rank r carries r in bits 24+ (0x0r000400 on sm_100); the
+      // matrix descriptor's 14-bit start-address field is CTA-local, so strip the window base before it is added in.
+      const uint32_t cta_win = sA & 0xFF000000u;
       const bool leader = elect_one_sync() != 0;  // the same lane issues every MMA / commit of this CTA
       // MT / K16 are compile-time (dispatched once, below): a per-tap switch or elect costs ~140 cycles per tap, which
       // the tensor pipe does not hide — it starts each MMA as it is issued (umma_microbench.cu, "issue shape")
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           for (int kc = 0; kc < p.nkc; ++kc) {
             mbar_wait(bar_af + 8 * a_slot_i, a_par);
             if (kc == 0 && lane == 0) TRACE(3, it);
-            const uint64_t a_chunk = a_desc0 + ((sA + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
+            const uint64_t a_chunk = a_desc0 + ((sA - cta_win + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
             for (int tap = 0; tap < p.taps; ++tap, ++step) {
               uint32_t b_addr;
               if (p.b_resident) {
@@ -273,14 +283,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
                 b_addr = sB + stage_bytes * b_st + step_bytes * si;
               }
               const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
-              const uint64_t b_d = b_desc0 + (b_addr >> 4);
+              const uint64_t b_d = b_desc0 + ((b_addr - cta_win) >> 4);
               const uint32_t accf = step > 0 ? 1u : 0u;
               if (leader) issue_mmas<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
               if (!p.b_resident) {
                 ++si;
                 if (si == p.sps || step == p.total_steps - 1) {
                   if (leader) {
-                    if (nc > 1) tc_commit_multicast(bar_be + 8 * b_st, cta_mask);
+                    if (CLUSTER) tc_commit_multicast(bar_be + 8 * b_st, cta_mask);
                     else tc_commit(bar_be + 8 * b_st);
                   }
                   si = 0;
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     uint32_t it = 0;
     for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
       const uint32_t buf = it & 1;
-      const TileInfo ti = locate_item(p, item, rank);
+      const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
       float* bias = bias_s + (bias_per_item ? buf * p.nb : 0);
       if (bias_per_item || it == 0) {
         // (per item: the set used two items ago has been fully consumed — its acc_empty arrivals
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       tc_fence_after();
       if (threadIdx.x == 64) TRACE(5, it);
       const uint32_t tmem_acc = tmem_base + buf * acc_cols;
-      if (p.gate_half > 0) {
+      if (GATE) {
         const int per_acc = p.gate_half / 16;
         for (int sub = part; sub < p.mt * per_acc; sub += NUM_EPI_WARPS / 4) {
           const int a = sub / per_acc;
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off + p.group_out_off[ti.grp];
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
         const int cg = ti.nblk * p.nb + c0;
-        if (p.rm_out != nullptr) {
+        if (ROWMAJOR) {
           epilogue_item_rm(p, taddr, valid, (long long)p.rm_start[ti.b] + t, cg, bias + c0);
         } else if (p.accum_mode != UACC_NONE) {
           if (p.has_res) epilogue_item<16, true, 1>(p, taddr, valid, orow, cg, bias + c0);
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (nc > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
+  if (CLUSTER) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -625,7 +635,14 @@ int mt_slot(int mt) { return mt == 1 ? 0 : (mt == 2 ? 1 : (mt == 4 ? 2 : (mt == 
 
 void set_smem_attr() {
   static PerDeviceOnce attr_once;
-  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)); });
+  attr_once.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  });
 }
 
 }  // namespace
@@ -798,14 +815,16 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  // Thread-block clusters with multicast weight stages (SBV2_B200_CLUSTER = 1 / 2 / 4, default 2: a cluster of 2 is one
-  // TPC, so all 148 SMs stay usable; 4 halves the weight traffic again but strands the SMs of a GPC that do not fill a
-  // cluster).  Streaming layers only: resident weights are fetched once per CTA anyway.
+  // Thread-block clusters with multicast weight stages (SBV2_B200_CLUSTER = 1 / 2 / 4).  OFF by default: measured on the
+  // bench workload the lock-step of the cluster (every CTA waits for all peers' slices and all peers' MMAs per stage) costs
+  // more than the divided L2 -> SM weight traffic saves — decoder 20.05 / 20.73 / 27.94 ms, flow 7.44 / 7.84 / 8.84 ms
+  // for 1 / 2 / 4 CTAs per cluster (profiles/r2_cluster_multicast.log); results are identical in all three modes
+  // (tools/umma_conv_check.py).  Streaming layers only: resident weights are fetched once per CTA anyway.
   static int cluster_pref = -1;
   if (cluster_pref < 0) {
     const char* e = getenv("SBV2_B200_CLUSTER");
-    cluster_pref = e ? atoi(e) : 2;
-    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 2;
+    cluster_pref = e ? atoi(e) : 1;
+    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 1;
   }
   int nc = L.b_resident ? 1 : cluster_pref;
   while (nc > 1 && (gi.n_tiles[slot] < nc || (size_t(L.nb) * L.kc * 2) % (size_t(16) * nc) != 0)) nc >>= 1;
@@ -813,7 +832,17 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.n_tiles = gi.n_tiles[slot];
   a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * L.n_nblk * L.n_groups;  // cluster items
   dim3 grid(std::min(a.n_items, num_sms / nc) * nc);
-  launch_pdl_cluster(ctx.pdl, nc, umma_conv_kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
+  void (*kernel)(UmmaConvArgs) = nullptr;
+  switch ((c.gate_half > 0 ? 1 : 0) | (nc > 1 ? 2 : 0) | (c.rm_out != nullptr ? 4 : 0)) {
+    case 0: kernel = umma_conv_kernel<0>; break;
+    case 1: kernel = umma_conv_kernel<1>; break;
+    case 2: kernel = umma_conv_kernel<2>; break;
+    case 3: kernel = umma_conv_kernel<3>; break;
+    case 4: kernel = umma_conv_kernel<4>; break;
+    case 6: kernel = umma_conv_kernel<6>; break;
+    default: fail(SBV2_ERR_INTERNAL, "conv kernel: unsupported epilogue combination");
+  }
+  launch_pdl_cluster(ctx.pdl, nc, kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
   ctx.count();
 }
 

@@ -388,6 +388,7 @@ extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const
     SBV2_REQUIRE(x && w && out_umma && out_ref && T > 0, "bad arguments");
     sbv2_model owner;
     owner.device = 0;
+    if (const char* pe = getenv("SBV2_B200_PDL")) owner.pdl = pe[0] != '0';
     CUDA_CHECK(cudaSetDevice(0));
     CUDA_CHECK(cudaStreamCreateWithFlags(&owner.stream, cudaStreamNonBlocking));
     LaunchCtx ctx = owner.ctx();

@@ -249,3 +249,60 @@ extern "C" int sbv2_debug_mma_rate(int n, int layout, int shift_rows, int iters,
     cudaFree(d);
   });
 }
+
+// ---- cluster multicast probe: every CTA of a cluster of NC fetches 1/NC of a buffer and multicasts it to all CTAs; each
+// CTA then dumps what landed in its shared memory.  Also reports %cluster_ctarank and the shared-window addresses.
+namespace {
+__global__ void __launch_bounds__(128) multicast_probe_kernel(const uint32_t* src, uint32_t* out, int words, int nc, uint32_t* info) {
+  extern __shared__ __align__(128) uint8_t psm[];
+  const uint32_t sbuf = sbv2::smem_u32(psm);
+  const uint32_t bar = sbuf + (uint32_t)words * 4;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (threadIdx.x == 0) {
+    sbv2::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(psm)[i] = 0xdeadbeefu;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)words * 4, slice = bytes / (uint32_t)nc;
+    sbv2::mbar_expect_tx(bar, bytes);
+    sbv2::bulk_g2s_multicast(sbuf + rank * slice, reinterpret_cast<const uint8_t*>(src) + rank * slice, slice, bar,
+                             (uint16_t)((1u << nc) - 1u));
+    info[blockIdx.x * 4 + 0] = rank;
+    info[blockIdx.x * 4 + 1] = sbuf;
+    info[blockIdx.x * 4 + 2] = bar;
+  }
+  sbv2::mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) out[(size_t)blockIdx.x * words + i] = reinterpret_cast<volatile uint32_t*>(psm)[i];
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+}  // namespace
+
+extern "C" int sbv2_debug_multicast_probe(int nc, int words, int blocks, uint32_t* out /*[blocks*words]*/, uint32_t* info /*[blocks*4]*/) {
+  return sbv2::guarded([&] {
+    CUDA_CHECK(cudaSetDevice(0));
+    uint32_t *d_src = nullptr, *d_out = nullptr, *d_info = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_src, size_t(words) * 4));
+    CUDA_CHECK(cudaMalloc(&d_out, size_t(blocks) * words * 4));
+    CUDA_CHECK(cudaMalloc(&d_info, size_t(blocks) * 16));
+    std::vector<uint32_t> h;
+    h.resize(size_t(words));
+    for (int i = 0; i < words; ++i) h[size_t(i)] = uint32_t(i);
+    CUDA_CHECK(cudaMemcpy(d_src, h.data(), size_t(words) * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(d_out, 0xff, size_t(blocks) * words * 4));
+    sbv2::launch_pdl_cluster(false, nc, multicast_probe_kernel, dim3(blocks), dim3(128), size_t(words) * 4 + 64, nullptr, d_src, d_out, words, nc,
+                             d_info);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(out, d_out, size_t(blocks) * words * 4, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(info, d_info, size_t(blocks) * 16, cudaMemcpyDeviceToHost));
+    cudaFree(d_src);
+    cudaFree(d_out);
+    cudaFree(d_info);
+  });
+}
