@@ -775,10 +775,69 @@ void launch_add_utt_vec(const LaunchCtx& ctx, float* out, const float* x, const 
   POST_LAUNCH(ctx);
 }
 
+// Wide rows (C a multiple of 128, e.g. DeBERTa's 1024): one warp per row, NV float4 per lane, every load of the row issued
+// before the first use.  The scalar kernel's conditional loads were consumed one by one, i.e. one memory round trip per
+// 32 channels — 35-41 us for a 7-row LayerNorm of 1024 channels (profiles/r2_launches_bert_exact_s7.csv).
+template <int NV>
+__global__ void layernorm_vec_kernel(float* out, const float* a, const float* addin, const float* res, const float* gamma,
+                                     const float* beta, float eps, int act, int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  constexpr int C = NV * 128;
+  const size_t base = (size_t)warp * C;
+  float4 v[NV], w[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(a + base + (i * 32 + lane) * 4);
+  if (addin) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = *reinterpret_cast<const float4*>(addin + base + (i * 32 + lane) * 4);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = make_float4(v[i].x + w[i].x, v[i].y + w[i].y, v[i].z + w[i].z, v[i].w + w[i].w);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+    float4 y = make_float4(apply_act((v[i].x - mean) * rstd * g.x + bt.x, act), apply_act((v[i].y - mean) * rstd * g.y + bt.y, act),
+                           apply_act((v[i].z - mean) * rstd * g.z + bt.z, act), apply_act((v[i].w - mean) * rstd * g.w + bt.w, act));
+    if (res) {
+      const float4 r = *reinterpret_cast<const float4*>(res + base + c);
+      y = make_float4(y.x + r.x, y.y + r.y, y.z + r.z, y.w + r.w);
+    }
+    *reinterpret_cast<float4*>(out + base + c) = y;
+  }
+}
+
 void launch_layernorm(const LaunchCtx& ctx, float* out, const float* a, const float* addin, const float* res,
                       const float* gamma, const float* beta, float eps, int act, int C, int rows) {
   if (rows <= 0) return;
   int blocks = (rows + 7) / 8;  // 8 warps per block
+  if (C == 1024) {
+    layernorm_vec_kernel<8><<<blocks, 256, 0, ctx.stream>>>(out, a, addin, res, gamma, beta, eps, act, rows);
+    POST_LAUNCH(ctx);
+    return;
+  }
+  if (C == 512 || C == 768) {
+    if (C == 512) layernorm_vec_kernel<4><<<blocks, 256, 0, ctx.stream>>>(out, a, addin, res, gamma, beta, eps, act, rows);
+    else layernorm_vec_kernel<6><<<blocks, 256, 0, ctx.stream>>>(out, a, addin, res, gamma, beta, eps, act, rows);
+    POST_LAUNCH(ctx);
+    return;
+  }
   if (C <= 256) layernorm_kernel<8><<<blocks, 256, 0, ctx.stream>>>(out, a, addin, res, gamma, beta, eps, act, C, rows);
   else if (C <= 1024) layernorm_kernel<32><<<blocks, 256, 0, ctx.stream>>>(out, a, addin, res, gamma, beta, eps, act, C, rows);
   else fail(SBV2_ERR_UNSUPPORTED, "layernorm: C > 1024");

@@ -107,11 +107,22 @@ sbv2_model::~sbv2_model() {
     cudaEventDestroy(kv.second.first);
     cudaEventDestroy(kv.second.second);
   }
+  if (wait_event) cudaEventDestroy(wait_event);
   for (void* p : owned_device) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
 }
 
 void sbv2_model::bind_device() const { CUDA_CHECK(cudaSetDevice(device)); }
+
+void sbv2_model::wait_stream(bool yield) {
+  if (!yield) {
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    return;
+  }
+  if (!wait_event) CUDA_CHECK(cudaEventCreateWithFlags(&wait_event, cudaEventBlockingSync | cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(wait_event, stream));
+  CUDA_CHECK(cudaEventSynchronize(wait_event));
+}
 
 void* sbv2_model::upload_bytes(const void* host, size_t bytes) {
   void* d = nullptr;

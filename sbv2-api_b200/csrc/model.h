@@ -76,6 +76,12 @@ struct sbv2_model {
   bool pdl = true;  // programmatic dependent launch of the tensor-core kernels (SBV2_B200_PDL=0, read at model creation, disables)
   sbv2::LaunchCtx ctx() { return sbv2::LaunchCtx{stream, &launches, pdl}; }
   void bind_device() const;
+  // Waits for the model's stream.  `yield` = true parks the host thread on a blocking-sync event instead of spinning in
+  // cudaStreamSynchronize: the two long waits of a batched synthesize call (T_y read-back, final download) would otherwise
+  // burn one host core per in-flight call — with 3 replicas on each of 8 GPUs that is more spinning threads than the
+  // box has cores, and the end-to-end scaling pays for it.  Short (batch-1) calls keep spinning: waking up costs ~50 us.
+  void wait_stream(bool yield);
+  cudaEvent_t wait_event = nullptr;
   // uploads host data, tracked for release at destroy
   void* upload_bytes(const void* host, size_t bytes);
   float* upload_f32(const std::vector<float>& v) { return static_cast<float*>(upload_bytes(v.data(), v.size() * 4)); }

@@ -1409,7 +1409,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   M.region_end("text");
   M.pin_ylen.ensure(size_t(B) * 4);
   CUDA_CHECK(cudaMemcpyAsync(M.pin_ylen.p, d_ylen, size_t(B) * 4, cudaMemcpyDeviceToHost, M.stream));
-  CUDA_CHECK(cudaStreamSynchronize(M.stream));
+  M.wait_stream(/*yield=*/B >= 8);
   b->ylen.assign(M.pin_ylen.as<int>(), M.pin_ylen.as<int>() + B);
   b->ystart.resize(B);
   int64_t ny = 0;
@@ -1716,7 +1716,7 @@ void synth_download(sbv2_model* mm, sbv2_device_batch* b, float** out_samples, i
       hf2p = static_cast<int32_t*>(alloc_out(size_t(b->Ny) * 4, true));
       CUDA_CHECK(cudaMemcpyAsync(hf2p, b->f2p.p, size_t(b->Ny) * 4, cudaMemcpyDeviceToHost, M->stream));
     }
-    CUDA_CHECK(cudaStreamSynchronize(M->stream));
+    M->wait_stream(/*yield=*/b->B >= 8);
   } catch (...) {
     free_out(host);
     free_out(hdur);

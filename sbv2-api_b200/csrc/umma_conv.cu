@@ -14,8 +14,11 @@
 //
 // Per CTA: rows [t0, t0 + 128*MT) of one utterance x NB output channels, K loop over
 // (64-channel chunk, tap).
-//   warp 0   : producer — bulk copies of activation chunks (ring of A slots) and of the packed
-//              weights (ring of B stages), completion on mbarriers
+//   warp 0   : activation producer — bulk copies of activation chunks (ring of A slots), completion on mbarriers
+//   warp 18  : weight producer — bulk copies of the packed weights (ring of B stages).  Its own thread since round 2:
+//              issued from the activation producer's loop, a weight stage was only requested once the NEXT activation
+//              slot had been obtained, i.e. one round trip late whenever the activation ring was the one that blocked
+//              (few-rows GEMMs ran at one K chunk per L2 round trip: profiles/r2_launches_bert_exact_s7.csv)
 //   warp 1   : TMEM alloc + single-thread tcgen05.mma issue, MT accumulators of 128 x NB fp32
 //   warps 2-17: epilogue — tcgen05.ld, bias, residual, MRF accumulation, activation, fp16 store
 // Two CTAs fit on an SM for every decoder shape (<= 113 KB smem, <= 256 TMEM columns), so one CTA's
@@ -40,7 +43,8 @@ constexpr int MAX_ASLOTS = 8;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + 32;  // + the weight producer (last warp)
+constexpr int B_PRODUCER_WARP = 2 + NUM_EPI_WARPS;
 
 struct UmmaConvArgs {
   const __half* in;
@@ -191,14 +195,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- producer ----------------
-      uint32_t a_it = 0, b_it = 0;  // running ring counters
-      bool first = true;
+      // ---------------- activation producer ----------------
+      uint32_t a_it = 0;  // running ring counter
       uint32_t pit = 0;
-      for (int item = unit0; item < p.n_items; item += unit_step, first = false, ++pit) {
+      for (int item = unit0; item < p.n_items; item += unit_step, ++pit) {
         const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
         TRACE(0, pit);
-        const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
         auto load_a_chunk = [&](int kc) {
           const uint32_t slot = a_it % p.a_slots;
@@ -211,6 +213,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           }
           ++a_it;
         };
+        for (int kc = 0; kc < p.nkc; ++kc) load_a_chunk(kc);
+        TRACE(1, pit);
+      }
+    }
+  } else if (warp == B_PRODUCER_WARP) {
+    if (lane == 0) {
+      // ---------------- weight producer ----------------
+      uint32_t b_it = 0;  // running ring counter
+      bool first = true;
+      for (int item = unit0; item < p.n_items; item += unit_step, first = false) {
+        if (p.b_resident && !first) continue;  // resident weights are fetched once per CTA
+        const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
+        const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         auto load_b = [&](int i) {  // i-th stage load of this item
           const uint32_t st = b_it % p.nstages;
           mbar_wait(bar_be + 8 * st, ((b_it / p.nstages) & 1) ^ 1);
@@ -229,16 +244,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           }
           ++b_it;
         };
-        const bool load_w = !p.b_resident || first;
-        // consumption order is (kc, tap); keep one A chunk of lookahead ahead of the B loads
-        load_a_chunk(0);
-        int next_b = 0;
-        for (int kc = 0; kc < p.nkc; ++kc) {
-          if (kc + 1 < p.nkc) load_a_chunk(kc + 1);
-          const int last_step = (kc + 1) * p.taps - 1;  // last step that uses chunk kc
-          while (load_w && next_b < p.nloads && next_b * p.sps <= last_step) load_b(next_b++);
-        }
-        TRACE(1, pit);
+        for (int i = 0; i < p.nloads; ++i) load_b(i);
       }
     }
   } else if (warp == 1) {
@@ -597,6 +603,24 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_group
     // streaming rate (4 stages = 64 KB gave ~17 B/clk where the big decoder layers consume 32 B/clk); the activation
     // ring needs far fewer bytes in flight, three chunk slots keep one chunk of lookahead.
     const int ring_min_slots = std::max(2, std::min(L.nkc + 1, 3));
+    // Few-rows packing (N blocks <= 64, 128-row items: one sentence through DeBERTa, a batch-1 utterance): per 64-channel
+    // K chunk the activation slot (16 KB) is larger than the weight step (8 KB) and every chunk costs one L2 / HBM round
+    // trip, so the chunks in flight set the rate — K = 12288 with three slots is 64 round trips in a row
+    // (profiles/r2_launches_bert_exact_s7.csv).  There the activation ring gets the depth first.
+    const bool latency_mode = nb_max <= 64 && mt == 1 && L.nkc > 4;
+    if (latency_mode) {
+      for (int slots = std::min(MAX_ASLOTS, L.nkc + 1); slots >= ring_min_slots && !placed; --slots)
+        for (int ns = std::min(MAX_STAGES, std::max(2, L.nloads)); ns >= 2 && !placed; --ns) {
+          size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + kMisc;
+          if (sm <= size_t(SMEM_LIMIT) && (ns >= 4 || ns >= L.nloads)) {
+            L.mt = mt;
+            L.a_slots = slots;
+            L.nstages = ns;
+            L.smem = sm;
+            placed = true;
+          }
+        }
+    }
     for (int ns = std::min(MAX_STAGES, std::max(2, L.nloads)); ns >= 2 && !placed; --ns) {
       for (int slots = std::min(MAX_ASLOTS, std::max(ring_min_slots, L.nkc + 1)); slots >= ring_min_slots && !placed; --slots) {
         size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + kMisc;
