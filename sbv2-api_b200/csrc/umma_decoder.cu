@@ -156,12 +156,13 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
       std::vector<char> lf;
       for (size_t l = 0; l < w.res_c1[rb].size(); ++l) {
         PairLayer P;
-        // C = 128 pairs are fused only for k = 3 (measured: 461 vs 523 us; k = 7 / 11 stream too many weight bytes per item);
-        // C = 64, k = 11 pairs only where the MRF mean rides on the epilogue (693 vs 632 us plain, 748 vs 942 us with the
-        // mean: profiles/r1_pair_vs_unfused.log)
+        // Per-shape choice from profiles/r2_pair_vs_unfused.log (fused vs unfused, us, 32 x ~860 frames): C = 128 pairs are
+        // fused for k = 3 (426 vs 519) and k = 7 (709 vs 740) but not k = 11 (1150 vs 1019: too many weight bytes per
+        // 118-row item); C = 64, k = 11 pairs only where the MRF mean rides on the epilogue (679 vs 675 plain, 778 vs 960 with
+        // the mean); everything narrower is fused.
         const bool mrf_pair = l + 1 == w.res_c1[rb].size() && j + 1 == w.per;
         const bool want = (C <= pair_maxc && !(C == 64 && w.res_c1[rb][l].k == 11 && !mrf_pair)) ||
-                          (C == 128 && pair_maxc >= 64 && w.res_c1[rb][l].k == 3);
+                          (C == 128 && pair_maxc >= 64 && w.res_c1[rb][l].k <= 7);
         const bool f = (w.per == 1 || w.per == 3) && want && make_pair_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], w.res_c2[rb][l], &P);
         lf.push_back(f ? 1 : 0);
         lp.push_back(P);

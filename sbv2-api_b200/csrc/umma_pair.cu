@@ -26,7 +26,8 @@
 namespace sbv2 {
 namespace {
 
-constexpr int P_MAX_ASLOTS = 8, P_MAX_STAGES = 4, P_EPI_WARPS = 16, P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_MAX_ASLOTS = 8, P_MAX_STAGES = 4, P_EPI_WARPS = 16, P_THREADS = 64 + 32 * P_EPI_WARPS + 32;
+constexpr int P_B_PRODUCER_WARP = 2 + P_EPI_WARPS;  // weight stages have their own producer thread (see umma_conv.cu)
 constexpr int P_SMEM_LIMIT = 227 * 1024;
 
 struct PairArgs {
@@ -170,8 +171,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- producer: A chunks for phase 1, weight stages in MMA consumption order ----------------
-      uint32_t a_it = 0, b_it = 0;
+      // ---------------- activation producer: A chunks for phase 1 ----------------
+      uint32_t a_it = 0;
       auto load_a_item = [&](int it) {
         const PTile ti = locate_pair_item(p, tb, (int)blockIdx.x + it * (int)gridDim.x);
         const long long in_row0 = (long long)ti.pstart + ti.t0 - p.h2 - p.h1;
@@ -186,6 +187,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
           }
         }
       };
+      for (int it = 0; it < n_my; ++it) load_a_item(it);
+    }
+  } else if (warp == P_B_PRODUCER_WARP) {
+    if (lane == 0) {
+      // ---------------- weight producer: stages in MMA consumption order ----------------
+      uint32_t b_it = 0;
       auto load_b_all = [&](const __half* w) {  // all steps of one conv through the ring
         for (int i = 0; i < p.nloads; ++i, ++b_it) {
           const uint32_t st = b_it % p.nstages;
@@ -204,16 +211,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_pair_kernel(const __grid_co
         bulk_g2s(sB + wb, p.w2, wb, bar_bf);
       }
       // MMA order: P1(0), then per item it: P1(it+1), P2(it)
-      if (n_my > 0) {
-        load_a_item(0);
-        if (!p.b_resident) load_b_all(p.w1);
-      }
-      for (int it = 0; it < n_my; ++it) {
-        if (it + 1 < n_my) {
-          load_a_item(it + 1);
-          if (!p.b_resident) load_b_all(p.w1);
+      if (!p.b_resident) {
+        if (n_my > 0) load_b_all(p.w1);
+        for (int it = 0; it < n_my; ++it) {
+          if (it + 1 < n_my) load_b_all(p.w1);
+          load_b_all(p.w2);
         }
-        if (!p.b_resident) load_b_all(p.w2);
       }
     }
   } else if (warp == 1) {
