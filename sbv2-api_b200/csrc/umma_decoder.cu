@@ -140,6 +140,10 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
   // output rows).  SBV2_B200_PAIR_MAXC=0 disables fusion.
   int pair_maxc = 64;
   if (const char* e = getenv("SBV2_B200_PAIR_MAXC")) pair_maxc = atoi(e);
+  // N block of the C >= 256 ResBlock convs: 256 (one 128-row item streams the whole [256 x K] weight slab) or 128 (256-row
+  // items, two N blocks: half the weight bytes per row)
+  int wide_nb = 256;
+  if (const char* e = getenv("SBV2_B200_DEC_WIDE_NB")) wide_nb = atoi(e);
   D->pair_heights.assign(size_t(D->n_stages) + 1, {});
   int C = D->c0;
   for (int s = 0; s < D->n_stages; ++s) {
@@ -172,8 +176,8 @@ UmmaDecoder* umma_decoder_create(const DecoderHostWeights& w, sbv2_model* owner)
           l1.emplace_back();
           l2.emplace_back();
         } else {
-          l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 16));
-          l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 16));
+          l1.push_back(make_conv1d_layer(owner, w.res_c1[rb][l], w.res_dil[rb][l], 16, C >= 256 ? wide_nb : 256));
+          l2.push_back(make_conv1d_layer(owner, w.res_c2[rb][l], 1, 16, C >= 256 ? wide_nb : 256));
         }
       }
       D->c1.push_back(l1);
