@@ -76,10 +76,11 @@ struct CouplingW {
 };
 
 // Every flow / text layer is packed twice: [0] for batches (N blocks up to 256 channels, 256-row work items: fewest weight
-// bytes per row) and [1] for few rows (64-channel N blocks, 128-row items): a batch-1 call is latency-bound, its layers
-// are weight streams, and the wide packing would leave each of them to 2-12 CTAs (profiles/r2_latency_*).  Both give
-// bit-identical results: the K order of every output element is the same.
-constexpr int kSmallNb = 64;
+// bytes per row) and [1] for few rows (16-channel N blocks, 128-row items): a batch-1 call is latency-bound, its layers
+// are weight streams, and the wide packing would leave each of them to 2-12 CTAs (profiles/r2_latency_*).  An N = 16 MMA
+// issues as fast as an N = 64 one (48 cycles), so the narrowest block simply gives the most CTAs per weight stream.
+// Both packings give bit-identical results: the K order of every output element is the same.
+constexpr int kSmallNb = 16;
 constexpr int64_t kSmallFlowRows = 1024, kSmallTextRows = 512;
 struct FlowTCLayer {
   ConvLayer qkv[2], o[2], f1[2], f2[2];

@@ -202,15 +202,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
         TRACE(0, pit);
         const long long in_row0 = (long long)p.pstart_in[ti.b] + ti.t0 - p.halo_lo;
+        // Rows of the tile that can matter: the utterance's remaining rows plus the halo (rows past the utterance's end
+        // are the zero padding the last valid outputs read).  A ragged last tile — or a one-sentence DeBERTa call, 7 rows
+        // of a 128-row tile — copies only those; the rest of the slot keeps stale bytes, which only reach output rows
+        // that the epilogue discards (every output row depends on its own input rows only).
+        const uint32_t rows_ld = (uint32_t)min(RA, max(ti.len - ti.t0, 0) + p.halo_lo + p.halo_hi);
         auto load_a_chunk = [&](int kc) {
           const uint32_t slot = a_it % p.a_slots;
           mbar_wait(bar_ae + 8 * slot, ((a_it / p.a_slots) & 1) ^ 1);
-          mbar_expect_tx(bar_af + 8 * slot, slot_bytes);
-          for (int q = 0; q < planes_per_chunk; ++q) {
-            const int plane = kc * planes_per_chunk + q;
-            bulk_g2s(sA + slot_bytes * slot + (uint32_t)q * RA * 16, p.in + (size_t)plane * p.in_plane_stride + in_row0 * 8,
-                     (uint32_t)RA * 16, bar_af + 8 * slot);
-          }
+          mbar_expect_tx(bar_af + 8 * slot, (uint32_t)planes_per_chunk * rows_ld * 16);
+          if (rows_ld > 0)
+            for (int q = 0; q < planes_per_chunk; ++q) {
+              const int plane = kc * planes_per_chunk + q;
+              bulk_g2s(sA + slot_bytes * slot + (uint32_t)q * RA * 16, p.in + (size_t)plane * p.in_plane_stride + in_row0 * 8, rows_ld * 16,
+                       bar_af + 8 * slot);
+            }
           ++a_it;
         };
         for (int kc = 0; kc < p.nkc; ++kc) load_a_chunk(kc);
