@@ -10,6 +10,24 @@
 namespace sbv2 {
 namespace {
 
+// two-term fp16 split of 8 fp32 values stored as the plane blocks [h0 | h1 | h0] (umma_conv.h make_split_conv1d_layer)
+__device__ __forceinline__ void store_split8_attn(__half* base, long long blk, const float* f, float scale) {
+  uint4 o0, o1;
+  __half2* q0 = reinterpret_cast<__half2*>(&o0);
+  __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x0 = f[2 * e] * scale, x1 = f[2 * e + 1] * scale;
+    const __half2 h0 = __floats2half2_rn(x0, x1);
+    const float2 g0 = __half22float2(h0);
+    q0[e] = h0;
+    q1[e] = __floats2half2_rn(x0 - g0.x, x1 - g0.y);
+  }
+  *reinterpret_cast<uint4*>(base) = o0;
+  *reinterpret_cast<uint4*>(base + blk) = o1;
+  *reinterpret_cast<uint4*>(base + 2 * blk) = o0;
+}
+
 __global__ void embed_rows_kernel(float* h, const float* table, const int* ids, int C, int n_vocab, int64_t rows) {
   int64_t row = blockIdx.x;
   if (row >= rows) return;
@@ -88,6 +106,83 @@ __global__ void ln_planar_wide_kernel(float* h, __half* hp, __half* hp2, const f
   }
 }
 
+// Exact mode: h = LN(a + addin) (fp32 row-major, one warp per row, 8 channels per lane and iteration) and, in the same pass,
+// the split-planar operand [h0 | h1 | h0] of the GEMM that consumes h.  NV8 = C / 256.
+template <int NV8>
+__global__ void ln_split_kernel(float* out, __half* split, float split_scale, const float* a, const float* addin, const float* gamma,
+                                const float* beta, float eps, int C, PlanarSegs s) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= s.len[b]) return;
+  const size_t base = ((size_t)s.start[b] + t) * C;
+  float v[NV8][8];
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (c < C) {
+      x0 = *reinterpret_cast<const float4*>(a + base + c);
+      x1 = *reinterpret_cast<const float4*>(a + base + c + 4);
+    }
+    v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w; v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+  }
+  if (addin) {
+    float w[NV8][8];
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
+      if (c < C) {
+        y0 = *reinterpret_cast<const float4*>(addin + base + c);
+        y1 = *reinterpret_cast<const float4*>(addin + base + c + 4);
+      }
+      w[i][0] = y0.x; w[i][1] = y0.y; w[i][2] = y0.z; w[i][3] = y0.w; w[i][4] = y1.x; w[i][5] = y1.y; w[i][6] = y1.z; w[i][7] = y1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NV8; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] += w[i][e];
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += v[i][e];  // lanes past C hold zeros
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    if ((i * 32 + lane) * 8 < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
+  const size_t prow = (size_t)(s.pstart[b] + t) * 8;
+  const long long blk = (long long)(C / 8) * s.plane_stride;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c >= C) continue;
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = (v[i][e] - mean) * rstd * gamma[c + e] + beta[c + e];
+    if (out) {
+      *reinterpret_cast<float4*>(out + base + c) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(out + base + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+    if (split) store_split8_attn(split + (size_t)(c >> 3) * s.plane_stride + prow, blk, r, split_scale);
+  }
+}
+
 __global__ void scatter_rows_kernel(float* out, const float* h, int C, int S, PlanarSegs s) {
   const int b = blockIdx.y, t = blockIdx.x;
   float4* dst = reinterpret_cast<float4*>(out + ((size_t)b * S + t) * C);
@@ -121,9 +216,12 @@ __device__ __forceinline__ void from_f32(__half& d, float v) { d = __float2half_
 // F32 = true ("exact" mode, SBV2_B200_BERT=exact): q|k|v fp32 row-major [rows, 3*heads*64] in, fp32 row-major context
 // [rows, heads*64] out, everything staged in fp32 — the features feed ceil() in the synthesizer (tts_util.rs:120-154 ->
 // model.rs:66-68), and fp16 storage between the GEMMs alone costs 5e-4 relative.
+// F32 with split_scale > 0: the context is written as the split-planar operand [h0 | h1 | h0] of the output projection
+// (out_v = __half*, blocks of heads * 8 planes) instead of fp32 row-major — no separate split pass.
 template <bool F32>
 __global__ void __launch_bounds__(256) deberta_attention_kernel(void* out_v, const void* qkv_v, const float* pos_k_t, const float* pos_q_t,
-                                                                int n_pos, const int* bucket_idx, int max_rel, int heads, PlanarSegs s) {
+                                                                int n_pos, const int* bucket_idx, int max_rel, int heads, PlanarSegs s,
+                                                                float split_scale) {
   using TS = typename std::conditional<F32, float, __half>::type;
   __half* out = static_cast<__half*>(out_v);
   const __half* qkv = static_cast<const __half*>(qkv_v);
@@ -341,6 +439,11 @@ __global__ void __launch_bounds__(256) deberta_attention_kernel(void* out_v, con
   for (int i = tid; i < BQ * DP; i += 256) {
     const int r = i % BQ, pl = i / BQ;
     if (q0 + r >= len) continue;
+    if (F32 && split_scale > 0.f) {
+      store_split8_attn(out + (size_t)(h * DP + pl) * s.plane_stride + (pbase + q0 + r) * 8, (long long)heads * DP * s.plane_stride,
+                        Os + r * BD + pl * 8, split_scale);
+      continue;
+    }
     if (F32) {
       float4* dst = reinterpret_cast<float4*>(out32 + (row32 + q0 + r) * (size_t)HD + h * BD + pl * 8);
       const float* o8 = Os + r * BD + pl * 8;
@@ -382,6 +485,20 @@ void launch_ln_planar_wide(const LaunchCtx& ctx, float* h, __half* hp, __half* h
   POST_LAUNCH(ctx);
 }
 
+bool ln_split_supported(int C) { return C % 8 == 0 && C >= 8 && C <= 1024; }
+
+void launch_ln_split(const LaunchCtx& ctx, float* out, __half* split, float split_scale, const float* a, const float* addin,
+                     const float* gamma, const float* beta, float eps, int C, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (!ln_split_supported(C)) fail(SBV2_ERR_UNSUPPORTED, "ln_split: hidden size must be a multiple of 8 and <= 1024");
+  dim3 grid((s.max_len + 7) / 8, s.n);
+  if (C <= 256) ln_split_kernel<1><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  else if (C <= 512) ln_split_kernel<2><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  else if (C <= 768) ln_split_kernel<3><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  else ln_split_kernel<4><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  POST_LAUNCH(ctx);
+}
+
 void launch_scatter_rows(const LaunchCtx& ctx, float* out, const float* h, int C, int S, const PlanarSegs& s) {
   if (s.n <= 0 || S <= 0) return;
   dim3 grid(S, s.n);
@@ -397,19 +514,23 @@ void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __hal
   static PerDeviceOnce attr_once;
   attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
   dim3 grid((s.max_len + BQ - 1) / BQ, heads, s.n);
-  deberta_attention_kernel<false><<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s);
+  deberta_attention_kernel<false><<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s, 0.f);
   POST_LAUNCH(ctx);
 }
 
-void launch_deberta_attention_f32(const LaunchCtx& ctx, float* ctx_out, const float* qkv, const float* pos_k_t, const float* pos_q_t,
-                                  int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s) {
+void launch_deberta_attention_f32(const LaunchCtx& ctx, float* ctx_out, __half* ctx_split, float split_scale, const float* qkv,
+                                  const float* pos_k_t, const float* pos_q_t, int n_pos, const int* bucket_idx, int max_rel, int heads,
+                                  int head_dim, const PlanarSegs& s) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (head_dim != BD) fail(SBV2_ERR_UNSUPPORTED, "deberta attention: head_dim must be 64");
   size_t smem = sizeof(float) * (size_t)(BD * PQ + BD * PK + BD * PPT) + sizeof(float) * (size_t)(BK * BD + BQ * PCP + BK * PCP);
   static PerDeviceOnce attr_once;
   attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
   dim3 grid((s.max_len + BQ - 1) / BQ, heads, s.n);
-  deberta_attention_kernel<true><<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s);
+  if (ctx_split)
+    deberta_attention_kernel<true><<<grid, 256, smem, ctx.stream>>>(ctx_split, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s, split_scale);
+  else
+    deberta_attention_kernel<true><<<grid, 256, smem, ctx.stream>>>(ctx_out, qkv, pos_k_t, pos_q_t, n_pos, bucket_idx, max_rel, heads, s, 0.f);
   POST_LAUNCH(ctx);
 }
 

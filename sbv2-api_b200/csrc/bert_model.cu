@@ -324,46 +324,50 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     // ---- exact mode: fp32 row-major activations, two-term fp16 operand splits for every GEMM -------------------------
     M.x_emb.ensure(size_t(n) * H * 4);
     M.x_qkv.ensure(size_t(n) * 3 * H * 4);
-    M.x_ctx.ensure(size_t(n) * H * 4);
-    M.x_f1.ensure(size_t(n) * M.inter * 4);
     M.x_y.ensure(size_t(n) * H * 4);
-    M.x_split.ensure(R * 3 * size_t(M.max_cin) * 2);
+    // split-planar operands [h0 | h1 | h0]: written by the kernel that produces the values (LayerNorm, attention, the FFN's
+    // first GEMM), never by a separate pass.  sp_e: embeddings (layer 0 and the ConvLayer read it), sp_a: the residual
+    // stream after a LayerNorm, sp_b: attention context, sp_c: gelu(intermediate).
+    M.x_split.ensure(R * 3 * size_t(H) * 2 * 3 + R * 3 * size_t(M.inter) * 2);
     M.outd.ensure(out_elems * 4);
     float* h = M.h.as<float>();
     float* emb = M.x_emb.as<float>();
     float* qkv = M.x_qkv.as<float>();
-    float* ctxb = M.x_ctx.as<float>();
-    float* f1 = M.x_f1.as<float>();
     float* y = M.x_y.as<float>();
-    __half* split = M.x_split.as<__half>();
-    launch_zero_gaps(ctx, split, 3 * M.max_cin, G, batch);  // the splits only ever write sequence rows (k = 3 ConvLayer halo)
-    auto gemm = [&](const ConvLayer& L, const float* in, int cin, float* out, int cout, int act) {
-      launch_split_planar(ctx, split, in, cin, cin, bg.d_ystart, G, batch, 2, L.in_scale);
+    __half* sp_e = M.x_split.as<__half>();
+    __half* sp_a = sp_e + R * 3 * size_t(H);
+    __half* sp_b = sp_a + R * 3 * size_t(H);
+    __half* sp_c = sp_b + R * 3 * size_t(H);
+    const float sc = M.layers[0].qkv.in_scale;  // the same for every split layer
+    if (M.has_conv) launch_zero_gaps(ctx, sp_e, 3 * H, G, batch);  // k = 3 ConvLayer halo; the GEMMs have none
+    auto gemm = [&](const ConvLayer& L, const __half* in, float* out, int cout, __half* out_split, int act) {
       ConvCall c;
-      c.in = split;
+      c.in = in;
       c.rm_out = out;
       c.rm_ld = cout;
       c.rm_start = bg.d_ystart;
+      c.split_out = out_split;
+      c.split_scale = sc;
       c.act_out = act;
       launch_umma(ctx, L, G, G, c, batch);
     };
     launch_embed_rows(ctx, h, M.word_emb, M.ids.as<int>(), H, M.vocab, n);
-    launch_layernorm(ctx, emb, h, nullptr, nullptr, M.emb_g, M.emb_b, M.eps, ACT_NONE, H, int(n));
+    launch_ln_split(ctx, emb, sp_e, sc, h, nullptr, M.emb_g, M.emb_b, M.eps, H, ps);
     const bool small = n <= kSmallTokens;
     for (int l = 0; l < M.n_run; ++l) {
       const BertLayer& B = M.layers[l];
       const float* in = l == 0 ? emb : h;
-      gemm(small ? B.qkv_s : B.qkv, in, H, qkv, 3 * H, ACT_NONE);
-      launch_deberta_attention_f32(ctx, ctxb, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
-      gemm(small ? B.o_s : B.o, ctxb, H, y, H, ACT_NONE);
-      launch_layernorm(ctx, h, in, y, nullptr, B.ln1_g, B.ln1_b, M.eps, ACT_NONE, H, int(n));
-      gemm(small ? B.f1_s : B.f1, h, H, f1, M.inter, ACT_GELU);
-      gemm(small ? B.f2_s : B.f2, f1, M.inter, y, H, ACT_NONE);
-      launch_layernorm(ctx, h, h, y, nullptr, B.ln2_g, B.ln2_b, M.eps, ACT_NONE, H, int(n));
+      gemm(small ? B.qkv_s : B.qkv, l == 0 ? sp_e : sp_a, qkv, 3 * H, nullptr, ACT_NONE);
+      launch_deberta_attention_f32(ctx, nullptr, sp_b, sc, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+      gemm(small ? B.o_s : B.o, sp_b, y, H, nullptr, ACT_NONE);
+      launch_ln_split(ctx, h, sp_a, sc, in, y, B.ln1_g, B.ln1_b, M.eps, H, ps);
+      gemm(small ? B.f1_s : B.f1, sp_a, nullptr, M.inter, sp_c, ACT_GELU);
+      gemm(small ? B.f2_s : B.f2, sp_c, y, H, nullptr, ACT_NONE);
+      launch_ln_split(ctx, h, sp_a, sc, h, y, B.ln2_g, B.ln2_b, M.eps, H, ps);
       if (l == 0 && M.has_conv) {
         // ConvLayer: LN(layer0_out + gelu(conv(embeddings)))
-        gemm(small ? M.conv_s : M.conv, emb, H, y, H, ACT_GELU);
-        launch_layernorm(ctx, h, h, y, nullptr, M.conv_g, M.conv_b, M.eps, ACT_NONE, H, int(n));
+        gemm(small ? M.conv_s : M.conv, sp_e, y, H, nullptr, ACT_GELU);
+        launch_ln_split(ctx, h, sp_a, sc, h, y, M.conv_g, M.conv_b, M.eps, H, ps);
       }
     }
     launch_scatter_rows(ctx, M.outd.as<float>(), h, H, int(S), ps);

@@ -202,8 +202,14 @@ void launch_embed_rows(const LaunchCtx& ctx, float* h, const float* table, const
 void launch_deberta_attention(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const float* pos_k_t, const float* pos_q_t,
                               int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
 // "exact" mode: the same kernel on fp32 row-major q|k|v [rows, 3*heads*64] -> fp32 row-major context [rows, heads*64]
-void launch_deberta_attention_f32(const LaunchCtx& ctx, float* ctx_out, const float* qkv, const float* pos_k_t, const float* pos_q_t,
-                                  int n_pos, const int* bucket_idx, int max_rel, int heads, int head_dim, const PlanarSegs& s);
+// ctx_split != null: the context goes out as the split-planar operand [h0 | h1 | h0] (scaled by split_scale) instead
+void launch_deberta_attention_f32(const LaunchCtx& ctx, float* ctx_out, __half* ctx_split, float split_scale, const float* qkv,
+                                  const float* pos_k_t, const float* pos_q_t, int n_pos, const int* bucket_idx, int max_rel, int heads,
+                                  int head_dim, const PlanarSegs& s);
+// out = LN(a + addin) (fp32 row-major [rows, C], out optional) and the split-planar operand of the consuming GEMM in one pass
+bool ln_split_supported(int C);
+void launch_ln_split(const LaunchCtx& ctx, float* out, __half* split, float split_scale, const float* a, const float* addin,
+                     const float* gamma, const float* beta, float eps, int C, const PlanarSegs& s);
 // tensor-core version for sequences of at most 128 tokens (bert_attention_tc.cu); pos_*_p: fp16 [heads][D/8][n_pos][8]
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len);
 void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,

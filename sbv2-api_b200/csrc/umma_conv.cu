@@ -87,6 +87,9 @@ struct UmmaConvArgs {
   float rm_scale;       // accumulator scale of the row-major epilogue
   int rm_ld;
   const int* rm_start;
+  __half* split_out;    // the row-major epilogue's values as a split-planar operand (geometry of `out`), or null
+  int split_npl;        // planes per split block (= output channels / 8)
+  float split_scale;    // the consuming split layer's in_scale
   long long* trace;  // debug: [grid][64 items][8 events] clock64 stamps, or null
 };
 
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     const int wq = warp & 3;           // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;  // NUM_EPI_WARPS/4 warps per quarter split the work items
     const int etid = threadIdx.x - 64;
-    const bool wide = (p.nb % 32 == 0) && p.accum_mode == UACC_NONE && p.has_res != 3 && p.rm_out == nullptr;
+    const bool wide = !ROWMAJOR && (p.nb % 32 == 0) && p.accum_mode == UACC_NONE && p.has_res != 3;
     const int nch = wide ? 32 : 16;
     const int items_per_acc = p.nb / nch;
     const int n_sub = p.mt * items_per_acc;
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
         const int cg = ti.nblk * p.nb + c0;
         if (ROWMAJOR) {
-          epilogue_item_rm(p, taddr, valid, (long long)p.rm_start[ti.b] + t, cg, bias + c0);
+          epilogue_item_rm(p, taddr, valid, p.rm_out != nullptr ? (long long)p.rm_start[ti.b] + t : 0, orow, cg, bias + c0);
         } else if (p.accum_mode != UACC_NONE) {
           if (p.has_res) epilogue_item<16, true, 1>(p, taddr, valid, orow, cg, bias + c0);
           else epilogue_item<16, true, 0>(p, taddr, valid, orow, cg, bias + c0);
@@ -837,6 +840,9 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.rm_scale = L.out_scale;
   a.rm_ld = c.rm_ld;
   a.rm_start = c.rm_start;
+  a.split_out = c.split_out;
+  a.split_npl = L.cout / 8;
+  a.split_scale = c.split_scale;
   a.trace = g_trace;
   if (gi.n_tiles[slot] <= 0) return;
   static int num_sms = 0;
@@ -863,7 +869,7 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * L.n_nblk * L.n_groups;  // cluster items
   dim3 grid(std::min(a.n_items, num_sms / nc) * nc);
   void (*kernel)(UmmaConvArgs) = nullptr;
-  switch ((c.gate_half > 0 ? 1 : 0) | (nc > 1 ? 2 : 0) | (c.rm_out != nullptr ? 4 : 0)) {
+  switch ((c.gate_half > 0 ? 1 : 0) | (nc > 1 ? 2 : 0) | ((c.rm_out != nullptr || c.split_out != nullptr) ? 4 : 0)) {
     case 0: kernel = umma_conv_kernel<0>; break;
     case 1: kernel = umma_conv_kernel<1>; break;
     case 2: kernel = umma_conv_kernel<2>; break;

@@ -129,6 +129,10 @@ struct ConvCall {
   float* rm_out = nullptr;
   int rm_ld = 0;
   const int* rm_start = nullptr;
+  // and / or the same values (bias and activation applied) written as the split-planar operand [h0 | h1 | h0] of the next
+  // split layer (geometry `go`, cout / 8 planes per block): fuses launch_split_planar into the producing GEMM
+  __half* split_out = nullptr;
+  float split_scale = 16.f;
 };
 void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt);
 void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, int n_utt);

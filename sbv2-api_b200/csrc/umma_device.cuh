@@ -293,25 +293,63 @@ __device__ __forceinline__ void epilogue_gate(const Args& p, uint32_t taddr_t, u
   }
 }
 
-// fp32 row-major epilogue of 16 accumulator columns of one row: out[row][co0 .. co0+15] = act(acc + bias)
+// Two-term fp16 split of 8 fp32 values (x * scale = h0 + h1, make_split_conv1d_layer) stored as the three plane blocks
+// [h0 | h1 | h0] a split layer reads: `base` points at plane p of block 0, `blk` = elements between blocks.
+__device__ __forceinline__ void store_split8(__half* base, long long blk, const float* f, float scale) {
+  uint4 o0, o1;
+  __half2* q0 = reinterpret_cast<__half2*>(&o0);
+  __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x0 = f[2 * e] * scale, x1 = f[2 * e + 1] * scale;  // power of two: exact
+    const __half2 h0 = __floats2half2_rn(x0, x1);
+    const float2 g0 = __half22float2(h0);
+    q0[e] = h0;
+    q1[e] = __floats2half2_rn(x0 - g0.x, x1 - g0.y);
+  }
+  *reinterpret_cast<uint4*>(base) = o0;
+  *reinterpret_cast<uint4*>(base + blk) = o1;
+  *reinterpret_cast<uint4*>(base + 2 * blk) = o0;
+}
+
+// fp32 row-major epilogue of 16 accumulator columns of one row: out[row][co0 .. co0+15] = act(acc + bias); and / or the
+// same values as the split-planar operand of the next split layer (p.split_out: no separate split pass, no fp32 round trip)
 template <class Args>
-__device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, bool valid, long long rm_row, int co0_global,
-                                                 const float* bias) {
+__device__ __forceinline__ void epilogue_item_rm(const Args& p, uint32_t taddr, bool valid, long long rm_row, long long prow,
+                                                 int co0_global, const float* bias) {
   uint32_t v[16];
   tc_ld16(taddr, v);
   tc_wait_ld();
   if (!valid) return;
-  float* dst = p.rm_out + rm_row * p.rm_ld + co0_global;
   const bool relu = p.act_out == ACT_RELU, gelu = p.act_out == ACT_GELU;
+  float f[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
     const float sc = p.rm_scale;  // power of two
-    float4 f = make_float4(__uint_as_float(v[4 * q]) * sc + b.x, __uint_as_float(v[4 * q + 1]) * sc + b.y,
-                           __uint_as_float(v[4 * q + 2]) * sc + b.z, __uint_as_float(v[4 * q + 3]) * sc + b.w);
-    if (relu) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
-    if (gelu) f = make_float4(act_apply(f.x, ACT_GELU), act_apply(f.y, ACT_GELU), act_apply(f.z, ACT_GELU), act_apply(f.w, ACT_GELU));
-    *reinterpret_cast<float4*>(dst + 4 * q) = f;
+    f[4 * q] = __uint_as_float(v[4 * q]) * sc + b.x;
+    f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * sc + b.y;
+    f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * sc + b.z;
+    f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * sc + b.w;
+  }
+  if (relu) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+  }
+  if (gelu) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = act_apply(f[e], ACT_GELU);
+  }
+  if (p.rm_out != nullptr) {
+    float* dst = p.rm_out + rm_row * p.rm_ld + co0_global;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+  }
+  if (p.split_out != nullptr) {
+    const long long blk = (long long)p.split_npl * p.out_plane_stride;
+    __half* base = p.split_out + (long long)(co0_global >> 3) * p.out_plane_stride + prow * 8;
+    store_split8(base, blk, f, p.split_scale);
+    store_split8(base + p.out_plane_stride, blk, f + 8, p.split_scale);
   }
 }
 
