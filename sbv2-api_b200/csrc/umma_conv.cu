@@ -23,10 +23,13 @@
 //   warps 2-17: epilogue — tcgen05.ld, bias, residual, MRF accumulation, activation, fp16 store
 // Two CTAs fit on an SM for every decoder shape (<= 113 KB smem, <= 256 TMEM columns), so one CTA's
 // epilogue overlaps the other's MMA phase.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
+#include <unordered_map>
 
 #include "kernels.h"
 #include "model.h"
@@ -47,6 +50,8 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + 32;  // + the weight produ
 constexpr int B_PRODUCER_WARP = 2 + NUM_EPI_WARPS;
 
 struct UmmaConvArgs {
+  CUtensorMap tmap;            // `in` as a 3-D tensor {8, rows, planes}, box {8, RA, kc / 8} (use_tmap), 64-byte aligned
+  int use_tmap;                // activation chunks by one tensor-map TMA request instead of kc / 8 bulk copies
   const __half* in;
   long long in_plane_stride;   // elements between planes of `in`
   __half* out;
@@ -212,7 +217,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const uint32_t rows_ld = (uint32_t)min(RA, max(ti.len - ti.t0, 0) + p.halo_lo + p.halo_hi);
         auto load_a_chunk = [&](int kc) {
           const uint32_t slot = a_it % p.a_slots;
-          mbar_wait(bar_ae + 8 * slot, ((a_it / p.a_slots) & 1) ^ 1);
+          mbar_wait_poll(bar_ae + 8 * slot, ((a_it / p.a_slots) & 1) ^ 1);
+          if (p.use_tmap) {
+            mbar_expect_tx(bar_af + 8 * slot, slot_bytes);  // the whole box, rows past the buffer's end are zero-filled
+            tma_load_3d(sA + slot_bytes * slot, &p.tmap, 0, (int)in_row0, kc * planes_per_chunk, bar_af + 8 * slot);
+            ++a_it;
+            return;
+          }
           mbar_expect_tx(bar_af + 8 * slot, (uint32_t)planes_per_chunk * rows_ld * 16);
           if (rows_ld > 0)
             for (int q = 0; q < planes_per_chunk; ++q) {
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         auto load_b = [&](int i) {  // i-th stage load of this item
           const uint32_t st = b_it % p.nstages;
-          mbar_wait(bar_be + 8 * st, ((b_it / p.nstages) & 1) ^ 1);
+          mbar_wait_poll(bar_be + 8 * st, ((b_it / p.nstages) & 1) ^ 1);
           const int first_step = i * p.sps;
           const int nsteps = min(p.sps, p.total_steps - first_step);
           const uint32_t bytes = step_bytes * nsteps;
@@ -278,23 +289,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0, it = 0;
         for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
           const uint32_t buf = it & 1;
-          mbar_wait(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
+          mbar_wait_poll(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
           tc_fence_after();
           if (lane == 0) TRACE(2, it);
           const uint32_t tmem_acc = tmem_base + buf * acc_cols;
           const int grp = (item % (p.n_nblk * p.n_groups)) / p.n_nblk;
           int step = 0, si = 0;
           for (int kc = 0; kc < p.nkc; ++kc) {
-            mbar_wait(bar_af + 8 * a_slot_i, a_par);
+            mbar_wait_poll(bar_af + 8 * a_slot_i, a_par);
             if (kc == 0 && lane == 0) TRACE(3, it);
             const uint64_t a_chunk = a_desc0 + ((sA - cta_win + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
             for (int tap = 0; tap < p.taps; ++tap, ++step) {
               uint32_t b_addr;
               if (p.b_resident) {
-                if (it == 0 && step == 0) mbar_wait(bar_bf, 0);
+                if (it == 0 && step == 0) mbar_wait_poll(bar_bf, 0);
                 b_addr = sB + step_bytes * step;
               } else {
-                if (si == 0) mbar_wait(bar_bf + 8 * b_st, b_par);
+                if (si == 0) mbar_wait_poll(bar_bf + 8 * b_st, b_par);
                 b_addr = sB + stage_bytes * b_st + step_bytes * si;
               }
               const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
@@ -666,6 +677,65 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_group
 
 int mt_slot(int mt) { return mt == 1 ? 0 : (mt == 2 ? 1 : (mt == 4 ? 2 : (mt == 8 ? 3 : 4))); }
 
+// ---- tensor maps for the activation operand ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+struct TmapKey {
+  const void* ptr;
+  long long rows_tot;
+  int planes, box_rows, box_planes;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows_tot == o.rows_tot && planes == o.planes && box_rows == o.box_rows && box_planes == o.box_planes;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (long long v : {k.rows_tot, (long long)k.planes, (long long)k.box_rows, (long long)k.box_planes}) h = h * 1000003u ^ std::hash<long long>()(v);
+    return h;
+  }
+};
+// planar fp16 buffer [planes][rows_tot][8] as {8 halves, rows_tot, planes}; box {8, box_rows, box_planes}.  Encoding costs
+// a few microseconds of host time, so the maps are cached by (buffer, geometry, box); a map holds no device state.
+bool activation_tmap(const __half* base, long long rows_tot, int planes, int box_rows, int box_planes, CUtensorMap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || box_rows > 256 || box_planes > 256 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{base, rows_tot, planes, box_rows, box_planes};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  const cuuint64_t dims[3] = {8, (cuuint64_t)rows_tot, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {16, (cuuint64_t)rows_tot * 16};
+  const cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return true;
+}
+
 void set_smem_attr() {
   static PerDeviceOnce attr_once;
   attr_once.run([&] {
@@ -786,6 +856,17 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   UmmaConvArgs a;
   a.in = c.in;
   a.in_plane_stride = gi.rows_tot * 8;
+  {
+    // one tensor-map request per activation chunk when the tile (rows incl. halo) fits a TMA box; SBV2_B200_TMAP=0 keeps
+    // the per-plane bulk copies
+    static int tmap_on = -1;
+    if (tmap_on < 0) {
+      const char* e = getenv("SBV2_B200_TMAP");
+      tmap_on = !(e && e[0] == '0');
+    }
+    const int ra = 128 * L.mt + L.halo_lo + L.halo_hi;
+    a.use_tmap = c.tmap && tmap_on && ra <= 256 && activation_tmap(c.in, gi.rows_tot, L.cin / 8, ra, L.kc / 8, &a.tmap) ? 1 : 0;
+  }
   a.out = c.out;
   a.out_plane_stride = go.rows_tot * 8;
   a.residual = c.residual;

@@ -31,6 +31,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity), "r"(0x989680u)  // suspend-time hint (ns): a waiting warp sleeps in hardware instead of re-polling
       : "memory");
 }
+// The same without the suspend-time hint, for the single-thread roles (producers, MMA issuer): a hinted wait that
+// actually blocks costs ~0.7 us to wake up, and in few-rows GEMMs the producer blocks on every K chunk (every K = 3072
+// GEMM of a one-sentence DeBERTa call took 37 us whatever its grid: 48 chunks x 0.77 us).  One polling thread per role
+// does not compete with the epilogue warps the way sixteen polling warps did.
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
@@ -56,6 +73,16 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(cta_mask)
+               : "memory");
+}
+// One activation chunk (P planes x R rows x 16 bytes) as ONE tensor-map TMA request: the planar buffer is described as a
+// 3-D tensor {8 halves, rows, planes}, the box lands in shared memory as [plane][row][16 B] — the slot layout.  The
+// per-plane bulk copies it replaces cost one TMA request each, and the TMA unit accepts only ~10 requests per
+// microsecond: with 8 planes per 64-channel chunk that was 0.7 us per chunk whatever its size, the bound of every
+// few-rows GEMM and of the 128-row-tile GEMMs (DeBERTa, C = 256 decoder convs).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
