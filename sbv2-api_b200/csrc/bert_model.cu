@@ -157,6 +157,12 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
     hc.b = f32(n + ".bias");
     return hc;
   };
+  // N block of the batch packing.  256 (one CTA per 128 x 256 tile).  With SBV2_B200_BERT_NB=128 two adjacent blocks form the
+  // N = 256 of one CTA-pair MMA (cta_group::2, ConvCall::pair, SBV2_B200_PAIR2=1) — built, bit-identical, and measured
+  // slower: 32 x 128 tokens fp16 mode 6.27 ms (256, single CTA) / 8.48 ms (128, single) / 9.12 ms (128, pairs); exact mode
+  // 23.1 / 29.7 / 32.2 ms (tools/bert_pair_ab.py, profiles/r2_cta_pair_ab.log)
+  int big_nb = 256;
+  if (const char* e = getenv("SBV2_B200_BERT_NB")) big_nb = atoi(e);
   DBuf wt;
   wt.stream = M->stream;
   const int H = M->hidden;
@@ -220,10 +226,10 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
     const HostConv od = host_linear(lp + ".attention.output.dense"), f2 = host_linear(lp + ".output.dense");
     HostConv f1 = host_linear(lp + ".intermediate.dense");
     M->inter = f1.d0;
-    B.qkv = layer(qkv, 256);
-    B.o = layer(od, 256);
-    B.f1 = layer(f1, 256);
-    B.f2 = layer(f2, 256);
+    B.qkv = layer(qkv, big_nb);
+    B.o = layer(od, big_nb);
+    B.f1 = layer(f1, big_nb);
+    B.f2 = layer(f2, big_nb);
     B.qkv_s = layer(qkv, kSmallNb);
     B.o_s = layer(od, kSmallNb);
     B.f1_s = layer(f1, kSmallNb);

@@ -147,7 +147,12 @@ __device__ __forceinline__ TileInfo locate_item(const UmmaConvArgs& p, int item,
 // registers per thread at 576 threads: the epilogue is the part that spills first).
 template <int VARIANT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_constant__ UmmaConvArgs p) {
-  constexpr bool GATE = (VARIANT & 1) != 0, CLUSTER = (VARIANT & 2) != 0, ROWMAJOR = (VARIANT & 4) != 0;
+  constexpr bool GATE = (VARIANT & 1) != 0, ROWMAJOR = (VARIANT & 4) != 0;
+  // bit 3: CTA pair (cta_group::2): clusters of two CTAs, ONE M = 256 MMA per K step issued by rank 0, each CTA holding
+  // its own 128-row activation tile and half (by N) of every weight stage.  Uses the cluster item mapping; no multicast.
+  constexpr bool PAIR2 = (VARIANT & 8) != 0;
+  constexpr bool CLUSTER = (VARIANT & 2) != 0 || PAIR2;
+  constexpr bool MCAST = (VARIANT & 2) != 0 && !PAIR2;
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index made provably warp-uniform so that role branches are uniform and the MMA
   // descriptors stay in uniform registers (UTCHMMA takes UR operands; R2UR per MMA is slow)
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   const int RA = TM + p.halo_lo + p.halo_hi;
   const int planes_per_chunk = p.kc / 8;
   const uint32_t slot_bytes = (uint32_t)planes_per_chunk * RA * 16;
-  const uint32_t step_bytes = (uint32_t)p.nb * p.kc * 2;
+  const uint32_t step_bytes = (uint32_t)(PAIR2 ? p.nb / 2 : p.nb) * p.kc * 2;  // per CTA: a pair CTA holds half of N
   const uint32_t stage_bytes = step_bytes * p.sps;
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + ((slot_bytes * p.a_slots + 127u) & ~127u);
@@ -168,6 +173,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sA));
   float* bias_s = reinterpret_cast<float*>(smem + (sBar - sA) + 320);  // [2][NB] (after 36 barriers + the TMEM slot)
   const int acc_cols = p.mt * p.nb;  // TMEM columns of one accumulator set
+  // pair mode, leader side: "the peer's slot / stage / accumulator set is ready" (arrivals come from the peer CTA)
+  const uint32_t bar_paf = sBar + 3072, bar_pbf = bar_paf + 8 * MAX_ASLOTS, bar_pacce = bar_pbf + 8 * MAX_STAGES;
   const int nc = CLUSTER ? p.cluster : 1;
   const int rank = CLUSTER ? (int)cluster_ctarank() : 0;
   const int unit0 = (int)blockIdx.x / nc, unit_step = (int)gridDim.x / nc;  // this CTA's (cluster's) first item and stride
@@ -180,7 +187,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     }
     for (int i = 0; i < p.nstages; ++i) {
       mbar_init(bar_bf + 8 * i, 1);
-      mbar_init(bar_be + 8 * i, nc);  // a weight stage is free again when every CTA of the cluster has consumed it
+      mbar_init(bar_be + 8 * i, MCAST ? nc : 1);  // multicast: free again when every CTA of the cluster has consumed it
+    }
+    if (PAIR2) {
+      for (int i = 0; i < p.a_slots; ++i) mbar_init(bar_paf + 8 * i, 1);
+      for (int i = 0; i < p.nstages; ++i) mbar_init(bar_pbf + 8 * i, 1);
+      for (int i = 0; i < 2; ++i) mbar_init(bar_pacce + 8 * i, NUM_EPI_WARPS);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accf + 8 * i, 1);
@@ -189,8 +201,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR2) {  // both CTAs of the pair, same warp, same shared-memory offset for the result
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -245,7 +262,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       for (int item = unit0; item < p.n_items; item += unit_step, first = false) {
         if (p.b_resident && !first) continue;  // resident weights are fetched once per CTA
         const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
-        const __half* wbase = p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
+        // pair mode: the layer is packed in N blocks of nb / 2; this CTA streams block 2 * nblk + rank
+        const __half* wbase = PAIR2 ? p.w + (size_t)((ti.grp * p.n_nblk + ti.nblk) * 2 + rank) * p.total_steps * (step_bytes / 2)
+                                    : p.w + (size_t)(ti.grp * p.n_nblk + ti.nblk) * p.total_steps * (step_bytes / 2);
         auto load_b = [&](int i) {  // i-th stage load of this item
           const uint32_t st = b_it % p.nstages;
           mbar_wait_poll(bar_be + 8 * st, ((b_it / p.nstages) & 1) ^ 1);
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           const int nsteps = min(p.sps, p.total_steps - first_step);
           const uint32_t bytes = step_bytes * nsteps;
           mbar_expect_tx(bar_bf + 8 * st, bytes);
-          if (CLUSTER) {
+          if (MCAST) {
             // this CTA's 1/nc of the stage goes to every CTA of the cluster (all of them expect the whole stage)
             const uint32_t slice = bytes / (uint32_t)nc;
             bulk_g2s_multicast(sB + stage_bytes * st + (uint32_t)rank * slice,
@@ -275,8 +294,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       const int k16_per_chunk = p.kc / 16;
       const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
       const uint64_t a_desc0 = desc_hi | ((uint64_t)((uint32_t)RA & 0x3FFF) << 16);    // LBO = RA*16 B
-      const uint64_t b_desc0 = desc_hi | ((uint64_t)((uint32_t)p.nb & 0x3FFF) << 16);  // LBO = NB*16 B
-      const uint32_t a_kstep = 2u * (uint32_t)RA, b_kstep = 2u * (uint32_t)p.nb;       // two planes per K=16 step (16-B units)
+      const uint32_t nb_cta = PAIR2 ? (uint32_t)p.nb / 2 : (uint32_t)p.nb;              // weight rows (N) in this CTA's shared memory
+      const uint64_t b_desc0 = desc_hi | ((uint64_t)(nb_cta & 0x3FFF) << 16);           // LBO = nb_cta*16 B
+      const uint32_t a_kstep = 2u * (uint32_t)RA, b_kstep = 2u * nb_cta;                // two planes per K=16 step (16-B units)
       const uint32_t nb_u = (uint32_t)p.nb, idesc = p.idesc;
       // In a cluster launch the shared-window address of CTA rank r carries r in bits 24+ (0x0r000400 on sm_100); the
       // matrix descriptor's 14-bit start-address field is CTA-local, so strip the window base before it is added in.
@@ -287,9 +307,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       auto run = [&](auto mtk) {
         constexpr int MT = decltype(mtk)::mt, K16 = decltype(mtk)::k16;
         uint32_t a_slot_i = 0, a_par = 0, b_st = 0, b_par = 0, it = 0;
+        if (PAIR2 && rank != 0) {
+          // ---- peer CTA of a pair: no MMAs here.  This warp relays "my slot / stage has landed" to the leader, in the
+          // order the leader consumes them; slots, stages and accumulators are released by the leader's multicast commits.
+          for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
+            int step = 0, si = 0;
+            for (int kc = 0; kc < p.nkc; ++kc) {
+              mbar_wait_poll(bar_af + 8 * a_slot_i, a_par);
+              if (lane == 0) mbar_arrive_remote(bar_paf + 8 * a_slot_i, 0);
+              for (int tap = 0; tap < p.taps; ++tap, ++step) {
+                if (p.b_resident) {
+                  if (it == 0 && step == 0) {
+                    mbar_wait_poll(bar_bf, 0);
+                    if (lane == 0) mbar_arrive_remote(bar_pbf, 0);
+                  }
+                } else {
+                  if (si == 0) {
+                    mbar_wait_poll(bar_bf + 8 * b_st, b_par);
+                    if (lane == 0) mbar_arrive_remote(bar_pbf + 8 * b_st, 0);
+                  }
+                  ++si;
+                  if (si == p.sps || step == p.total_steps - 1) {
+                    si = 0;
+                    if (++b_st == (uint32_t)p.nstages) {
+                      b_st = 0;
+                      b_par ^= 1;
+                    }
+                  }
+                }
+              }
+              if (++a_slot_i == (uint32_t)p.a_slots) {
+                a_slot_i = 0;
+                a_par ^= 1;
+              }
+            }
+          }
+          return;
+        }
         for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
           const uint32_t buf = it & 1;
           mbar_wait_poll(bar_acce + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
+          if (PAIR2) mbar_wait_poll_cluster(bar_pacce + 8 * buf, ((it >> 1) & 1) ^ 1);  // ... and so has the peer's
           tc_fence_after();
           if (lane == 0) TRACE(2, it);
           const uint32_t tmem_acc = tmem_base + buf * acc_cols;
@@ -297,26 +355,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           int step = 0, si = 0;
           for (int kc = 0; kc < p.nkc; ++kc) {
             mbar_wait_poll(bar_af + 8 * a_slot_i, a_par);
+            if (PAIR2) mbar_wait_poll_cluster(bar_paf + 8 * a_slot_i, a_par);
             if (kc == 0 && lane == 0) TRACE(3, it);
             const uint64_t a_chunk = a_desc0 + ((sA - cta_win + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
             for (int tap = 0; tap < p.taps; ++tap, ++step) {
               uint32_t b_addr;
               if (p.b_resident) {
-                if (it == 0 && step == 0) mbar_wait_poll(bar_bf, 0);
+                if (it == 0 && step == 0) {
+                  mbar_wait_poll(bar_bf, 0);
+                  if (PAIR2) mbar_wait_poll_cluster(bar_pbf, 0);
+                }
                 b_addr = sB + step_bytes * step;
               } else {
-                if (si == 0) mbar_wait_poll(bar_bf + 8 * b_st, b_par);
+                if (si == 0) {
+                  mbar_wait_poll(bar_bf + 8 * b_st, b_par);
+                  if (PAIR2) mbar_wait_poll_cluster(bar_pbf + 8 * b_st, b_par);
+                }
                 b_addr = sB + stage_bytes * b_st + step_bytes * si;
               }
               const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
               const uint64_t b_d = b_desc0 + ((b_addr - cta_win) >> 4);
               const uint32_t accf = step > 0 ? 1u : 0u;
-              if (leader) issue_mmas<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
+              if (leader) {
+                if (PAIR2) issue_mmas_pair<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
+                else issue_mmas<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
+              }
               if (!p.b_resident) {
                 ++si;
                 if (si == p.sps || step == p.total_steps - 1) {
                   if (leader) {
-                    if (CLUSTER) tc_commit_multicast(bar_be + 8 * b_st, cta_mask);
+                    if (PAIR2) tc_commit_pair(bar_be + 8 * b_st);
+                    else if (MCAST) tc_commit_multicast(bar_be + 8 * b_st, cta_mask);
                     else tc_commit(bar_be + 8 * b_st);
                   }
                   si = 0;
@@ -327,13 +396,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
                 }
               }
             }
-            if (leader) tc_commit(bar_ae + 8 * a_slot_i);
+            if (leader) {
+              if (PAIR2) tc_commit_pair(bar_ae + 8 * a_slot_i);
+              else tc_commit(bar_ae + 8 * a_slot_i);
+            }
             if (++a_slot_i == (uint32_t)p.a_slots) {
               a_slot_i = 0;
               a_par ^= 1;
             }
           }
-          if (leader) tc_commit(bar_accf + 8 * buf);
+          if (leader) {
+            if (PAIR2) tc_commit_pair(bar_accf + 8 * buf);
+            else tc_commit(bar_accf + 8 * buf);
+          }
           __syncwarp();
           if (lane == 0) TRACE(4, it);
         }
@@ -420,14 +495,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 64) TRACE(6, it);
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * buf) : "memory");
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * buf) : "memory");
+        if (PAIR2 && rank != 0) mbar_arrive_remote(bar_pacce + 8 * buf, 0);  // the leader issues the MMAs into both TMEMs
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (CLUSTER) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (PAIR2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -745,6 +824,8 @@ void set_smem_attr() {
     CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   });
 }
 
@@ -945,21 +1026,40 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   }
   int nc = L.b_resident ? 1 : cluster_pref;
   while (nc > 1 && (gi.n_tiles[slot] < nc || (size_t(L.nb) * L.kc * 2) % (size_t(16) * nc) != 0)) nc >>= 1;
+  // CTA pairs (cta_group::2, SBV2_B200_PAIR2=1 or ConvCall::pair): two adjacent N blocks of the layer's packing form the N
+  // of one M = 256 MMA, each CTA of the pair streams one of them.  Needs an even number of N blocks, N = 2 * nb <= 256 and
+  // both accumulator sets (2 * mt * N columns) in TMEM.
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("SBV2_B200_PAIR2");
+    pair_env = e ? atoi(e) : 0;
+  }
+  const bool pair = (c.pair || pair_env == 1) && pair_env != 2 && !L.b_resident && L.n_groups == 1 && c.gate_half == 0 && L.n_nblk % 2 == 0 &&
+                    2 * L.nb <= 256 && 4 * L.mt * L.nb <= 512 && gi.n_tiles[slot] >= 2;
+  if (pair) {
+    nc = 2;
+    a.nb = 2 * L.nb;
+    a.n_nblk = L.n_nblk / 2;
+    a.tmem_cols = pow2_at_least(4 * L.mt * L.nb);
+    a.idesc = (1u << 4) | ((unsigned)(a.nb >> 3) << 17) | ((unsigned)(256 >> 4) << 24);  // M = 256 across the pair
+  }
   a.cluster = nc;
   a.n_tiles = gi.n_tiles[slot];
-  a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * L.n_nblk * L.n_groups;  // cluster items
+  a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * a.n_nblk * L.n_groups;  // cluster items
   dim3 grid(std::min(a.n_items, num_sms / nc) * nc);
   void (*kernel)(UmmaConvArgs) = nullptr;
-  switch ((c.gate_half > 0 ? 1 : 0) | (nc > 1 ? 2 : 0) | ((c.rm_out != nullptr || c.split_out != nullptr) ? 4 : 0)) {
+  switch ((c.gate_half > 0 ? 1 : 0) | (pair ? 8 : (nc > 1 ? 2 : 0)) | ((c.rm_out != nullptr || c.split_out != nullptr) ? 4 : 0)) {
     case 0: kernel = umma_conv_kernel<0>; break;
     case 1: kernel = umma_conv_kernel<1>; break;
     case 2: kernel = umma_conv_kernel<2>; break;
     case 3: kernel = umma_conv_kernel<3>; break;
     case 4: kernel = umma_conv_kernel<4>; break;
     case 6: kernel = umma_conv_kernel<6>; break;
+    case 8: kernel = umma_conv_kernel<8>; break;
+    case 12: kernel = umma_conv_kernel<12>; break;
     default: fail(SBV2_ERR_INTERNAL, "conv kernel: unsupported epilogue combination");
   }
-  launch_pdl_cluster(ctx.pdl, nc, kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
+  launch_pdl_cluster(ctx.pdl && !pair, nc, kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);
   ctx.count();
 }
 

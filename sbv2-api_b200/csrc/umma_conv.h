@@ -138,6 +138,8 @@ struct ConvCall {
   // synthesizer's few-rows layers lose 4 % (the box always carries all rows of the tile, the bulk copies only the valid
   // ones), batches are unchanged — so DeBERTa asks for it and the synthesizer does not.
   bool tmap = false;
+  // run as CTA pairs (tcgen05 cta_group::2, M = 256) when the layer's packing allows it (see launch_umma)
+  bool pair = false;
 };
 void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt);
 void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, int n_utt);

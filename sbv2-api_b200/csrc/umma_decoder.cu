@@ -403,7 +403,9 @@ extern "C" int sbv2_debug_conv_compare(const float* x, int64_t T, int cin, const
     hc.k = k;
     hc.w.assign(w, w + size_t(cout) * cin * k);
     if (bias) hc.b.assign(bias, bias + cout);
-    ConvLayer L = make_conv1d_layer(&owner, hc, dil, mt_pref);
+    int nb_max = 256;
+    if (const char* e = getenv("SBV2_B200_TEST_NBMAX")) nb_max = atoi(e);
+    ConvLayer L = make_conv1d_layer(&owner, hc, dil, mt_pref, nb_max);
     // fp32 reference weights [k][cin][cout]
     std::vector<float> wr(size_t(k) * cin * cout);
     for (int co = 0; co < cout; ++co)

@@ -85,6 +85,55 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
                "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                : "memory");
 }
+// ---- CTA pair (cta_group::2) primitives --------------------------------------------------------------------------
+// One tcgen05.mma issued by the leader CTA computes a 256-row tile: rows 0-127 from the leader's activation tile into the
+// leader's TMEM, rows 128-255 from the peer's tile into the peer's TMEM; the N x K weight operand is split by N, each CTA
+// holding one half in ITS shared memory.  An SM therefore takes in only half of every weight stage from L2 — the
+// per-SM ingest (64 B/clk) is what bounds 128-row-tile GEMMs whose K loop streams the weights once per tile.
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// commit of the pair's MMAs: the arrival is delivered to the barrier at the same offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same offset in CTA `target_rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t target_rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(target_rank)
+      : "memory");
+}
+// wait that also acquires at cluster scope (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_poll_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+template <int MT, int K16>
+__device__ __forceinline__ void issue_mmas_pair(uint32_t tacc0, uint64_t a0, uint64_t b0, uint32_t a_kstep, uint32_t b_kstep,
+                                                uint32_t acc_stride, uint32_t idesc, uint32_t accf);
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -151,6 +200,17 @@ __device__ __forceinline__ void issue_mmas(uint32_t tacc0, uint64_t a0, uint64_t
     for (int k = 0; k < K16; ++k)
       tc_mma_f16(tacc0 + (uint32_t)a * acc_stride, a0 + (uint32_t)(a * 128) + (uint32_t)k * a_kstep, b0 + (uint32_t)k * b_kstep, idesc,
                  k == 0 ? accf : 1u);
+  }
+}
+template <int MT, int K16>
+__device__ __forceinline__ void issue_mmas_pair(uint32_t tacc0, uint64_t a0, uint64_t b0, uint32_t a_kstep, uint32_t b_kstep,
+                                                uint32_t acc_stride, uint32_t idesc, uint32_t accf) {
+#pragma unroll
+  for (int a = 0; a < MT; ++a) {
+#pragma unroll
+    for (int k = 0; k < K16; ++k)
+      tc_mma_f16_pair(tacc0 + (uint32_t)a * acc_stride, a0 + (uint32_t)(a * 128) + (uint32_t)k * a_kstep, b0 + (uint32_t)k * b_kstep, idesc,
+                      k == 0 ? accf : 1u);
   }
 }
 // Warp-uniform dispatch on (mt, k16); call from the elected lane only.
