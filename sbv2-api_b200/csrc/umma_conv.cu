@@ -720,6 +720,30 @@ ConvLayer make_layer(sbv2_model* owner, int cin, int cout, int taps, int n_group
           }
         }
     }
+    // Deep-K GEMMs (one tap, 128-row items: DeBERTa): a K chunk consumes one activation slot AND one weight step, and with
+    // 0.27 us of MMA work per chunk against ~1.5 us of L2 latency the chunks in flight set the rate — give both rings the
+    // same depth in chunks instead of the weight ring first (slots 3 / stages 5 -> 4 / 4 for N = 256; 6 / 6 for N = 128)
+    if (!latency_mode && taps == 1 && mt == 1 && L.nkc >= 8 && !placed) {
+      int best = 0, bs = 0, bn = 0;
+      for (int slots = ring_min_slots; slots <= MAX_ASLOTS; ++slots)
+        for (int ns = 2; ns <= MAX_STAGES; ++ns) {
+          const size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + kMisc;
+          if (sm > size_t(SMEM_LIMIT)) continue;
+          const int depth = std::min(slots, ns * L.sps);
+          if (depth > best || (depth == best && slots + ns > bs + bn)) {
+            best = depth;
+            bs = slots;
+            bn = ns;
+          }
+        }
+      if (best > 0) {
+        L.mt = mt;
+        L.a_slots = bs;
+        L.nstages = bn;
+        L.smem = ((slot * bs + 127) & ~size_t(127)) + stage_bytes * bn + kMisc;
+        placed = true;
+      }
+    }
     for (int ns = std::min(MAX_STAGES, std::max(2, L.nloads)); ns >= 2 && !placed; --ns) {
       for (int slots = std::min(MAX_ASLOTS, std::max(ring_min_slots, L.nkc + 1)); slots >= ring_min_slots && !placed; --slots) {
         size_t sm = ((slot * slots + 127) & ~size_t(127)) + stage_bytes * ns + kMisc;
