@@ -112,3 +112,19 @@ def test_text_split_convs_match_fp32_path(S):
         assert np.abs(got[mode][1] - got["fp32"][1]).max() <= 1e-4 * max(1.0, np.abs(got["fp32"][1]).max())
         assert np.abs(got[mode][2] - got["fp32"][2]).max() <= 2e-5
         assert np.abs(got[mode][3] - got["fp32"][3]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("env", [{"SBV2_B200_CLUSTER": "2"}, {"SBV2_B200_CLUSTER": "4"},
+                                 {"SBV2_B200_PAIR2": "1", "SBV2_B200_TEST_NBMAX": "128"}])
+def test_conv_kernel_cluster_and_pair_variants(S, env):
+    """The optional launch modes of umma_conv_kernel — thread-block clusters with multicast weight stages and CTA pairs
+    (tcgen05 cta_group::2, M = 256) — against the fp32 CUDA-core conv on 20 shapes (tools/umma_conv_check.py).  The
+    switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "umma_conv_check.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, **env))
+    lines = [l for l in r.stdout.splitlines() if l.startswith(("OK", "BAD")) or "ERROR" in l]
+    assert r.returncode == 0 and len(lines) >= 20, r.stderr[-1500:]
+    assert all(l.startswith("OK") for l in lines), "\n".join(l for l in lines if not l.startswith("OK"))
