@@ -317,9 +317,253 @@ __global__ void __launch_bounds__(160, 1) deberta_attention_tc_kernel(__half* ou
   }
 }
 
+
+// Sequences of 129..512 tokens: one CTA per (head, utterance, 128-query tile), key tiles visited in order with an online
+// softmax (running maximum / sum per row, O kept in registers and rescaled per key tile).  A (query tile, key tile) pair
+// sees 255 consecutive relative positions rel = i - j; beyond |rel| = span / 2 HF's log buckets map several of them to
+// one position row, so the two 256-row position windows are GATHERED through bucket_idx (row w = position of
+// rel = (qt - kt) * 128 + w - 127) instead of bulk-copied.  With the windows in rel order, the products, the skewed
+// copies and the softmax are those of the single-tile kernel.
+__global__ void __launch_bounds__(160, 1) deberta_attention_tc_multi_kernel(__half* out, const __half* qkv, const __half* pos_k_p,
+                                                                            const __half* pos_q_p, int n_pos, const int* bucket_idx,
+                                                                            int max_rel, int heads, PlanarSegs s) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y, qt = blockIdx.z;
+  const int len = s.len[b];
+  if (qt * T >= len) return;
+  const int nk = (len + T - 1) / T;
+  const long long pbase = s.pstart[b];
+
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + QKV_BYTES, sV = sK + QKV_BYTES, sPK = sV + QKV_BYTES, sPQ = sPK + POS_BYTES, sP = sPQ + POS_BYTES;
+  const uint32_t sC = sP + P_BYTES, sDd = sC + SKEW_BYTES, sBar = sDd + SKEW_BYTES;
+  const uint32_t bar_q = sBar, bar_s1 = sBar + 8, bar_c = sBar + 16, bar_s2 = sBar + 24, bar_p = sBar + 32, bar_o = sBar + 40,
+                 bar_kv = sBar + 48, bar_g = sBar + 56;
+  const uint32_t tmem_slot = sBar + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ));
+  __half* Cs = reinterpret_cast<__half*>(smem + (sC - sQ));
+  __half* Ds = reinterpret_cast<__half*>(smem + (sDd - sQ));
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_c, 128);
+    mbar_init(bar_s2, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_g, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int q_plane0 = h * DPL, k_plane0 = heads * DPL + h * DPL, v_plane0 = 2 * heads * DPL + h * DPL;
+
+  if (warp == 4) {
+    // ---------------- control warp: Q / K / V loads and MMA issue ----------------
+    if (lane == 0) mbar_expect_tx(bar_q, QKV_BYTES);
+    __syncwarp();
+    if (lane < DPL) bulk_g2s(sQ + lane * T * 16, qkv + (size_t)(q_plane0 + lane) * s.plane_stride + (size_t)(pbase + qt * T) * 8, T * 16, bar_q);
+    const uint64_t dq = make_desc(sQ, T * 16, 128), dk = make_desc(sK, T * 16, 128);
+    const uint64_t dpk = make_desc(sPK, W * 16, 128), dpq = make_desc(sPQ, W * 16, 128);
+    const uint64_t dp = make_desc(sP, T * 16, 128);
+    const uint64_t dv = make_desc(sV, 128, T * 16);
+    constexpr uint32_t ID_S = idesc_f16(T, 0), ID_B = idesc_f16(W, 0), ID_O = idesc_f16(D, 1);
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t par = kt & 1;
+      // every MMA of the previous key tile has completed (bar_o below): its K / V tiles can be overwritten
+      if (lane == 0) mbar_expect_tx(bar_kv, 2 * QKV_BYTES);
+      __syncwarp();
+      if (lane < DPL) {
+        const size_t row8 = (size_t)(pbase + kt * T) * 8;
+        bulk_g2s(sK + lane * T * 16, qkv + (size_t)(k_plane0 + lane) * s.plane_stride + row8, T * 16, bar_kv);
+        bulk_g2s(sV + lane * T * 16, qkv + (size_t)(v_plane0 + lane) * s.plane_stride + row8, T * 16, bar_kv);
+      }
+      __syncwarp();
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, par);
+      mbar_wait(bar_g, par);  // position windows gathered and visible to the async proxy
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) tc_mma_f16(tmem + TM_S, dq + (uint64_t)(k * 2 * T), dk + (uint64_t)(k * 2 * T), ID_S, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) tc_mma_f16(tmem + TM_B, dq + (uint64_t)(k * 2 * T), dpk + (uint64_t)(k * 2 * W), ID_B, k > 0 ? 1u : 0u);
+        tc_commit(bar_s1);
+      }
+      __syncwarp();
+      mbar_wait(bar_c, par);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) tc_mma_f16(tmem + TM_B, dk + (uint64_t)(k * 2 * T), dpq + (uint64_t)(k * 2 * W), ID_B, k > 0 ? 1u : 0u);
+        tc_commit(bar_s2);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, par);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp + (uint64_t)(k * 2 * T), dv + (uint64_t)(k * 16), ID_O, k > 0 ? 1u : 0u);
+        tc_commit(bar_o);
+      }
+      __syncwarp();
+      mbar_wait(bar_o, par);
+    }
+  } else {
+    // ---------------- softmax threads ----------------
+    const int row = warp * 32 + lane;  // query row within the tile; key row within the tile while staging P2C
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c_scale = 1.4426950408889634f / sqrtf(3.0f * (float)D);
+    float m = -CUDART_INF_F, l = 0.f;
+    float o[D];
+#pragma unroll
+    for (int e = 0; e < D; ++e) o[e] = 0.f;
+    const __half* crow = Cs + row * PCS;
+    const __half* drow = Ds + row * PCS;
+    uint8_t* prow = smem + (sP - sQ) + row * 16;
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t par = kt & 1;
+      const int klen = len - kt * T;  // keys of this tile below klen are real
+      // position windows of this tile pair (the previous pair's MMAs have completed: bar_o was waited for)
+#pragma unroll 1
+      for (int w = row; w < W; w += T) {
+        int rel = (qt - kt) * T + w - (T - 1);
+        rel = rel < -max_rel ? -max_rel : (rel > max_rel ? max_rel : rel);
+        const int pr = bucket_idx[rel + max_rel];
+#pragma unroll
+        for (int pl = 0; pl < DPL; ++pl) {
+          const size_t src = ((size_t)(h * DPL + pl) * n_pos + pr) * 8;
+          *reinterpret_cast<uint4*>(smem + (sPK - sQ) + (size_t)(pl * W + w) * 16) = *reinterpret_cast<const uint4*>(pos_k_p + src);
+          *reinterpret_cast<uint4*>(smem + (sPQ - sQ) + (size_t)(pl * W + w) * 16) = *reinterpret_cast<const uint4*>(pos_q_p + src);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_g);
+      mbar_wait(bar_kv, par);
+      if (row >= klen) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int pl = 0; pl < DPL; ++pl) *reinterpret_cast<uint4*>(smem + (sV - sQ) + (size_t)(pl * T + row) * 16) = z;
+      }
+      mbar_wait(bar_s1, par);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < W / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_B + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int jj = q * 32 + e - row;
+          if (jj >= 0 && jj < T) Cs[row * PCS + jj] = __float2half_rn(__uint_as_float(v[e]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_c);
+      mbar_wait(bar_s2, par);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < W / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_B + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int ii = q * 32 + e + row - (T - 1);
+          if (ii >= 0 && ii < T) Ds[ii * PCS + row] = __float2half_rn(__uint_as_float(v[e]));
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float mt = -CUDART_INF_F;
+#pragma unroll 1
+      for (int q = 0; q < T / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_S + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = q * 32 + e;
+          const float sc = __uint_as_float(v[e]) + __half2float(crow[T - 1 - j]) + __half2float(drow[j]);
+          mt = fmaxf(mt, j < klen ? sc : -CUDART_INF_F);
+        }
+      }
+      const float m_new = fmaxf(m, mt);
+      const float mc = m_new * c_scale;
+      const float alpha = ex2_approx(fmaf(m, c_scale, -mc));  // 0 on the first tile (m = -inf)
+      m = m_new;
+      float lt = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < T / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_S + q * 32, v);
+        tc_wait_ld();
+        float pv[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = q * 32 + e;
+          const float sc = __uint_as_float(v[e]) + __half2float(crow[T - 1 - j]) + __half2float(drow[j]);
+          const float p = j < klen ? ex2_approx(fmaf(sc, c_scale, -mc)) : 0.f;
+          pv[e] = p;
+          lt += p;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(pv[g * 8 + 2 * e], pv[g * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(prow + (size_t)(q * 4 + g) * T * 16) = u;
+        }
+      }
+      l = fmaf(l, alpha, lt);
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_p);
+      mbar_wait(bar_o, par);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < D / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_O + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[q * 32 + e] = fmaf(o[q * 32 + e], alpha, __uint_as_float(v[e]));
+      }
+      tc_fence_before();
+    }
+    const float inv_l = 1.0f / l;
+    const int grow = qt * T + row;
+    if (grow < len) {
+#pragma unroll
+      for (int g = 0; g < DPL; ++g) {
+        uint4 u;
+        __half2* uh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(o[g * 8 + 2 * e] * inv_l, o[g * 8 + 2 * e + 1] * inv_l);
+        *reinterpret_cast<uint4*>(out + (size_t)(h * DPL + g) * s.plane_stride + (pbase + grow) * 8) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len) { return head_dim == D && span >= 254 && max_len <= T; }
+
+bool deberta_attention_tc_multi_supported(int head_dim, int max_rel, int max_len) { return head_dim == D && max_len - 1 <= max_rel; }
 
 void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
                                  int n_pos, int span, int heads, const PlanarSegs& s) {
@@ -332,6 +576,20 @@ void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __
   attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
   dim3 grid(heads, s.n);
   deberta_attention_tc_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, pos_k_p, pos_q_p, n_pos, win0, heads, s);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+void launch_deberta_attention_tc_multi(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
+                                       int n_pos, const int* bucket_idx, int max_rel, int heads, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (!deberta_attention_tc_multi_supported(D, max_rel, s.max_len))
+    fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention (multi-tile): unsupported shape");
+  const size_t smem = 3 * QKV_BYTES + 2 * POS_BYTES + P_BYTES + 2 * SKEW_BYTES + 128;
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+  dim3 grid(heads, s.n, (s.max_len + T - 1) / T);
+  deberta_attention_tc_multi_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, pos_k_p, pos_q_p, n_pos, bucket_idx, max_rel, heads, s);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -412,7 +412,9 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
   };
   // sequences of at most 128 tokens: disentangled attention on the tensor cores (SBV2_B200_BERT_ATTN=simt: CUDA cores)
   const bool tc_attn = M.use_tc_attn && M.hidden / M.heads == 64 && deberta_attention_tc_supported(64, M.span, max_len);
-  if (tc_attn && M.qkvp.gen != M.qkvp_cleared_gen) {
+  // 129..512 tokens: the multi-tile kernel (log-bucket position windows gathered per tile pair)
+  const bool tc_multi = !tc_attn && M.use_tc_attn && M.hidden / M.heads == 64 && deberta_attention_tc_multi_supported(64, M.max_rel, max_len);
+  if ((tc_attn || tc_multi) && M.qkvp.gen != M.qkvp_cleared_gen) {
     // rows past an utterance's end are read by the tensor-core attention: they must hold finite values
     CUDA_CHECK(cudaMemsetAsync(M.qkvp.p, 0, M.qkvp.cap, M.stream));
     M.qkvp_cleared_gen = M.qkvp.gen;
@@ -423,6 +425,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     const __half* in = l == 0 ? embp : hp;
     umma(small ? B.qkv_s : B.qkv, in, qkvp, nullptr, ACT_NONE);
     if (tc_attn) launch_deberta_attention_tc(ctx, ctxp, qkvp, B.pos_k_p, B.pos_q_p, 2 * M.span, M.span, M.heads, ps);
+    else if (tc_multi) launch_deberta_attention_tc_multi(ctx, ctxp, qkvp, B.pos_k_p, B.pos_q_p, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, ps);
     else launch_deberta_attention(ctx, ctxp, qkvp, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
     umma(small ? B.o_s : B.o, ctxp, nullptr, y32, ACT_NONE);
     launch_ln_planar_wide(ctx, h, hp, nullptr, y32, B.ln1_g, B.ln1_b, M.eps, H, ps);

@@ -214,6 +214,10 @@ void launch_ln_split(const LaunchCtx& ctx, float* out, __half* split, float spli
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len);
 void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
                                  int n_pos, int span, int heads, const PlanarSegs& s);
+// 129..512 tokens: 128-query tiles x 128-key tiles with an online softmax; position windows gathered through bucket_idx
+bool deberta_attention_tc_multi_supported(int head_dim, int max_rel, int max_len);
+void launch_deberta_attention_tc_multi(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
+                                       int n_pos, const int* bucket_idx, int max_rel, int heads, const PlanarSegs& s);
 // out[b, t, :] = h[start[b] + t, :] for t < len[b], zeros elsewhere (out: [n, S, C] fp32)
 void launch_scatter_rows(const LaunchCtx& ctx, float* out, const float* h, int C, int S, const PlanarSegs& s);
 }  // namespace sbv2

@@ -84,9 +84,10 @@ def test_predict_matches_hf(tiny, s):
     close(got, ref)
 
 
-@pytest.mark.parametrize("s", [1, 7, 64, 128, 129, 300])
+@pytest.mark.parametrize("s", [1, 7, 64, 128, 129, 200, 256, 257, 300, 384, 385, 511, 512])
 def test_predict_matches_hf_fp16_mode(tiny_fp16, s):
-    """The throughput mode: tensor-core attention up to 128 tokens, CUDA-core kernel beyond."""
+    """The throughput mode: single-tile tensor-core attention up to 128 tokens, the multi-tile kernel (online softmax,
+    log-bucket position windows) from 129 to 512."""
     cfg, hf, model = tiny_fp16
     g = torch.Generator().manual_seed(100 + s)
     ids = torch.randint(3, cfg.vocab_size, (1, s), generator=g)
@@ -132,9 +133,11 @@ def test_error_paths(tiny, S):
     assert model.predict([5, 6, 7], [1, 1, 1]).shape == (3, cfg.hidden_size)
 
 
-def test_tensor_core_attention_matches_cuda_core_attention(S):
-    """Sequences of at most 128 tokens run the disentangled attention on tcgen05 (bert_attention_tc.cu); the CUDA-core
-    kernel (SBV2_B200_BERT_ATTN=simt) is the cross-check, on a ragged right-padded batch."""
+@pytest.mark.parametrize("smax,lens", [(128, [128, 1, 77, 128, 5, 100]), (512, [512, 129, 300, 1, 128, 257, 400, 385, 256, 511])])
+def test_tensor_core_attention_matches_cuda_core_attention(S, smax, lens):
+    """The disentangled attention runs on tcgen05 (bert_attention_tc.cu: one tile up to 128 tokens, 128 x 128 tile pairs
+    with gathered log-bucket position windows up to 512); the CUDA-core kernel (SBV2_B200_BERT_ATTN=simt) is the
+    cross-check, on a ragged right-padded batch."""
     from sbv2_b200 import assets
     cfg = od.tiny_config()
     onnx = assets.deberta_onnx(od.state_dict_numpy(od.build_model(cfg, seed=1)))
@@ -145,14 +148,13 @@ def test_tensor_core_attention_matches_cuda_core_attention(S):
     finally:
         del os.environ["SBV2_B200_BERT_ATTN"]
     g = torch.Generator().manual_seed(9)
-    lens = [128, 1, 77, 128, 5, 100]
-    ids = torch.randint(3, cfg.vocab_size, (len(lens), 128), generator=g).numpy()
-    mask = np.zeros((len(lens), 128), np.int64)
+    ids = torch.randint(3, cfg.vocab_size, (len(lens), smax), generator=g).numpy()
+    mask = np.zeros((len(lens), smax), np.int64)
     for b, n in enumerate(lens):
         mask[b, :n] = 1
     a = tc.predict_batch(ids, mask)
     b_ = simt.predict_batch(ids, mask)
-    assert a.shape == b_.shape == (len(lens), 128, cfg.hidden_size)
+    assert a.shape == b_.shape == (len(lens), smax, cfg.hidden_size)
     assert np.isfinite(a).all()
     for i, n in enumerate(lens):
         assert not a[i, n:].any()

@@ -109,6 +109,8 @@ def test_cfg2_deberta_large_ragged_and_long(deberta_large):
     refs = [od.predict(hf, torch.from_numpy(ids[b:b + 1, :n]), torch.ones(1, n, dtype=torch.long))[0].numpy() for b, n in enumerate(lens)]
     ids300 = torch.randint(3, cfg.vocab_size, (1, 300), generator=g)
     ref300 = od.predict(hf, ids300, torch.ones_like(ids300))[0].numpy()
+    ids512 = torch.randint(3, cfg.vocab_size, (1, 512), generator=g)
+    ref512 = od.predict(hf, ids512, torch.ones_like(ids512))[0].numpy()
     for k, model in models.items():
         got = model.predict_batch(ids, mask)
         for b, n in enumerate(lens):
@@ -118,6 +120,11 @@ def test_cfg2_deberta_large_ragged_and_long(deberta_large):
         got = model.predict(ids300[0].numpy(), np.ones(300, np.int64))
         e = feat_err(got, ref300)
         print(f"cfg2 S=300 [{k}] vs HF fp32: max-abs {e[0]:.3e}, rel-Frobenius {e[1]:.3e}")
+        assert e[0] <= FEAT_TOL[k][0] and e[1] <= FEAT_TOL[k][1], (k, e)
+        # the graph's maximum: 512 tokens (4 x 4 attention tile pairs, relative positions up to +-511)
+        got = model.predict(ids512[0].numpy(), np.ones(512, np.int64))
+        e = feat_err(got, ref512)
+        print(f"cfg2 S=512 [{k}] vs HF fp32: max-abs {e[0]:.3e}, rel-Frobenius {e[1]:.3e}")
         assert e[0] <= FEAT_TOL[k][0] and e[1] <= FEAT_TOL[k][1], (k, e)
 
 
