@@ -5,9 +5,9 @@
 // shared memory as the fp16 A operand of O += P V, with V read as an MN-major B operand straight
 // from the planar activation layout.  The window terms are two extra tiny MMAs: Srel = Q Ek^T
 // (9 relative keys, padded to 16) before the loop and O += Prel Ev after it.
-// Softmax is exact two-pass (pass A: row max / sum; pass B: normalised probabilities), so the O
-// accumulator is never rescaled.  Replaces rel_attention_planar_kernel (fp32 CUDA cores) in the flow;
-// oracle: oracle/vits.py MultiHeadAttention.attention.
+// Softmax is exact two-pass (pass A: row max only; pass B: unnormalised probabilities 2^(x - max) and their row sum;
+// the epilogue divides by the sum), so the O accumulator is never rescaled and each logit costs one exponential.
+// Replaces rel_attention_planar_kernel (fp32 CUDA cores) in the flow; oracle: oracle/vits.py MultiHeadAttention.attention.
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -296,25 +296,25 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
 #pragma unroll
       for (int r = 0; r < 9; ++r) srel[r] = __uint_as_float(v[r]) * c_scale;
     }
-    float m2 = -CUDART_INF_F, l = 0.f, mb = 0.f;  // running max, running sum (pass A); mb = max + log2(sum) (pass B)
+    float m2 = -CUDART_INF_F, l = 0.f, mb = 0.f;  // running max (pass A); mb = row max, l = row sum of 2^(x - mb) (pass B)
     uint8_t* prow = smem + (sP - sQ) + row * 16;
     uint8_t* prel_row = smem + (sPrel - sQ) + row * 16;
-    // pass A on 32 logits x[e] * c: running (max, sum) update
+    // pass A on 32 logits x[e] * c: running maximum only (no exponentials: the row sum is accumulated in pass B)
     auto pass_a = [&](const float* x, float c) {
       float mx = x[0];
 #pragma unroll
       for (int e = 1; e < 32; ++e) mx = fmaxf(mx, x[e]);
-      const float m_new = fmaxf(m2, mx * c);  // finite: the caller skips chunks without a valid key
+      m2 = fmaxf(m2, mx * c);  // finite: the caller skips chunks without a valid key
+    };
+    // pass B: p[e] = 2^(x[e] * c - mb), unnormalised, fp16 into the P tile (columns 32 * c32 ...); the epilogue divides by l
+    auto pass_b_store = [&](const float* x, float c, int c32, float* pv) {
       float sum = 0.f;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) sum += ex2_approx(fmaf(x[e], c, -m_new));
-      l = fmaf(l, ex2_approx(m2 - m_new), sum);  // first chunk: 0 * 2^-inf = 0
-      m2 = m_new;
-    };
-    // pass B: p[e] = 2^(x[e] * c - mb), fp16 into the P tile (columns 32 * c32 ...)
-    auto pass_b_store = [&](const float* x, float c, int c32, float* pv) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) pv[e] = ex2_approx(fmaf(x[e], c, -mb));
+      for (int e = 0; e < 32; ++e) {
+        pv[e] = ex2_approx(fmaf(x[e], c, -mb));
+        sum += pv[e];
+      }
+      l += sum;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u;
@@ -335,15 +335,10 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
       }
       if (threadIdx.x == 0) ATRACE(4, i);
       if (i == n_kt) {
-        // combine the two key-halves of each row: (m, l) -> final max and log2(sum)
+        // combine the two key-halves of each row: the row maximum
         ml_x[(half * QT + row) * 2] = m2;
-        ml_x[(half * QT + row) * 2 + 1] = l;
         asm volatile("bar.sync 1, %0;" ::"r"(32 * NSM_WARPS) : "memory");
-        const float mo = ml_x[((half ^ 1) * QT + row) * 2], lo = ml_x[((half ^ 1) * QT + row) * 2 + 1];
-        const float mf = fmaxf(m2, mo);  // finite: key 0 is always valid
-        const float lf = l * ex2_approx(m2 - mf) + lo * ex2_approx(mo - mf);
-        m2 = mf;
-        mb = mf + log2f(lf);
+        mb = fmaxf(m2, ml_x[((half ^ 1) * QT + row) * 2]);  // finite: key 0 is always valid
       }
       if (pass_b && kt > 0) mbar_wait(bar_pfree, (kt - 1) & 1);  // previous P tile consumed by the MMA
       if (threadIdx.x == 0) ATRACE(5, i);
@@ -410,7 +405,10 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
         mbar_arrive(bar_p);
       }
     }
-    // epilogue: O -> fp16 planar ctx (half 0: columns 0..63, half 1: 64..95)
+    // epilogue: O / l -> fp16 planar ctx (half 0: columns 0..63, half 1: 64..95); l = the two halves' sums
+    ml_x[(half * QT + row) * 2 + 1] = l;
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * NSM_WARPS) : "memory");
+    const float inv_l = 1.0f / (l + ml_x[((half ^ 1) * QT + row) * 2 + 1]);
     mbar_wait(bar_done, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -424,7 +422,8 @@ __global__ void __launch_bounds__(288, 1) flow_attention_tc_kernel(__half* out, 
           uint4 u;
           __half2* uh = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) uh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+          for (int e = 0; e < 4; ++e)
+            uh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]) * inv_l, __uint_as_float(v[q * 8 + 2 * e + 1]) * inv_l);
           *reinterpret_cast<uint4*>(out + (size_t)(h * DP + c * 4 + q) * s.plane_stride + (pbase + qi) * 8) = u;
         }
       }

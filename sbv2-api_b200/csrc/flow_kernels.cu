@@ -3,6 +3,8 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sbv2 {
@@ -41,54 +43,70 @@ __global__ void flow_mix_kernel(float* h_out, __half* hp, const float* h_in, con
   *reinterpret_cast<uint4*>(hp + poff) = o;
 }
 
+// One warp normalises R consecutive rows: all of their loads are issued before the first reduction (the kernel is bound by
+// memory latency, not bandwidth: 2.7 KB per row), and a lane's R rows are contiguous in the planar buffers (R * 32 B of y32).
+template <int R>
 __global__ void ln_planar_kernel(float* h, __half* hp, const float* y32, const float* gamma, const float* beta, float eps, int C,
                                  PlanarSegs s) {
   const int b = blockIdx.y;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   const int lane = threadIdx.x & 31;
-  if (t >= s.len[b]) return;  // warp-uniform
+  const int len = s.len[b];
+  if (t0 >= len) return;  // warp-uniform
   const bool act = lane < C / 8;
-  const size_t row = (size_t)s.start[b] + t;
-  const size_t poff = (size_t)lane * s.plane_stride + (size_t)(s.pstart[b] + t) * 8;
-  float v[8];
+  const size_t row0 = (size_t)s.start[b] + t0;
+  const size_t poff0 = (size_t)lane * s.plane_stride + (size_t)(s.pstart[b] + t0) * 8;
+  float v[R][8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = 0.f;
-  if (act) {
-    const float4 x0 = *reinterpret_cast<const float4*>(h + row * C + lane * 8);
-    const float4 x1 = *reinterpret_cast<const float4*>(h + row * C + lane * 8 + 4);
-    const float4 y0 = *reinterpret_cast<const float4*>(y32 + poff);
-    const float4 y1 = *reinterpret_cast<const float4*>(y32 + poff + 4);
-    v[0] = x0.x + y0.x; v[1] = x0.y + y0.y; v[2] = x0.z + y0.z; v[3] = x0.w + y0.w;
-    v[4] = x1.x + y1.x; v[5] = x1.y + y1.y; v[6] = x1.z + y1.z; v[7] = x1.w + y1.w;
-  }
-  float sum = 0.f;
+  for (int r = 0; r < R; ++r) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) sum += v[e];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)C;
-  float sq = 0.f;
-  if (act) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = v[e] - mean;
-      sq += d * d;
+    for (int e = 0; e < 8; ++e) v[r][e] = 0.f;
+    if (act && t0 + r < len) {
+      const float4 x0 = *reinterpret_cast<const float4*>(h + (row0 + r) * C + lane * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(h + (row0 + r) * C + lane * 8 + 4);
+      const float4 y0 = *reinterpret_cast<const float4*>(y32 + poff0 + r * 8);
+      const float4 y1 = *reinterpret_cast<const float4*>(y32 + poff0 + r * 8 + 4);
+      v[r][0] = x0.x + y0.x; v[r][1] = x0.y + y0.y; v[r][2] = x0.z + y0.z; v[r][3] = x0.w + y0.w;
+      v[r][4] = x1.x + y1.x; v[r][5] = x1.y + y1.y; v[r][6] = x1.z + y1.z; v[r][7] = x1.w + y1.w;
     }
   }
+  float g[8], bt[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
-  if (!act) return;
-  float r[8];
+  for (int e = 0; e < 8; ++e) {
+    g[e] = act ? gamma[lane * 8 + e] : 0.f;
+    bt[e] = act ? beta[lane * 8 + e] : 0.f;
+  }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) r[e] = (v[e] - mean) * rstd * gamma[lane * 8 + e] + beta[lane * 8 + e];
-  *reinterpret_cast<float4*>(h + row * C + lane * 8) = make_float4(r[0], r[1], r[2], r[3]);
-  *reinterpret_cast<float4*>(h + row * C + lane * 8 + 4) = make_float4(r[4], r[5], r[6], r[7]);
-  uint4 o;
-  __half2* oh = reinterpret_cast<__half2*>(&o);
+  for (int r = 0; r < R; ++r) {
+    float sum = 0.f;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(r[2 * e], r[2 * e + 1]);
-  *reinterpret_cast<uint4*>(hp + poff) = o;
+    for (int e = 0; e < 8; ++e) sum += v[r][e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+    if (act) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[r][e] - mean;
+        sq = fmaf(d, d, sq);  // explicit fma here and below: left to ptxas, R = 1 and R = 4 may be contracted differently
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
+    if (!act || t0 + r >= len) continue;
+    float q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = fmaf(__fmul_rn(v[r][e] - mean, rstd), g[e], bt[e]);
+    *reinterpret_cast<float4*>(h + (row0 + r) * C + lane * 8) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(h + (row0 + r) * C + lane * 8 + 4) = make_float4(q[4], q[5], q[6], q[7]);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(q[2 * e], q[2 * e + 1]);
+    *reinterpret_cast<uint4*>(hp + poff0 + r * 8) = o;
+  }
 }
 
 __global__ void coupling_sub_planar_kernel(float* z, const float* m32, int C, PlanarSegs s) {
@@ -316,8 +334,15 @@ void launch_ln_planar(const LaunchCtx& ctx, float* h, __half* hp, const float* y
                       int C, const PlanarSegs& s) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (C % 8 != 0 || C / 8 > 32) fail(SBV2_ERR_UNSUPPORTED, "ln_planar: C must be a multiple of 8 and <= 256");
-  dim3 grid((s.max_len + 7) / 8, s.n);
-  ln_planar_kernel<<<grid, 256, 0, ctx.stream>>>(h, hp, y32, gamma, beta, eps, C, s);
+  // few rows (batch-1 latency): one row per warp spreads over more SMs; otherwise four rows per warp for loads in flight
+  static const int force_r = [] { const char* e = getenv("SBV2_B200_LN_ROWS"); return e ? atoi(e) : 0; }();  // test hook
+  if (force_r == 1 || (force_r == 0 && (long long)s.max_len * s.n <= 4096)) {
+    dim3 grid((s.max_len + 7) / 8, s.n);
+    ln_planar_kernel<1><<<grid, 256, 0, ctx.stream>>>(h, hp, y32, gamma, beta, eps, C, s);
+  } else {
+    dim3 grid((s.max_len + 31) / 32, s.n);
+    ln_planar_kernel<4><<<grid, 256, 0, ctx.stream>>>(h, hp, y32, gamma, beta, eps, C, s);
+  }
   POST_LAUNCH(ctx);
 }
 

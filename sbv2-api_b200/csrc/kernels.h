@@ -15,6 +15,9 @@ struct Segs {             // device pointers
   const int* len = nullptr;    // [n] rows of each utterance
   int n = 0;
   int max_len = 0;  // host-side max over len (grid sizing)
+  // rows are per-utterance conditioning vectors (one segment of B rows): k = 1 convs over them run utt_linear_kernel
+  // whatever B is, so an utterance's vectors do not depend on the batch it is in
+  bool vectors = false;
 };
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 /*0.1*/, ACT_GELU = 3, ACT_LRELU01 = 4 /*0.01*/, ACT_TANH = 5 };

@@ -2,6 +2,8 @@
 // alignment) and the glue around the tensor-core kernels.  See kernels.h for layouts.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sbv2 {
@@ -252,15 +254,27 @@ __global__ void layernorm_kernel(float* out, const float* a, const float* addin,
 }
 
 // ---------------------------------------------------------------------------------------------
-// window-relative attention, flash style. 64 queries x 64 keys per step, 256 threads.
+// window-relative attention, flash style. 16 * RQ queries x 64 keys per step, 256 threads (thread = RQ rows x 4 keys).
+// A row's arithmetic does not depend on RQ (its 16 threads hold the same 4 keys each in the same order), so the variants
+// are bit-identical; few phoneme rows (one utterance) use RQ = 1 for four times the CTAs.
 // ---------------------------------------------------------------------------------------------
-constexpr int AQ = 64, AK = 64;
+constexpr int AK = 64;
 
-template <int D>
-__global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const float* qkv, const float* rel_k,
-                                                            const float* rel_v, int heads, int window, Segs seg) {
+// plain (not .nc) volatile loads: ptxas sinks read-only loads below the barrier that follows them, next to their first use,
+// and the tile load becomes a chain of dependent round trips again
+__device__ __forceinline__ float4 ldg_f4_issue_now(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+template <int D, int RQ>
+__global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const float* __restrict__ qkv, const float* __restrict__ rel_k,
+                                                            const float* __restrict__ rel_v, int heads, int window, Segs seg) {
   extern __shared__ float sm[];
+  constexpr int AQ = 16 * RQ;
   constexpr int DC = D / 16;  // output columns per thread
+  constexpr int D4 = D / 4;
   const int R = 2 * window + 1;
   float* Qt = sm;                    // [D][AQ+1]
   float* Kt = Qt + D * (AQ + 1);     // [D][AK+1]
@@ -283,11 +297,19 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const fl
     Ek[i] = rel_k[i];
     Ev[i] = rel_v[i];
   }
-  for (int i = tid; i < AQ * D; i += 256) {
-    int r = i / D, d = i % D;
-    float v = 0.f;
-    if (q0 + r < len) v = qkv[(size_t)(base + q0 + r) * ld + h * D + d] * scale;
-    Qt[d * (AQ + 1) + r] = v;
+  // 16-byte loads, all of a thread's loads issued before the first use: these phases are memory-latency bound
+#pragma unroll
+  for (int u = 0; u < (AQ * D4 + 255) / 256; ++u) {
+    const int i = tid + u * 256;
+    if (i < AQ * D4) {
+      const int r = i / D4, d4 = i - r * D4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < len) v = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)(base + q0 + r) * ld + h * D) + d4);
+      Qt[(d4 * 4 + 0) * (AQ + 1) + r] = v.x * scale;
+      Qt[(d4 * 4 + 1) * (AQ + 1) + r] = v.y * scale;
+      Qt[(d4 * 4 + 2) * (AQ + 1) + r] = v.z * scale;
+      Qt[(d4 * 4 + 3) * (AQ + 1) + r] = v.w * scale;
+    }
   }
   __syncthreads();
   for (int i = tid; i < AQ * R; i += 256) {
@@ -297,55 +319,73 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const fl
     Qrel[r * R + rr] = s;
   }
 
-  float m_run[4], l_run[4], o[4][DC];
+  float m_run[RQ], l_run[RQ], o[RQ][DC];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RQ; ++i) {
     m_run[i] = -CUDART_INF_F;
     l_run[i] = 0.f;
 #pragma unroll
     for (int c = 0; c < DC; ++c) o[i][c] = 0.f;
   }
 
-  for (int k0 = 0; k0 < len; k0 += AK) {
-    __syncthreads();  // previous step's consumers of Kt/Vs/Ps are done (also orders Qrel)
-    for (int i = tid; i < AK * D; i += 256) {
-      int r = i / D, d = i % D;
-      float kv = 0.f, vv = 0.f;
+  constexpr int KV_PER = AK * D4 / 256;  // float4 loads per thread and operand
+  static_assert(AK * D4 % 256 == 0, "K/V tile must divide over the block");
+  float4 kq[KV_PER], vq[KV_PER];
+  auto load_kv = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < KV_PER; ++u) {
+      const int i = tid + u * 256;
+      const int r = i / D4, d4 = i - r * D4;
+      kq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vq[u] = kq[u];
       if (k0 + r < len) {
         const float* row = qkv + (size_t)(base + k0 + r) * ld;
-        kv = row[heads * D + h * D + d];
-        vv = row[2 * heads * D + h * D + d];
+        kq[u] = ldg_f4_issue_now(row + heads * D + h * D + d4 * 4);
+        vq[u] = ldg_f4_issue_now(row + 2 * heads * D + h * D + d4 * 4);
       }
-      Kt[d * (AK + 1) + r] = kv;
-      Vs[r * D + d] = vv;
+    }
+  };
+  load_kv(0);
+  for (int k0 = 0; k0 < len; k0 += AK) {
+    __syncthreads();  // previous step's consumers of Kt/Vs/Ps are done (also orders Qrel)
+#pragma unroll
+    for (int u = 0; u < KV_PER; ++u) {
+      const int i = tid + u * 256;
+      const int r = i / D4, d4 = i - r * D4;
+      Kt[(d4 * 4 + 0) * (AK + 1) + r] = kq[u].x;
+      Kt[(d4 * 4 + 1) * (AK + 1) + r] = kq[u].y;
+      Kt[(d4 * 4 + 2) * (AK + 1) + r] = kq[u].z;
+      Kt[(d4 * 4 + 3) * (AK + 1) + r] = kq[u].w;
+      *reinterpret_cast<float4*>(Vs + r * D + d4 * 4) = vq[u];
     }
     __syncthreads();
-    float s[4][4];
+    if (k0 + AK < len) load_kv(k0 + AK);  // in flight while this tile is computed
+    float s[RQ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RQ; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
     for (int d = 0; d < D; ++d) {
-      float qa[4], kb[4];
+      float qa[RQ], kb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = Qt[d * (AQ + 1) + ty * 4 + i];
+      for (int i = 0; i < RQ; ++i) qa[i] = Qt[d * (AQ + 1) + ty * RQ + i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) kb[j] = Kt[d * (AK + 1) + tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RQ; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qa[i], kb[j], s[i][j]);
     }
     // relative-key bias, key validity, running softmax
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int qi = q0 + ty * 4 + i;
+    for (int i = 0; i < RQ; ++i) {
+      int qi = q0 + ty * RQ + i;
       float mx = -CUDART_INF_F;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int kj = k0 + tx * 4 + j;
         int rel = kj - qi;
-        if (rel >= -window && rel <= window) s[i][j] += Qrel[(ty * 4 + i) * R + rel + window];
+        if (rel >= -window && rel <= window) s[i][j] += Qrel[(ty * RQ + i) * R + rel + window];
         if (kj >= len) s[i][j] = -CUDART_INF_F;
         mx = fmaxf(mx, s[i][j]);
       }
@@ -357,12 +397,12 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const fl
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float p = (s[i][j] == -CUDART_INF_F) ? 0.f : expf(s[i][j] - m_new);
-        Ps[(ty * 4 + i) * (AK + 1) + tx * 4 + j] = p;
+        Ps[(ty * RQ + i) * (AK + 1) + tx * 4 + j] = p;
         psum += p;
       }
 #pragma unroll
       for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
-      l_run[i] = l_run[i] * corr + psum;
+      l_run[i] = fmaf(l_run[i], corr, psum);  // explicit: ptxas may or may not fuse a*b+c, and differently per instantiation
       m_run[i] = m_new;
 #pragma unroll
       for (int c = 0; c < DC; ++c) o[i][c] *= corr;
@@ -370,24 +410,24 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const fl
     __syncthreads();
     // O += P V
     for (int j = 0; j < AK; ++j) {
-      float pv[4], vv[DC];
+      float pv[RQ], vv[DC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = Ps[(ty * 4 + i) * (AK + 1) + j];
+      for (int i = 0; i < RQ; ++i) pv[i] = Ps[(ty * RQ + i) * (AK + 1) + j];
 #pragma unroll
       for (int c = 0; c < DC; ++c) vv[c] = Vs[j * D + tx * DC + c];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RQ; ++i)
 #pragma unroll
         for (int c = 0; c < DC; ++c) o[i][c] = fmaf(pv[i], vv[c], o[i][c]);
     }
     // relative-value term for keys of this tile inside the window
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int qi = q0 + ty * 4 + i;
+    for (int i = 0; i < RQ; ++i) {
+      int qi = q0 + ty * RQ + i;
       for (int rr = 0; rr < R; ++rr) {
         int kj = qi + rr - window;
         if (kj >= k0 && kj < k0 + AK && kj < len && kj >= 0) {
-          float p = Ps[(ty * 4 + i) * (AK + 1) + (kj - k0)];
+          float p = Ps[(ty * RQ + i) * (AK + 1) + (kj - k0)];
 #pragma unroll
           for (int c = 0; c < DC; ++c) o[i][c] = fmaf(p, Ev[rr * D + tx * DC + c], o[i][c]);
         }
@@ -395,13 +435,49 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(float* out, const fl
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int qi = q0 + ty * 4 + i;
+  for (int i = 0; i < RQ; ++i) {
+    int qi = q0 + ty * RQ + i;
     if (qi >= len) continue;
     float inv = 1.0f / l_run[i];
 #pragma unroll
     for (int c = 0; c < DC; ++c) out[(size_t)(base + qi) * (heads * D) + h * D + tx * DC + c] = o[i][c] * inv;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-utterance vector through a Linear (k = 1 conv on one row per utterance: speaker / style conditioning).
+// 32 outputs x 8 K slices per block; the generic conv kernel walks K in 16-channel steps at one memory latency each
+// (37 us for 512 inputs), this one issues its 64 loads per thread in unrolled batches.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) utt_linear_kernel(ConvArgs a) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.z, t = blockIdx.y;
+  if (t >= a.seg.len[b]) return;
+  const int in_base = a.seg.start[b] + t;
+  const int out_base = (a.seg_out_start ? a.seg_out_start[b] : a.seg.start[b]) + t * a.out_row_mul;
+  const int col = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int co = blockIdx.x * 32 + col;
+  const int per = (a.cin + 7) / 8;
+  const int c_lo = ks * per, c_hi = min(a.cin, c_lo + per);
+  const float* __restrict__ in = a.in + (size_t)in_base * a.in_ld;
+  const float* __restrict__ w = a.w;
+  float acc = 0.f;
+  if (co < a.cout) {
+#pragma unroll 16
+    for (int ci = c_lo; ci < c_hi; ++ci) acc = fmaf(apply_act(__ldg(in + ci), a.act_in), __ldg(w + (size_t)ci * a.cout + co), acc);
+  }
+  red[ks][col] = acc;
+  __syncthreads();
+  if (ks != 0 || co >= a.cout) return;
+  float v = red[0][col];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) v += red[q][col];
+  if (a.bias) v += a.bias[co];
+  if (a.bias_utt) v += a.bias_utt[(size_t)b * a.cout + co];
+  const size_t o = ((size_t)out_base + a.out_row_off) * a.out_ld + co;
+  if (a.residual) v += a.residual[o];
+  v = apply_act(v, a.act_out);
+  if (a.out) a.out[o] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -730,6 +806,12 @@ __global__ void dec_post_kernel(float* out, const float* x, const float* w, int 
 
 void launch_conv(const LaunchCtx& ctx, const ConvArgs& a) {
   if (a.seg.n <= 0 || a.seg.max_len <= 0) return;
+  if (a.seg.vectors && a.taps == 1 && a.off == 0) {  // per-utterance conditioning vectors
+    dim3 grid((a.cout + 31) / 32, a.seg.max_len, a.seg.n);
+    utt_linear_kernel<<<grid, 256, 0, ctx.stream>>>(a);
+    POST_LAUNCH(ctx);
+    return;
+  }
   dim3 grid((a.seg.max_len + CT - 1) / CT, (a.cout + CN - 1) / CN, a.seg.n);
   const bool vec = a.cin % 4 == 0 && a.cout % 4 == 0 && a.in_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;
@@ -850,11 +932,20 @@ void launch_rel_attention(const LaunchCtx& ctx, float* out, const float* qkv, co
   if (head_dim != 96) fail(SBV2_ERR_UNSUPPORTED, "rel_attention: head_dim must be 96");
   constexpr int D = 96;
   int R = 2 * window + 1;
-  size_t smem = sizeof(float) * (size_t)(D * (AQ + 1) + D * (AK + 1) + AK * D + AQ * (AK + 1) + 2 * R * D + AQ * R);
+  auto smem_for = [&](int aq) { return sizeof(float) * (size_t)(D * (aq + 1) + D * (AK + 1) + AK * D + aq * (AK + 1) + 2 * R * D + aq * R); };
   static PerDeviceOnce attr_once;
-  attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); });
-  dim3 grid((seg.max_len + AQ - 1) / AQ, heads, seg.n);
-  rel_attention_kernel<D><<<grid, 256, smem, ctx.stream>>>(out, qkv, rel_k, rel_v, heads, window, seg);
+  attr_once.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  });
+  static const int force_rq = [] { const char* e = getenv("SBV2_B200_TEXT_ATTN_RQ"); return e ? atoi(e) : 0; }();  // test hook
+  if (force_rq == 1 || (force_rq == 0 && (long long)seg.max_len * seg.n <= 1024)) {  // few phoneme rows: 16-query CTAs
+    dim3 grid((seg.max_len + 15) / 16, heads, seg.n);
+    rel_attention_kernel<D, 1><<<grid, 256, smem_for(16), ctx.stream>>>(out, qkv, rel_k, rel_v, heads, window, seg);
+  } else {
+    dim3 grid((seg.max_len + 63) / 64, heads, seg.n);
+    rel_attention_kernel<D, 4><<<grid, 256, smem_for(64), ctx.stream>>>(out, qkv, rel_k, rel_v, heads, window, seg);
+  }
   POST_LAUNCH(ctx);
 }
 

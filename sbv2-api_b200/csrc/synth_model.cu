@@ -1293,6 +1293,7 @@ void synth_run(sbv2_model* mm, sbv2_device_batch* b) {
   bseg.len = b->ylen_dev.as<int>() + 1;
   bseg.n = 1;
   bseg.max_len = B;
+  bseg.vectors = true;
   int* d_ylen = b->ylen_dev.as<int>() + 2;
 
   auto ens = [&](int id, size_t floats) { M.ws[id].ensure(floats * 4); return M.ws[id].as<float>(); };
@@ -1803,6 +1804,7 @@ void synth_decode(sbv2_model* mm, const float* const* z, const int64_t* t_y, con
   bseg.len = bseg.start + 1;
   bseg.n = 1;
   bseg.max_len = batch;
+  bseg.vectors = true;
   M.ws[W_Z].ensure(size_t(ny) * C * 4);
   M.ws[W_G].ensure(size_t(batch) * hp.gin * 4);
   float* zr = M.ws[W_Z].as<float>();
