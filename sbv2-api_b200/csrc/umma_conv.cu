@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   constexpr bool PAIR2 = (VARIANT & 8) != 0;
   constexpr bool CLUSTER = (VARIANT & 2) != 0 || PAIR2;
   constexpr bool MCAST = (VARIANT & 2) != 0 && !PAIR2;
+  // bit 4: split-K over a cluster (few-rows GEMMs with a deep K: one sentence through DeBERTa).  The `cluster` CTAs of a
+  // cluster share ONE item; CTA `rank` accumulates K chunks [rank * nkc / cluster, (rank + 1) * nkc / cluster) — the serial
+  // MMA chain and the weight bytes one SM has to pull both shrink by `cluster`.  The partial accumulators are exchanged
+  // through distributed shared memory and summed in rank order (deterministic), each CTA finishing 128 / cluster rows.
+  constexpr bool SPLITK = (VARIANT & 16) != 0;
   extern __shared__ __align__(128) uint8_t smem[];
   // warp index made provably warp-uniform so that role branches are uniform and the MMA
   // descriptors stay in uniform registers (UTCHMMA takes UR operands; R2UR per MMA is slow)
@@ -175,8 +180,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
   const int acc_cols = p.mt * p.nb;  // TMEM columns of one accumulator set
   // pair mode, leader side: "the peer's slot / stage / accumulator set is ready" (arrivals come from the peer CTA)
   const uint32_t bar_paf = sBar + 3072, bar_pbf = bar_paf + 8 * MAX_ASLOTS, bar_pacce = bar_pbf + 8 * MAX_STAGES;
-  const int nc = CLUSTER ? p.cluster : 1;
-  const int rank = CLUSTER ? (int)cluster_ctarank() : 0;
+  const int nc = (CLUSTER || SPLITK) ? p.cluster : 1;
+  const int rank = (CLUSTER || SPLITK) ? (int)cluster_ctarank() : 0;
+  const int kc_lo = SPLITK ? rank * p.nkc / nc : 0, kc_hi = SPLITK ? (rank + 1) * p.nkc / nc : p.nkc;  // this CTA's K chunks
+  const int step_lo = kc_lo * p.taps, step_hi = kc_hi * p.taps;
   const int unit0 = (int)blockIdx.x / nc, unit_step = (int)gridDim.x / nc;  // this CTA's (cluster's) first item and stride
   const uint16_t cta_mask = (uint16_t)((1u << nc) - 1u);
 
@@ -250,9 +257,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
             }
           ++a_it;
         };
-        for (int kc = 0; kc < p.nkc; ++kc) load_a_chunk(kc);
+        for (int kc = kc_lo; kc < kc_hi; ++kc) load_a_chunk(kc);
         TRACE(1, pit);
       }
+    }
+    if (SPLITK) {
+      __syncwarp();
+      cluster_sync_all();  // split-K exchange point: every CTA's partial tile is in its shared memory
     }
   } else if (warp == B_PRODUCER_WARP) {
     if (lane == 0) {
@@ -268,8 +279,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         auto load_b = [&](int i) {  // i-th stage load of this item
           const uint32_t st = b_it % p.nstages;
           mbar_wait_poll(bar_be + 8 * st, ((b_it / p.nstages) & 1) ^ 1);
-          const int first_step = i * p.sps;
-          const int nsteps = min(p.sps, p.total_steps - first_step);
+          const int first_step = step_lo + i * p.sps;
+          const int nsteps = min(p.sps, step_hi - first_step);
           const uint32_t bytes = step_bytes * nsteps;
           mbar_expect_tx(bar_bf + 8 * st, bytes);
           if (MCAST) {
@@ -283,8 +294,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           }
           ++b_it;
         };
-        for (int i = 0; i < p.nloads; ++i) load_b(i);
+        const int nloads = SPLITK ? (step_hi - step_lo + p.sps - 1) / p.sps : p.nloads;
+        for (int i = 0; i < nloads; ++i) load_b(i);
       }
+    }
+    if (SPLITK) {
+      __syncwarp();
+      cluster_sync_all();
     }
   } else if (warp == 1) {
     {
@@ -352,11 +368,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           if (lane == 0) TRACE(2, it);
           const uint32_t tmem_acc = tmem_base + buf * acc_cols;
           const int grp = (item % (p.n_nblk * p.n_groups)) / p.n_nblk;
-          int step = 0, si = 0;
-          for (int kc = 0; kc < p.nkc; ++kc) {
+          int step = step_lo, si = 0;
+          for (int kc = kc_lo; kc < kc_hi; ++kc) {
             mbar_wait_poll(bar_af + 8 * a_slot_i, a_par);
             if (PAIR2) mbar_wait_poll_cluster(bar_paf + 8 * a_slot_i, a_par);
-            if (kc == 0 && lane == 0) TRACE(3, it);
+            if (kc == kc_lo && lane == 0) TRACE(3, it);
             const uint64_t a_chunk = a_desc0 + ((sA - cta_win + slot_bytes * a_slot_i) >> 4) + (uint32_t)p.halo_lo;
             for (int tap = 0; tap < p.taps; ++tap, ++step) {
               uint32_t b_addr;
@@ -375,14 +391,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
               }
               const uint64_t a_tap = a_chunk + (int64_t)p.tap_shift[grp * MAX_TAPS + tap];
               const uint64_t b_d = b_desc0 + ((b_addr - cta_win) >> 4);
-              const uint32_t accf = step > 0 ? 1u : 0u;
+              const uint32_t accf = step > step_lo ? 1u : 0u;
               if (leader) {
                 if (PAIR2) issue_mmas_pair<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
                 else issue_mmas<MT, K16>(tmem_acc, a_tap, b_d, a_kstep, b_kstep, nb_u, idesc, accf);
               }
               if (!p.b_resident) {
                 ++si;
-                if (si == p.sps || step == p.total_steps - 1) {
+                if (si == p.sps || step == step_hi - 1) {
                   if (leader) {
                     if (PAIR2) tc_commit_pair(bar_be + 8 * b_st);
                     else if (MCAST) tc_commit_multicast(bar_be + 8 * b_st, cta_mask);
@@ -427,6 +443,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       }
 #undef SBV2_ROLE_CASE
     }
+    if (SPLITK) {
+      __syncwarp();
+      cluster_sync_all();
+    }
   } else {
     // ---------------- epilogue warps ----------------
     const int wq = warp & 3;           // TMEM lane quarter this warp may access
@@ -437,25 +457,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
     const int items_per_acc = p.nb / nch;
     const int n_sub = p.mt * items_per_acc;
     const bool bias_per_item = p.n_nblk > 1 || p.bias_utt != nullptr;
-    uint32_t it = 0;
-    for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
-      const uint32_t buf = it & 1;
-      const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
-      float* bias = bias_s + (bias_per_item ? buf * p.nb : 0);
-      if (bias_per_item || it == 0) {
-        // (per item: the set used two items ago has been fully consumed — its acc_empty arrivals
-        // happen after the last read)
-        for (int i = etid; i < p.nb; i += NUM_EPI_WARPS * 32) {
-          float v = p.bias[(size_t)ti.nblk * p.nb + i];
-          if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.bias_utt_ld + (size_t)ti.nblk * p.nb + i];
-          bias[i] = v;
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");
-      }
-      mbar_wait(bar_accf + 8 * buf, (it >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 64) TRACE(5, it);
-      const uint32_t tmem_acc = tmem_base + buf * acc_cols;
+    // drain one accumulator set: rows [row_lo, row_hi) of the tile (the whole tile unless split-K)
+    auto drain = [&](const TileInfo& ti, uint32_t tmem_acc, const float* bias, int row_lo, int row_hi) {
       if (GATE) {
         const int per_acc = p.gate_half / 16;
         for (int sub = part; sub < p.mt * per_acc; sub += NUM_EPI_WARPS / 4) {
@@ -471,8 +474,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
       for (int sub = part; sub < n_sub; sub += NUM_EPI_WARPS / 4) {
         const int a = sub / items_per_acc;
         const int c0 = (sub - a * items_per_acc) * nch;
-        const int t = ti.t0 + a * 128 + wq * 32 + lane;
-        const bool valid = t < ti.len;
+        const int r = a * 128 + wq * 32 + lane;
+        const int t = ti.t0 + r;
+        const bool valid = t < ti.len && (!SPLITK || (r >= row_lo && r < row_hi));
         const long long orow = (long long)p.pstart_out[ti.b] + (long long)t * p.out_mul + p.out_off + p.group_out_off[ti.grp];
         const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * p.nb + c0);
         const int cg = ti.nblk * p.nb + c0;
@@ -491,6 +495,90 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
           else epilogue_item<16, false, 0>(p, taddr, valid, orow, cg, bias + c0);
         }
       }
+    };
+    auto load_bias = [&](const TileInfo& ti, float* bias) {
+      for (int i = etid; i < p.nb; i += NUM_EPI_WARPS * 32) {
+        float v = p.bias[(size_t)ti.nblk * p.nb + i];
+        if (p.bias_utt) v += p.bias_utt[(size_t)ti.b * p.bias_utt_ld + (size_t)ti.nblk * p.nb + i];
+        bias[i] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");
+    };
+    if (SPLITK) {
+      // One item per cluster (launch_umma).  (1) every CTA copies its partial accumulators (valid rows) into its own shared
+      // memory — the activation ring: all of this CTA's MMAs, the ring's only readers, have completed; (2) cluster barrier;
+      // (3) CTA `rank` sums rows [rank * 128 / nc, ...) over the peers in rank order through DSMEM, puts the sums back into
+      // its TMEM accumulators and drains those rows through the ordinary epilogue.
+      const bool have = unit0 < p.n_items;
+      TileInfo ti{};
+      const int dpitch = p.nb + 4;  // floats per dumped row
+      const int n16 = p.nb / 16;
+      const int r = wq * 32 + lane;
+      if (have) {
+        ti = locate_item<false>(p, unit0, 0);
+        load_bias(ti, bias_s);
+        mbar_wait(bar_accf, 0);
+        tc_fence_after();
+        if (threadIdx.x == 64) TRACE(5, 0);
+        float* dump = reinterpret_cast<float*>(smem) + (size_t)r * dpitch;
+        for (int g = part; g < n16; g += NUM_EPI_WARPS / 4) {
+          uint32_t v[16];
+          tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 16), v);
+          tc_wait_ld();
+          if (ti.t0 + r < ti.len) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(dump + g * 16 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      __syncwarp();
+      cluster_sync_all();
+      if (have) {
+        const int row_lo = rank * 128 / nc, row_hi = (rank + 1) * 128 / nc;
+        const bool mine = r >= row_lo && r < row_hi && ti.t0 + r < ti.len;
+        if (wq * 32 < row_hi && wq * 32 + 32 > row_lo) {  // warp-uniform: this warp's lane quarter overlaps the slice
+          for (int g = part; g < n16; g += NUM_EPI_WARPS / 4) {
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            if (mine) {
+              const uint32_t local = sA + (uint32_t)((r * dpitch + g * 16) * 4);
+              for (int q = 0; q < nc; ++q) {
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                  const float4 f = ld_dsmem_f4(local + 16 * v4, (uint32_t)q);
+                  acc[4 * v4] += f.x;
+                  acc[4 * v4 + 1] += f.y;
+                  acc[4 * v4 + 2] += f.z;
+                  acc[4 * v4 + 3] += f.w;
+                }
+              }
+            }
+            __syncwarp();
+            tc_st16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 16), reinterpret_cast<const uint32_t*>(acc));
+          }
+          tc_wait_st();
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"r"(NUM_EPI_WARPS * 32) : "memory");  // the drain's column split differs from the sum's
+        tc_fence_after();
+        drain(ti, tmem_base, bias_s, row_lo, row_hi);
+        tc_fence_before();
+        if (threadIdx.x == 64) TRACE(6, 0);
+      }
+    } else {
+    uint32_t it = 0;
+    for (int item = unit0; item < p.n_items; item += unit_step, ++it) {
+      const uint32_t buf = it & 1;
+      const TileInfo ti = locate_item<CLUSTER>(p, item, rank);
+      float* bias = bias_s + (bias_per_item ? buf * p.nb : 0);
+      // (per item: the set used two items ago has been fully consumed — its acc_empty arrivals happen after the last read)
+      if (bias_per_item || it == 0) load_bias(ti, bias);
+      mbar_wait(bar_accf + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64) TRACE(5, it);
+      drain(ti, tmem_base + buf * acc_cols, bias, 0, TM);
       // release the accumulator set
       tc_fence_before();
       __syncwarp();
@@ -500,10 +588,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_kernel(const __grid_
         if (PAIR2 && rank != 0) mbar_arrive_remote(bar_pacce + 8 * buf, 0);  // the leader issues the MMAs into both TMEMs
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
+  if (CLUSTER || SPLITK) cluster_sync_all();  // no CTA leaves while a peer may still multicast into / read from its shared memory
   if (warp == 1) {
     if (PAIR2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -850,6 +939,8 @@ void set_smem_attr() {
     CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CUDA_CHECK(cudaFuncSetAttribute(umma_conv_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   });
 }
 
@@ -1070,9 +1161,28 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   a.cluster = nc;
   a.n_tiles = gi.n_tiles[slot];
   a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * a.n_nblk * L.n_groups;  // cluster items
+  // Split-K over a cluster (ConvCall::splitk: DeBERTa's GEMMs when a call has few tokens).  With 16-64 items each CTA
+  // walks the whole K alone: K / 16 MMAs in a row and K * nb * 2 bytes of weights through one SM's few stages in flight
+  // (one 7-token sentence: 40 us per GEMM for 1-2 us of work).  S CTAs per item divide both.  SBV2_B200_SPLITK=0: off.
+  static int splitk_env = -1;
+  if (splitk_env < 0) {
+    const char* e = getenv("SBV2_B200_SPLITK");
+    splitk_env = e ? atoi(e) : 1;
+  }
+  int splitk = 1;
+  if (c.splitk && splitk_env != 0 && nc == 1 && !pair && L.mt == 1 && !L.b_resident && L.n_groups == 1 && c.gate_half == 0 && L.nkc >= 8 &&
+      size_t(128) * (L.nb + 4) * 4 <= size_t(L.a_slots) * (L.kc / 8) * (128 + L.halo_lo + L.halo_hi) * 16) {
+    for (int sk = 8; sk >= 2 && splitk == 1; sk >>= 1)
+      if (a.n_items * sk <= num_sms && L.nkc % sk == 0 && L.nkc / sk >= 2) splitk = sk;
+  }
   dim3 grid(std::min(a.n_items, num_sms / nc) * nc);
+  if (splitk > 1) {
+    nc = splitk;
+    a.cluster = splitk;
+    grid = dim3(a.n_items * splitk);  // one item per cluster
+  }
   void (*kernel)(UmmaConvArgs) = nullptr;
-  switch ((c.gate_half > 0 ? 1 : 0) | (pair ? 8 : (nc > 1 ? 2 : 0)) | ((c.rm_out != nullptr || c.split_out != nullptr) ? 4 : 0)) {
+  switch ((c.gate_half > 0 ? 1 : 0) | (pair ? 8 : (splitk > 1 ? 16 : (nc > 1 ? 2 : 0))) | ((c.rm_out != nullptr || c.split_out != nullptr) ? 4 : 0)) {
     case 0: kernel = umma_conv_kernel<0>; break;
     case 1: kernel = umma_conv_kernel<1>; break;
     case 2: kernel = umma_conv_kernel<2>; break;
@@ -1081,6 +1191,8 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
     case 6: kernel = umma_conv_kernel<6>; break;
     case 8: kernel = umma_conv_kernel<8>; break;
     case 12: kernel = umma_conv_kernel<12>; break;
+    case 16: kernel = umma_conv_kernel<16>; break;
+    case 20: kernel = umma_conv_kernel<20>; break;
     default: fail(SBV2_ERR_INTERNAL, "conv kernel: unsupported epilogue combination");
   }
   launch_pdl_cluster(ctx.pdl && !pair, nc, kernel, grid, dim3(NUM_THREADS), L.smem, ctx.stream, a);

@@ -140,6 +140,9 @@ struct ConvCall {
   bool tmap = false;
   // run as CTA pairs (tcgen05 cta_group::2, M = 256) when the layer's packing allows it (see launch_umma)
   bool pair = false;
+  // split K over a thread-block cluster when the launch has few items (see launch_umma): the fp32 sums are formed in a
+  // different order than without the split, so callers that promise batch == single results bit for bit must not ask
+  bool splitk = false;
 };
 void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const Geom& go, const ConvCall& c, int n_utt);
 void launch_zero_gaps(const LaunchCtx& ctx, __half* buf, int C, const Geom& g, int n_utt);

@@ -158,6 +158,27 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+               "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16 bytes from the shared memory of CTA `rank` of this cluster, at the address `local` has in this CTA's window
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local, uint32_t rank) {
+  float4 f;
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %4, %5;\n"
+      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n"
+      "}\n"
+      : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+      : "r"(local), "r"(rank)
+      : "memory");
+  return f;
+}
 
 __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0;
