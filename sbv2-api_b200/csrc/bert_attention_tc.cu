@@ -559,6 +559,276 @@ __global__ void __launch_bounds__(160, 1) deberta_attention_tc_multi_kernel(__ha
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact-numerics variant (SBV2_B200_BERT=exact, the default) for sequences of at most 128 tokens: every operand is a
+// two-term fp16 split x = h0 + h1 (the plane blocks [h0 | h1 | h0] the split GEMMs exchange), every product is the three
+// cross terms h0 g0 + h0 g1 + h1 g0 accumulated in fp32, the position-bias windows go through ONE fp32 shared-memory tile
+// (c2p written, p2c added), and the probabilities are split as well before P V.  Replaces the fp32 CUDA-core kernel
+// (deberta_attention_kernel<true>) there; measured error against it: see tests/test_gpu_bert.py.
+//   qkv_s : split planar [h0 | h1 | h0] x [3 * heads * 8 planes][rows][8], values scaled by sc (power of two)
+//   pos_*_s: fp16 [2 terms][heads][8][n_pos][8], scaled by sc
+//   out_s : split planar ctx [h0 | h1 | h0] x [heads * 8 planes], scaled by sc (= V's scale: O needs no rescaling)
+// Shared memory: six 16 KB operand tiles, one 64 KB buffer (posK terms, then posQ terms, then P terms), the fp32 bias tile.
+constexpr int BCS = T + 4;                               // bias tile row pitch (floats): 16-byte row reads, odd * 4 skew
+constexpr uint32_t BIAS_BYTES = T * BCS * 4;             // 67 584 B
+constexpr uint32_t EX_SMEM = 6 * QKV_BYTES + 2 * POS_BYTES + BIAS_BYTES + 128;
+
+__global__ void __launch_bounds__(160, 1) deberta_attention_tc_exact_kernel(__half* out_s, long long out_blk, const __half* qkv_s,
+                                                                            long long qkv_blk, const __half* pos_k_s, const __half* pos_q_s,
+                                                                            int n_pos, int win0, int heads, float inv_sc2, PlanarSegs s) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int len = s.len[b];
+  if (len <= 0) return;
+  const long long pbase = s.pstart[b];
+
+  const uint32_t sQ0 = smem_u32(smem);
+  const uint32_t sQ1 = sQ0 + QKV_BYTES, sK0 = sQ1 + QKV_BYTES, sK1 = sK0 + QKV_BYTES, sV0 = sK1 + QKV_BYTES, sV1 = sV0 + QKV_BYTES;
+  const uint32_t sW0 = sV1 + QKV_BYTES, sW1 = sW0 + POS_BYTES;  // window terms 0 / 1; later P terms 0 / 1
+  const uint32_t sBias = sW1 + POS_BYTES, sBar = sBias + BIAS_BYTES;
+  const uint32_t bar_load = sBar, bar_s1 = sBar + 8, bar_c = sBar + 16, bar_s2 = sBar + 24, bar_p = sBar + 32, bar_o = sBar + 40,
+                 bar_w2 = sBar + 48;
+  const uint32_t tmem_slot = sBar + 56;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ0));
+  float* Bs = reinterpret_cast<float*>(smem + (sBias - sQ0));  // bias(i, j) = c2p + p2c at [i][j]
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_c, 128);
+    mbar_init(bar_s2, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_w2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int q_plane0 = h * DPL, k_plane0 = heads * DPL + h * DPL, v_plane0 = 2 * heads * DPL + h * DPL;
+  const size_t pos_term = (size_t)heads * DPL * n_pos * 8;  // halves between the two terms of a position table
+
+  if (warp == 4) {
+    // ---------------- control warp: loads and MMA issue ----------------
+    if (lane == 0) mbar_expect_tx(bar_load, 6 * QKV_BYTES + 2 * POS_BYTES);
+    __syncwarp();
+    {
+      const size_t row8 = (size_t)pbase * 8;
+      // 48 operand planes (q / k / v x 2 terms x 8) and 16 window planes over the 32 lanes
+      for (int i = lane; i < 48; i += 32) {
+        const int which = i / 16, term = (i >> 3) & 1, pl = i & 7;  // which: 0 q, 1 k, 2 v
+        const int plane0 = which == 0 ? q_plane0 : (which == 1 ? k_plane0 : v_plane0);
+        const uint32_t dst = sQ0 + (uint32_t)(which * 2 + term) * QKV_BYTES + pl * T * 16;
+        bulk_g2s(dst, qkv_s + (size_t)term * qkv_blk + (size_t)(plane0 + pl) * s.plane_stride + row8, T * 16, bar_load);
+      }
+      if (lane < 16) {
+        const int term = lane >> 3, pl = lane & 7;
+        bulk_g2s(sW0 + term * POS_BYTES + pl * W * 16, pos_k_s + term * pos_term + ((size_t)(h * DPL + pl) * n_pos + win0) * 8, W * 16, bar_load);
+      }
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    const uint64_t dq0 = make_desc(sQ0, T * 16, 128), dq1 = make_desc(sQ1, T * 16, 128);
+    const uint64_t dk0 = make_desc(sK0, T * 16, 128), dk1 = make_desc(sK1, T * 16, 128);
+    const uint64_t dw0 = make_desc(sW0, W * 16, 128), dw1 = make_desc(sW1, W * 16, 128);
+    const uint64_t dp0 = make_desc(sW0, T * 16, 128), dp1 = make_desc(sW1, T * 16, 128);  // P terms reuse the window buffer
+    const uint64_t dv0 = make_desc(sV0, 128, T * 16), dv1 = make_desc(sV1, 128, T * 16);
+    constexpr uint32_t ID_S = idesc_f16(T, 0), ID_B = idesc_f16(W, 0), ID_O = idesc_f16(D, 1);
+    // three cross terms of a product, K-major x K-major: (a0, b0), (a0, b1), (a1, b0)
+    auto cross = [&](uint32_t tm, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1, uint32_t astep, uint32_t bstep, uint32_t id, int nk) {
+      for (int k = 0; k < nk; ++k) tc_mma_f16(tm, a0 + (uint64_t)(k * astep), b0 + (uint64_t)(k * bstep), id, k > 0 ? 1u : 0u);
+      for (int k = 0; k < nk; ++k) tc_mma_f16(tm, a0 + (uint64_t)(k * astep), b1 + (uint64_t)(k * bstep), id, 1u);
+      for (int k = 0; k < nk; ++k) tc_mma_f16(tm, a1 + (uint64_t)(k * astep), b0 + (uint64_t)(k * bstep), id, 1u);
+    };
+    if (elect_one_sync()) {
+      cross(tmem + TM_S, dq0, dq1, dk0, dk1, 2 * T, 2 * T, ID_S, D / 16);
+      cross(tmem + TM_B, dq0, dq1, dw0, dw1, 2 * T, 2 * W, ID_B, D / 16);
+      tc_commit(bar_s1);
+    }
+    __syncwarp();
+    // the posK windows have been consumed once those MMAs complete: fetch the posQ windows into the same buffer
+    mbar_wait(bar_s1, 0);
+    if (lane == 0) mbar_expect_tx(bar_w2, 2 * POS_BYTES);
+    __syncwarp();
+    if (lane < 16) {
+      const int term = lane >> 3, pl = lane & 7;
+      bulk_g2s(sW0 + term * POS_BYTES + pl * W * 16, pos_q_s + term * pos_term + ((size_t)(h * DPL + pl) * n_pos + win0) * 8, W * 16, bar_w2);
+    }
+    __syncwarp();
+    mbar_wait(bar_w2, 0);
+    mbar_wait(bar_c, 0);  // C2P has been copied out of TMEM
+    tc_fence_after();
+    if (elect_one_sync()) {
+      cross(tmem + TM_B, dk0, dk1, dw0, dw1, 2 * T, 2 * W, ID_B, D / 16);
+      tc_commit(bar_s2);
+    }
+    __syncwarp();
+    mbar_wait(bar_p, 0);  // P terms (and the zeroed V rows) visible to the async proxy
+    tc_fence_after();
+    if (elect_one_sync()) {
+      // O = P0 V0 + P0 V1 + P1 V0: A K-major (P), B MN-major (V)
+      for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp0 + (uint64_t)(k * 2 * T), dv0 + (uint64_t)(k * 16), ID_O, k > 0 ? 1u : 0u);
+      for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp0 + (uint64_t)(k * 2 * T), dv1 + (uint64_t)(k * 16), ID_O, 1u);
+      for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp1 + (uint64_t)(k * 2 * T), dv0 + (uint64_t)(k * 16), ID_O, 1u);
+      tc_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- softmax threads ----------------
+    const int row = warp * 32 + lane;  // query row i; also key row j while staging P2C
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c_scale = 1.4426950408889634f / sqrtf(3.0f * (float)D) * inv_sc2;  // log2(e) / sqrt(3 d), operands carry sc each
+    mbar_wait(bar_load, 0);
+    if (row >= len) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int pl = 0; pl < DPL; ++pl) {
+        *reinterpret_cast<uint4*>(smem + (sV0 - sQ0) + (size_t)(pl * T + row) * 16) = z;
+        *reinterpret_cast<uint4*>(smem + (sV1 - sQ0) + (size_t)(pl * T + row) * 16) = z;
+      }
+    }
+    // C2P: column c = i - j + 127 of row i goes to Bs[i][j], j = i + 127 - c
+    mbar_wait(bar_s1, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int q = 0; q < W / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_B + q * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = row + (T - 1) - (q * 32 + e);
+        if (j >= 0 && j < T) Bs[row * BCS + j] = __uint_as_float(v[e]);
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar_c);
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // every c2p entry is written before any p2c entry is added
+    // P2C: thread = key row j; column c belongs to query i = c + j - 127: Bs[i][j] += it
+    mbar_wait(bar_s2, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int q = 0; q < W / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_B + q * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int ii = q * 32 + e + row - (T - 1);
+        if (ii >= 0 && ii < T) Bs[ii * BCS + row] += __uint_as_float(v[e]);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // pass 1: row maximum of s = S + bias
+    const float* brow = Bs + row * BCS;
+    float m = -CUDART_INF_F;
+#pragma unroll 1
+    for (int q = 0; q < T / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_S + q * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 bb = *reinterpret_cast<const float4*>(brow + q * 32 + 4 * e4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = q * 32 + 4 * e4 + u;
+          const float sc = __uint_as_float(v[4 * e4 + u]) + bv[u];
+          m = fmaxf(m, j < len ? sc : -CUDART_INF_F);
+        }
+      }
+    }
+    // pass 2: p = 2^((s - m) c), unnormalised; two fp16 terms into the P tiles (the window buffer: the posQ MMAs have completed)
+    float l = 0.f;
+    uint8_t* prow0 = smem + (sW0 - sQ0) + row * 16;
+    uint8_t* prow1 = smem + (sW1 - sQ0) + row * 16;
+    const float mc = m * c_scale;
+#pragma unroll 1
+    for (int q = 0; q < T / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_S + q * 32, v);
+      tc_wait_ld();
+      float pv[32];
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 bb = *reinterpret_cast<const float4*>(brow + q * 32 + 4 * e4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = q * 32 + 4 * e4 + u;
+          const float sc = __uint_as_float(v[4 * e4 + u]) + bv[u];
+          const float p = j < len ? ex2_approx(fmaf(sc, c_scale, -mc)) : 0.f;
+          pv[4 * e4 + u] = p;
+          l += p;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u0, u1;
+        __half2* h0 = reinterpret_cast<__half2*>(&u0);
+        __half2* h1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = pv[g * 8 + 2 * e], x1 = pv[g * 8 + 2 * e + 1];
+          const __half2 a = __floats2half2_rn(x0, x1);
+          const float2 af = __half22float2(a);
+          h0[e] = a;
+          h1[e] = __floats2half2_rn(x0 - af.x, x1 - af.y);
+        }
+        *reinterpret_cast<uint4*>(prow0 + (size_t)(q * 4 + g) * T * 16) = u0;
+        *reinterpret_cast<uint4*>(prow1 + (size_t)(q * 4 + g) * T * 16) = u1;
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(bar_p);
+    // epilogue: O / l (carries V's scale sc, the scale of the consuming split GEMM) -> split planar ctx
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+#pragma unroll 1
+    for (int q = 0; q < D / 32; ++q) {
+      uint32_t v[32];
+      tc_ld32(lane_addr + TM_O + q * 32, v);
+      tc_wait_ld();
+      if (row < len) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u0, u1;
+          __half2* h0 = reinterpret_cast<__half2*>(&u0);
+          __half2* h1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = __uint_as_float(v[g * 8 + 2 * e]) * inv_l, x1 = __uint_as_float(v[g * 8 + 2 * e + 1]) * inv_l;
+            const __half2 a = __floats2half2_rn(x0, x1);
+            const float2 af = __half22float2(a);
+            h0[e] = a;
+            h1[e] = __floats2half2_rn(x0 - af.x, x1 - af.y);
+          }
+          __half* dst = out_s + (size_t)(h * DPL + q * 4 + g) * s.plane_stride + (pbase + row) * 8;
+          *reinterpret_cast<uint4*>(dst) = u0;
+          *reinterpret_cast<uint4*>(dst + out_blk) = u1;
+          *reinterpret_cast<uint4*>(dst + 2 * out_blk) = u0;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len) { return head_dim == D && span >= 254 && max_len <= T; }
@@ -590,6 +860,25 @@ void launch_deberta_attention_tc_multi(const LaunchCtx& ctx, __half* ctx_out, co
   attr_once.run([&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
   dim3 grid(heads, s.n, (s.max_len + T - 1) / T);
   deberta_attention_tc_multi_kernel<<<grid, 160, smem, ctx.stream>>>(ctx_out, qkv, pos_k_p, pos_q_p, n_pos, bucket_idx, max_rel, heads, s);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+// Exact-numerics tensor-core attention (<= 128 tokens).  qkv_s / ctx_s are split-planar [h0 | h1 | h0] buffers scaled by `sc`
+// (qkv_blk / ctx_blk: halves between plane blocks); pos_*_s: two-term fp16 position tables scaled by `sc` as well.
+void launch_deberta_attention_tc_exact(const LaunchCtx& ctx, __half* ctx_s, long long ctx_blk, const __half* qkv_s, long long qkv_blk,
+                                       const __half* pos_k_s, const __half* pos_q_s, int n_pos, int span, int heads, float sc,
+                                       const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (!deberta_attention_tc_supported(D, span, s.max_len)) fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention: unsupported shape");
+  const int win0 = span - (T - 1);
+  if (win0 < 0 || win0 + W > n_pos) fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention: position window out of range");
+  static PerDeviceOnce attr_once;
+  attr_once.run(
+      [&] { CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EX_SMEM)); });
+  dim3 grid(heads, s.n);
+  deberta_attention_tc_exact_kernel<<<grid, 160, EX_SMEM, ctx.stream>>>(ctx_s, ctx_blk, qkv_s, qkv_blk, pos_k_s, pos_q_s, n_pos, win0, heads,
+                                                                         1.0f / (sc * sc), s);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

@@ -29,6 +29,8 @@ struct BertLayer {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   float *pos_k = nullptr, *pos_q = nullptr;  // [hidden, 2*span] (transposed) projections of LN(rel_embeddings)
   __half *pos_k_p = nullptr, *pos_q_p = nullptr;  // the same as fp16 [heads][64/8][2*span][8] (tensor-core attention operands)
+  // exact mode: two-term fp16 splits of the same tables, [2 terms][heads][64/8][2*span][8], values scaled by kSplitScale
+  __half *pos_k_s = nullptr, *pos_q_s = nullptr;
 };
 
 struct BertModel : sbv2_model {
@@ -47,6 +49,8 @@ struct BertModel : sbv2_model {
   bool exact = true;             // SBV2_B200_BERT=fp16 selects the single-term fp16 path
   int max_cin = 0;               // widest GEMM input (exact mode: size of the split buffer)
   DBuf x_emb, x_qkv, x_ctx, x_f1, x_y, x_split;  // exact mode: fp32 row-major activations + the split operand buffer
+  DBuf x_qkvs;                   // exact mode, <= 128 tokens: q|k|v as split-planar operands of the tensor-core attention
+  uint64_t x_qkvs_cleared_gen = 0;
   PinnedBuf pin_meta, pin_io;
 };
 
@@ -61,6 +65,7 @@ std::string find_prefix(const OnnxModel& m) {
 // (K / 16 MMAs at the 48-cycle issue floor: 19 us for K = 12288) and by launch latency, not by the weight stream, so 16-wide
 // blocks only multiply the CTAs that each re-read the activations (measured: 7.4 -> 8.9 ms exact, 2.8 -> 3.3 ms fp16)
 constexpr int kSmallNb = 64;
+constexpr float kSplitScale = 16.f;  // = ConvLayer::in_scale of the split layers (checked in the forward)
 constexpr int64_t kSmallTokens = 256;  // calls with at most this many tokens use it
 
 int log_bucket(int rel, int bucket_size, int max_position) {
@@ -209,6 +214,18 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
         for (int c = 0; c < H; ++c)
           for (size_t r = 0; r < np2; ++r) hp16[(size_t(c / 8) * np2 + r) * 8 + c % 8] = __float2half_rn(hrow[r * H + c]);
         (which == 0 ? B.pos_k_p : B.pos_q_p) = static_cast<__half*>(M->upload_bytes(hp16.data(), hp16.size() * 2));
+        if (M->exact) {
+          std::vector<__half> hs(2 * np2 * H);
+          for (int c = 0; c < H; ++c)
+            for (size_t r = 0; r < np2; ++r) {
+              const float x = hrow[r * H + c] * kSplitScale;
+              const __half h0 = __float2half_rn(x);
+              const size_t o = (size_t(c / 8) * np2 + r) * 8 + c % 8;
+              hs[o] = h0;
+              hs[np2 * H + o] = __float2half_rn(x - __half2float(h0));
+            }
+          (which == 0 ? B.pos_k_s : B.pos_q_s) = static_cast<__half*>(M->upload_bytes(hs.data(), hs.size() * 2));
+        }
       }
       (which == 0 ? B.pos_k : B.pos_q) = dst;
     }
@@ -259,7 +276,7 @@ sbv2_model* create_bert_model(const OnnxModel& m, int device) {
     }
     M->bucket_idx = static_cast<int*>(M->upload_bytes(tab.data(), tab.size() * 4));
   }
-  for (DBuf* b : {&M->ids, &M->h, &M->embp, &M->hp, &M->qkvp, &M->ctxp, &M->f1p, &M->y32, &M->meta, &M->outd, &M->x_emb, &M->x_qkv, &M->x_ctx,
+  for (DBuf* b : {&M->ids, &M->h, &M->embp, &M->hp, &M->qkvp, &M->ctxp, &M->f1p, &M->y32, &M->meta, &M->outd, &M->x_emb, &M->x_qkv, &M->x_qkvs, &M->x_ctx,
                   &M->x_f1, &M->x_y, &M->x_split})
     b->stream = M->stream;
   std::ostringstream js;
@@ -346,6 +363,20 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     __half* sp_c = sp_b + R * 3 * size_t(H);
     const float sc = M.layers[0].qkv.in_scale;  // the same for every split layer
     if (M.has_conv) launch_zero_gaps(ctx, sp_e, 3 * H, G, batch);  // k = 3 ConvLayer halo; the GEMMs have none
+    // sequences of at most 128 tokens: attention on the tensor cores with split operands (SBV2_B200_BERT_ATTN=simt: fp32
+    // CUDA-core kernel); q|k|v then leave their GEMM as split planes instead of fp32 rows
+    const bool tc_exact = M.use_tc_attn && M.hidden / M.heads == 64 && sc == kSplitScale && deberta_attention_tc_supported(64, M.span, max_len);
+    __half* sp_qkv = nullptr;
+    const long long qkv_blk = (long long)(3 * H / 8) * ps.plane_stride, ctx_blk = (long long)(H / 8) * ps.plane_stride;
+    if (tc_exact) {
+      M.x_qkvs.ensure(R * 9 * size_t(H) * 2);
+      if (M.x_qkvs.gen != M.x_qkvs_cleared_gen) {
+        // rows past an utterance's end are read as operands: they must hold finite values
+        CUDA_CHECK(cudaMemsetAsync(M.x_qkvs.p, 0, M.x_qkvs.cap, M.stream));
+        M.x_qkvs_cleared_gen = M.x_qkvs.gen;
+      }
+      sp_qkv = M.x_qkvs.as<__half>();
+    }
     auto gemm = [&](const ConvLayer& L, const __half* in, float* out, int cout, __half* out_split, int act) {
       ConvCall c;
       c.in = in;
@@ -365,8 +396,13 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     for (int l = 0; l < M.n_run; ++l) {
       const BertLayer& B = M.layers[l];
       const float* in = l == 0 ? emb : h;
-      gemm(small ? B.qkv_s : B.qkv, l == 0 ? sp_e : sp_a, qkv, 3 * H, nullptr, ACT_NONE);
-      launch_deberta_attention_f32(ctx, nullptr, sp_b, sc, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+      if (tc_exact) {
+        gemm(small ? B.qkv_s : B.qkv, l == 0 ? sp_e : sp_a, nullptr, 3 * H, sp_qkv, ACT_NONE);
+        launch_deberta_attention_tc_exact(ctx, sp_b, ctx_blk, sp_qkv, qkv_blk, B.pos_k_s, B.pos_q_s, 2 * M.span, M.span, M.heads, sc, ps);
+      } else {
+        gemm(small ? B.qkv_s : B.qkv, l == 0 ? sp_e : sp_a, qkv, 3 * H, nullptr, ACT_NONE);
+        launch_deberta_attention_f32(ctx, nullptr, sp_b, sc, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);
+      }
       gemm(small ? B.o_s : B.o, sp_b, y, H, nullptr, ACT_NONE);
       launch_ln_split(ctx, h, sp_a, sc, in, y, B.ln1_g, B.ln1_b, M.eps, H, ps);
       gemm(small ? B.f1_s : B.f1, sp_a, nullptr, M.inter, sp_c, ACT_GELU);

@@ -217,6 +217,10 @@ void launch_ln_split(const LaunchCtx& ctx, float* out, __half* split, float spli
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len);
 void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
                                  int n_pos, int span, int heads, const PlanarSegs& s);
+// exact numerics (two-term fp16 splits of every operand), <= 128 tokens; see bert_attention_tc.cu
+void launch_deberta_attention_tc_exact(const LaunchCtx& ctx, __half* ctx_s, long long ctx_blk, const __half* qkv_s, long long qkv_blk,
+                                       const __half* pos_k_s, const __half* pos_q_s, int n_pos, int span, int heads, float sc,
+                                       const PlanarSegs& s);
 // 129..512 tokens: 128-query tiles x 128-key tiles with an online softmax; position windows gathered through bucket_idx
 bool deberta_attention_tc_multi_supported(int head_dim, int max_rel, int max_len);
 void launch_deberta_attention_tc_multi(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,
