@@ -90,12 +90,15 @@ int sbv2_model_describe(const sbv2_model* model, const char** json);
  * SBV2_ERR_UNSUPPORTED) — the reference's tokenizer only ever produces all-ones masks (tts_util.rs:120-128).
  * Numerics: SBV2_B200_BERT (read at sbv2_model_create) = "exact" (default: two-term fp16 operand splits, fp32 activations;
  * features reproduce HF fp32 to ~3e-4 and the synthesizer's durations exactly) or "fp16" (single-term operands, ~4x
- * faster, ~1 duration in 2000 differs downstream). */
+ * faster, ~1 duration in 2000 differs downstream).  The disentangled attention runs on the tensor cores in both modes for
+ * every length up to 512 (SBV2_B200_BERT_ATTN=simt: CUDA-core cross-check kernels). */
 int sbv2_bert_predict(sbv2_model* bert, const int64_t* input_ids, const int64_t* attention_mask,
                       int64_t t_tok, float* out);
 /* Extension (the reference is batch 1): ids/mask int64 [batch, s] with right padding expressed by
- * mask zeros; out float32 [batch, s, hidden].  Row b equals sbv2_bert_predict on the unpadded
- * prefix of row b; padded positions are written as zeros. */
+ * mask zeros; out float32 [batch, s, hidden].  Row b is sbv2_bert_predict on the unpadded prefix of row b (bit for bit
+ * while both calls take the same GEMM path; calls with few tokens split K over a thread-block cluster, whose fp32 sums are
+ * formed in a different order — a relative difference of ~5e-5 in exact mode, far inside the mode's accuracy); padded
+ * positions are written as zeros. */
 int sbv2_bert_predict_batch(sbv2_model* bert, const int64_t* input_ids, const int64_t* attention_mask,
                             int batch, int64_t s, float* out);
 int sbv2_bert_hidden_size(const sbv2_model* bert, int* hidden);

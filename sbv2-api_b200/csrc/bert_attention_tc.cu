@@ -829,6 +829,291 @@ __global__ void __launch_bounds__(160, 1) deberta_attention_tc_exact_kernel(__ha
   }
 }
 
+
+// Exact numerics, 129..512 tokens: the tile-pair loop / online softmax / gathered log-bucket windows of
+// deberta_attention_tc_multi_kernel with the split operands, fp32 bias tile and split probabilities of
+// deberta_attention_tc_exact_kernel.  Per key tile the 64 KB window buffer holds the gathered posK terms, then the gathered
+// posQ terms, then the two P terms.
+__global__ void __launch_bounds__(160, 1)
+    deberta_attention_tc_exact_multi_kernel(__half* out_s, long long out_blk, const __half* qkv_s, long long qkv_blk, const __half* pos_k_s,
+                                            const __half* pos_q_s, int n_pos, const int* bucket_idx, int max_rel, int heads, float inv_sc2,
+                                            PlanarSegs s) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y, qt = blockIdx.z;
+  const int len = s.len[b];
+  if (qt * T >= len) return;
+  const int nk = (len + T - 1) / T;
+  const long long pbase = s.pstart[b];
+
+  const uint32_t sQ0 = smem_u32(smem);
+  const uint32_t sQ1 = sQ0 + QKV_BYTES, sK0 = sQ1 + QKV_BYTES, sK1 = sK0 + QKV_BYTES, sV0 = sK1 + QKV_BYTES, sV1 = sV0 + QKV_BYTES;
+  const uint32_t sW0 = sV1 + QKV_BYTES, sW1 = sW0 + POS_BYTES;
+  const uint32_t sBias = sW1 + POS_BYTES, sBar = sBias + BIAS_BYTES;
+  const uint32_t bar_q = sBar, bar_s1 = sBar + 8, bar_g2 = sBar + 16, bar_s2 = sBar + 24, bar_p = sBar + 32, bar_o = sBar + 40,
+                 bar_kv = sBar + 48, bar_g1 = sBar + 56;
+  const uint32_t tmem_slot = sBar + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - sQ0));
+  float* Bs = reinterpret_cast<float*>(smem + (sBias - sQ0));
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_g2, 128);
+    mbar_init(bar_s2, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_g1, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int q_plane0 = h * DPL, k_plane0 = heads * DPL + h * DPL, v_plane0 = 2 * heads * DPL + h * DPL;
+  const size_t pos_term = (size_t)heads * DPL * n_pos * 8;
+
+  if (warp == 4) {
+    // ---------------- control warp ----------------
+    if (lane == 0) mbar_expect_tx(bar_q, 2 * QKV_BYTES);
+    __syncwarp();
+    if (lane < 16) {
+      const int term = lane >> 3, pl = lane & 7;
+      bulk_g2s(sQ0 + term * QKV_BYTES + pl * T * 16,
+               qkv_s + (size_t)term * qkv_blk + (size_t)(q_plane0 + pl) * s.plane_stride + (size_t)(pbase + qt * T) * 8, T * 16, bar_q);
+    }
+    const uint64_t dq0 = make_desc(sQ0, T * 16, 128), dq1 = make_desc(sQ1, T * 16, 128);
+    const uint64_t dk0 = make_desc(sK0, T * 16, 128), dk1 = make_desc(sK1, T * 16, 128);
+    const uint64_t dw0 = make_desc(sW0, W * 16, 128), dw1 = make_desc(sW1, W * 16, 128);
+    const uint64_t dp0 = make_desc(sW0, T * 16, 128), dp1 = make_desc(sW1, T * 16, 128);
+    const uint64_t dv0 = make_desc(sV0, 128, T * 16), dv1 = make_desc(sV1, 128, T * 16);
+    constexpr uint32_t ID_S = idesc_f16(T, 0), ID_B = idesc_f16(W, 0), ID_O = idesc_f16(D, 1);
+    auto cross = [&](uint32_t tm, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1, uint32_t astep, uint32_t bstep, uint32_t id, int nk16) {
+      for (int k = 0; k < nk16; ++k) tc_mma_f16(tm, a0 + (uint64_t)(k * astep), b0 + (uint64_t)(k * bstep), id, k > 0 ? 1u : 0u);
+      for (int k = 0; k < nk16; ++k) tc_mma_f16(tm, a0 + (uint64_t)(k * astep), b1 + (uint64_t)(k * bstep), id, 1u);
+      for (int k = 0; k < nk16; ++k) tc_mma_f16(tm, a1 + (uint64_t)(k * astep), b0 + (uint64_t)(k * bstep), id, 1u);
+    };
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t par = kt & 1;
+      if (lane == 0) mbar_expect_tx(bar_kv, 4 * QKV_BYTES);
+      __syncwarp();
+      {
+        const int which = lane >> 4, term = (lane >> 3) & 1, pl = lane & 7;  // which: 0 k, 1 v
+        const int plane0 = which == 0 ? k_plane0 : v_plane0;
+        bulk_g2s(sK0 + (uint32_t)(which * 2 + term) * QKV_BYTES + pl * T * 16,
+                 qkv_s + (size_t)term * qkv_blk + (size_t)(plane0 + pl) * s.plane_stride + (size_t)(pbase + kt * T) * 8, T * 16, bar_kv);
+      }
+      __syncwarp();
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, par);
+      mbar_wait(bar_g1, par);  // posK terms gathered
+      tc_fence_after();
+      if (elect_one_sync()) {
+        cross(tmem + TM_S, dq0, dq1, dk0, dk1, 2 * T, 2 * T, ID_S, D / 16);
+        cross(tmem + TM_B, dq0, dq1, dw0, dw1, 2 * T, 2 * W, ID_B, D / 16);
+        tc_commit(bar_s1);
+      }
+      __syncwarp();
+      mbar_wait(bar_g2, par);  // C2P copied out of TMEM, posQ terms gathered
+      tc_fence_after();
+      if (elect_one_sync()) {
+        cross(tmem + TM_B, dk0, dk1, dw0, dw1, 2 * T, 2 * W, ID_B, D / 16);
+        tc_commit(bar_s2);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, par);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp0 + (uint64_t)(k * 2 * T), dv0 + (uint64_t)(k * 16), ID_O, k > 0 ? 1u : 0u);
+        for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp0 + (uint64_t)(k * 2 * T), dv1 + (uint64_t)(k * 16), ID_O, 1u);
+        for (int k = 0; k < T / 16; ++k) tc_mma_f16(tmem + TM_O, dp1 + (uint64_t)(k * 2 * T), dv0 + (uint64_t)(k * 16), ID_O, 1u);
+        tc_commit(bar_o);
+      }
+      __syncwarp();
+      mbar_wait(bar_o, par);
+    }
+  } else {
+    // ---------------- softmax threads ----------------
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c_scale = 1.4426950408889634f / sqrtf(3.0f * (float)D) * inv_sc2;
+    float m = -CUDART_INF_F, l = 0.f;
+    float o[D];
+#pragma unroll
+    for (int e = 0; e < D; ++e) o[e] = 0.f;
+    const float* brow = Bs + row * BCS;
+    uint8_t* prow0 = smem + (sW0 - sQ0) + row * 16;
+    uint8_t* prow1 = smem + (sW1 - sQ0) + row * 16;
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t par = kt & 1;
+      const int klen = len - kt * T;
+      auto gather = [&](const __half* tab) {
+#pragma unroll 1
+        for (int w = row; w < W; w += T) {
+          int rel = (qt - kt) * T + w - (T - 1);
+          rel = rel < -max_rel ? -max_rel : (rel > max_rel ? max_rel : rel);
+          const int pr = bucket_idx[rel + max_rel];
+#pragma unroll
+          for (int i = 0; i < 2 * DPL; ++i) {
+            const int term = i >> 3, pl = i & 7;
+            *reinterpret_cast<uint4*>(smem + (sW0 - sQ0) + (size_t)term * POS_BYTES + (size_t)(pl * W + w) * 16) =
+                *reinterpret_cast<const uint4*>(tab + term * pos_term + ((size_t)(h * DPL + pl) * n_pos + pr) * 8);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      };
+      gather(pos_k_s);  // the previous tile pair's MMAs have completed (bar_o below): the window buffer is free
+      mbar_arrive(bar_g1);
+      mbar_wait(bar_kv, par);
+      if (row >= klen) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int pl = 0; pl < DPL; ++pl) {
+          *reinterpret_cast<uint4*>(smem + (sV0 - sQ0) + (size_t)(pl * T + row) * 16) = z;
+          *reinterpret_cast<uint4*>(smem + (sV1 - sQ0) + (size_t)(pl * T + row) * 16) = z;
+        }
+      }
+      mbar_wait(bar_s1, par);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < W / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_B + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = row + (T - 1) - (q * 32 + e);
+          if (j >= 0 && j < T) Bs[row * BCS + j] = __uint_as_float(v[e]);
+        }
+      }
+      tc_fence_before();
+      gather(pos_q_s);  // the posK terms have been consumed (bar_s1)
+      mbar_arrive(bar_g2);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every c2p entry is written before any p2c entry is added
+      mbar_wait(bar_s2, par);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < W / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_B + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int ii = q * 32 + e + row - (T - 1);
+          if (ii >= 0 && ii < T) Bs[ii * BCS + row] += __uint_as_float(v[e]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float mt = -CUDART_INF_F;
+#pragma unroll 1
+      for (int q = 0; q < T / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_S + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 bb = *reinterpret_cast<const float4*>(brow + q * 32 + 4 * e4);
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = q * 32 + 4 * e4 + u;
+            const float sc = __uint_as_float(v[4 * e4 + u]) + bv[u];
+            mt = fmaxf(mt, j < klen ? sc : -CUDART_INF_F);
+          }
+        }
+      }
+      const float m_new = fmaxf(m, mt);
+      const float mc = m_new * c_scale;
+      const float alpha = ex2_approx(fmaf(m, c_scale, -mc));  // 0 on the first tile (m = -inf)
+      m = m_new;
+      float lt = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < T / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_S + q * 32, v);
+        tc_wait_ld();
+        float pv[32];
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 bb = *reinterpret_cast<const float4*>(brow + q * 32 + 4 * e4);
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = q * 32 + 4 * e4 + u;
+            const float sc = __uint_as_float(v[4 * e4 + u]) + bv[u];
+            const float p = j < klen ? ex2_approx(fmaf(sc, c_scale, -mc)) : 0.f;
+            pv[4 * e4 + u] = p;
+            lt += p;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u0, u1;
+          __half2* h0 = reinterpret_cast<__half2*>(&u0);
+          __half2* h1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = pv[g * 8 + 2 * e], x1 = pv[g * 8 + 2 * e + 1];
+            const __half2 a = __floats2half2_rn(x0, x1);
+            const float2 af = __half22float2(a);
+            h0[e] = a;
+            h1[e] = __floats2half2_rn(x0 - af.x, x1 - af.y);
+          }
+          *reinterpret_cast<uint4*>(prow0 + (size_t)(q * 4 + g) * T * 16) = u0;
+          *reinterpret_cast<uint4*>(prow1 + (size_t)(q * 4 + g) * T * 16) = u1;
+        }
+      }
+      l = fmaf(l, alpha, lt);
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_p);
+      mbar_wait(bar_o, par);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < D / 32; ++q) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + TM_O + q * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[q * 32 + e] = fmaf(o[q * 32 + e], alpha, __uint_as_float(v[e]));
+      }
+      tc_fence_before();
+    }
+    const float inv_l = 1.0f / l;
+    const int grow = qt * T + row;
+    if (grow < len) {
+#pragma unroll
+      for (int g = 0; g < DPL; ++g) {
+        uint4 u0, u1;
+        __half2* h0 = reinterpret_cast<__half2*>(&u0);
+        __half2* h1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = o[g * 8 + 2 * e] * inv_l, x1 = o[g * 8 + 2 * e + 1] * inv_l;
+          const __half2 a = __floats2half2_rn(x0, x1);
+          const float2 af = __half22float2(a);
+          h0[e] = a;
+          h1[e] = __floats2half2_rn(x0 - af.x, x1 - af.y);
+        }
+        __half* dst = out_s + (size_t)(h * DPL + g) * s.plane_stride + (pbase + grow) * 8;
+        *reinterpret_cast<uint4*>(dst) = u0;
+        *reinterpret_cast<uint4*>(dst + out_blk) = u1;
+        *reinterpret_cast<uint4*>(dst + 2 * out_blk) = u0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 bool deberta_attention_tc_supported(int head_dim, int span, int max_len) { return head_dim == D && span >= 254 && max_len <= T; }
@@ -879,6 +1164,23 @@ void launch_deberta_attention_tc_exact(const LaunchCtx& ctx, __half* ctx_s, long
   dim3 grid(heads, s.n);
   deberta_attention_tc_exact_kernel<<<grid, 160, EX_SMEM, ctx.stream>>>(ctx_s, ctx_blk, qkv_s, qkv_blk, pos_k_s, pos_q_s, n_pos, win0, heads,
                                                                          1.0f / (sc * sc), s);
+  CUDA_CHECK(cudaGetLastError());
+  ctx.count();
+}
+
+void launch_deberta_attention_tc_exact_multi(const LaunchCtx& ctx, __half* ctx_s, long long ctx_blk, const __half* qkv_s, long long qkv_blk,
+                                             const __half* pos_k_s, const __half* pos_q_s, int n_pos, const int* bucket_idx, int max_rel,
+                                             int heads, float sc, const PlanarSegs& s) {
+  if (s.n <= 0 || s.max_len <= 0) return;
+  if (!deberta_attention_tc_multi_supported(D, max_rel, s.max_len))
+    fail(SBV2_ERR_INTERNAL, "tensor-core DeBERTa attention (exact, multi-tile): unsupported shape");
+  static PerDeviceOnce attr_once;
+  attr_once.run([&] {
+    CUDA_CHECK(cudaFuncSetAttribute(deberta_attention_tc_exact_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EX_SMEM));
+  });
+  dim3 grid(heads, s.n, (s.max_len + T - 1) / T);
+  deberta_attention_tc_exact_multi_kernel<<<grid, 160, EX_SMEM, ctx.stream>>>(ctx_s, ctx_blk, qkv_s, qkv_blk, pos_k_s, pos_q_s, n_pos, bucket_idx,
+                                                                               max_rel, heads, 1.0f / (sc * sc), s);
   CUDA_CHECK(cudaGetLastError());
   ctx.count();
 }

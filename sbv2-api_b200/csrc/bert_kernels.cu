@@ -108,13 +108,13 @@ __global__ void ln_planar_wide_kernel(float* h, __half* hp, __half* hp2, const f
 
 // Exact mode: h = LN(a + addin) (fp32 row-major, one warp per row, 8 channels per lane and iteration) and, in the same pass,
 // the split-planar operand [h0 | h1 | h0] of the GEMM that consumes h.  NV8 = C / 256.
+constexpr int LN_ROWS = 8;  // rows (= warps) per block
+
 template <int NV8>
-__global__ void ln_split_kernel(float* out, __half* split, float split_scale, const float* a, const float* addin, const float* gamma,
-                                const float* beta, float eps, int C, PlanarSegs s) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__device__ __forceinline__ void ln_split_row(float* out, __half* split, float split_scale, const float* a, const float* addin,
+                                             const float* gamma, const float* beta, float eps, int C, const PlanarSegs& s, int b, int t,
+                                             uint8_t* stage_raw) {
   const int lane = threadIdx.x & 31;
-  if (t >= s.len[b]) return;
   const size_t base = ((size_t)s.start[b] + t) * C;
   float v[NV8][8];
 #pragma unroll
@@ -166,8 +166,12 @@ __global__ void ln_split_kernel(float* out, __half* split, float split_scale, co
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
-  const size_t prow = (size_t)(s.pstart[b] + t) * 8;
-  const long long blk = (long long)(C / 8) * s.plane_stride;
+  // The split planes are staged in shared memory, [row of this block][term][plane][16 B] (+ one 16-byte pad per row: the
+  // transposed read below is then conflict-free), and written out by the whole
+  // block afterwards: a plane then receives the block's 8 consecutive rows as one 128-byte run instead of eight 16-byte
+  // stores from eight warps (384 half-filled sectors per row were what the kernel spent its time on).
+  uint4* stage = reinterpret_cast<uint4*>(stage_raw);
+  const int w = threadIdx.x >> 5, planes = C / 8;
 #pragma unroll
   for (int i = 0; i < NV8; ++i) {
     const int c = (i * 32 + lane) * 8;
@@ -179,8 +183,57 @@ __global__ void ln_split_kernel(float* out, __half* split, float split_scale, co
       *reinterpret_cast<float4*>(out + base + c) = make_float4(r[0], r[1], r[2], r[3]);
       *reinterpret_cast<float4*>(out + base + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
     }
-    if (split) store_split8_attn(split + (size_t)(c >> 3) * s.plane_stride + prow, blk, r, split_scale);
+    if (split) {
+      uint4 o0, o1;
+      __half2* q0 = reinterpret_cast<__half2*>(&o0);
+      __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = r[2 * e] * split_scale, x1 = r[2 * e + 1] * split_scale;
+        const __half2 h0 = __floats2half2_rn(x0, x1);
+        const float2 g0 = __half22float2(h0);
+        q0[e] = h0;
+        q1[e] = __floats2half2_rn(x0 - g0.x, x1 - g0.y);
+      }
+      stage[(size_t)w * (2 * planes + 1) + (c >> 3)] = o0;
+      stage[(size_t)w * (2 * planes + 1) + planes + (c >> 3)] = o1;
+    }
   }
+}
+
+// second half of ln_split: the block's staged split planes -> [h0 | h1 | h0] plane blocks, 128-byte runs
+__device__ __forceinline__ void ln_split_flush(__half* split, const uint4* stage, int C, int t0, int nrows, const PlanarSegs& s, int b) {
+  const int planes = C / 8;
+  const long long blk = (long long)planes * s.plane_stride;
+  const size_t prow0 = (size_t)(s.pstart[b] + t0) * 8;
+  const int r = threadIdx.x & (LN_ROWS - 1);
+  if (r >= nrows) return;
+  for (int seg = threadIdx.x / LN_ROWS; seg < 2 * planes; seg += blockDim.x / LN_ROWS) {
+    const int term = seg >= planes ? 1 : 0, pl = seg - term * planes;
+    const uint4 val = stage[(size_t)r * (2 * planes + 1) + seg];
+    __half* dst = split + (size_t)pl * s.plane_stride + prow0 + (size_t)r * 8;
+    if (term == 0) {
+      *reinterpret_cast<uint4*>(dst) = val;
+      *reinterpret_cast<uint4*>(dst + 2 * blk) = val;
+    } else {
+      *reinterpret_cast<uint4*>(dst + blk) = val;
+    }
+  }
+}
+
+template <int NV8>
+__global__ void __launch_bounds__(32 * LN_ROWS) ln_split_kernel(float* out, __half* split, float split_scale, const float* a,
+                                                                const float* addin, const float* gamma, const float* beta, float eps, int C,
+                                                                PlanarSegs s) {
+  extern __shared__ __align__(16) uint8_t ln_stage[];  // [LN_ROWS][2 terms x C / 8 planes + 1][16 B]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * LN_ROWS, t = t0 + (threadIdx.x >> 5);
+  const int len = s.len[b];
+  if (t0 >= len) return;  // block-uniform
+  if (t < len) ln_split_row<NV8>(out, split, split_scale, a, addin, gamma, beta, eps, C, s, b, t, ln_stage);
+  if (split == nullptr) return;
+  __syncthreads();
+  ln_split_flush(split, reinterpret_cast<const uint4*>(ln_stage), C, t0, min(LN_ROWS, len - t0), s, b);
 }
 
 __global__ void scatter_rows_kernel(float* out, const float* h, int C, int S, PlanarSegs s) {
@@ -491,11 +544,12 @@ void launch_ln_split(const LaunchCtx& ctx, float* out, __half* split, float spli
                      const float* gamma, const float* beta, float eps, int C, const PlanarSegs& s) {
   if (s.n <= 0 || s.max_len <= 0) return;
   if (!ln_split_supported(C)) fail(SBV2_ERR_UNSUPPORTED, "ln_split: hidden size must be a multiple of 8 and <= 1024");
-  dim3 grid((s.max_len + 7) / 8, s.n);
-  if (C <= 256) ln_split_kernel<1><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
-  else if (C <= 512) ln_split_kernel<2><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
-  else if (C <= 768) ln_split_kernel<3><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
-  else ln_split_kernel<4><<<grid, 256, 0, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  dim3 grid((s.max_len + LN_ROWS - 1) / LN_ROWS, s.n);
+  const size_t smem = size_t(2 * (C / 8) + 1) * LN_ROWS * 16;  // <= 33 KB
+  if (C <= 256) ln_split_kernel<1><<<grid, 32 * LN_ROWS, smem, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  else if (C <= 512) ln_split_kernel<2><<<grid, 32 * LN_ROWS, smem, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  else if (C <= 768) ln_split_kernel<3><<<grid, 32 * LN_ROWS, smem, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
+  else ln_split_kernel<4><<<grid, 32 * LN_ROWS, smem, ctx.stream>>>(out, split, split_scale, a, addin, gamma, beta, eps, C, s);
   POST_LAUNCH(ctx);
 }
 

@@ -363,9 +363,11 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     __half* sp_c = sp_b + R * 3 * size_t(H);
     const float sc = M.layers[0].qkv.in_scale;  // the same for every split layer
     if (M.has_conv) launch_zero_gaps(ctx, sp_e, 3 * H, G, batch);  // k = 3 ConvLayer halo; the GEMMs have none
-    // sequences of at most 128 tokens: attention on the tensor cores with split operands (SBV2_B200_BERT_ATTN=simt: fp32
-    // CUDA-core kernel); q|k|v then leave their GEMM as split planes instead of fp32 rows
-    const bool tc_exact = M.use_tc_attn && M.hidden / M.heads == 64 && sc == kSplitScale && deberta_attention_tc_supported(64, M.span, max_len);
+    // attention on the tensor cores with split operands (one tile up to 128 tokens, tile pairs beyond;
+    // SBV2_B200_BERT_ATTN=simt: fp32 CUDA-core kernel); q|k|v then leave their GEMM as split planes instead of fp32 rows
+    const bool tc_single = deberta_attention_tc_supported(64, M.span, max_len);
+    const bool tc_exact = M.use_tc_attn && M.hidden / M.heads == 64 && sc == kSplitScale &&
+                          (tc_single || deberta_attention_tc_multi_supported(64, M.max_rel, max_len));
     __half* sp_qkv = nullptr;
     const long long qkv_blk = (long long)(3 * H / 8) * ps.plane_stride, ctx_blk = (long long)(H / 8) * ps.plane_stride;
     if (tc_exact) {
@@ -398,7 +400,11 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
       const float* in = l == 0 ? emb : h;
       if (tc_exact) {
         gemm(small ? B.qkv_s : B.qkv, l == 0 ? sp_e : sp_a, nullptr, 3 * H, sp_qkv, ACT_NONE);
-        launch_deberta_attention_tc_exact(ctx, sp_b, ctx_blk, sp_qkv, qkv_blk, B.pos_k_s, B.pos_q_s, 2 * M.span, M.span, M.heads, sc, ps);
+        if (tc_single)
+          launch_deberta_attention_tc_exact(ctx, sp_b, ctx_blk, sp_qkv, qkv_blk, B.pos_k_s, B.pos_q_s, 2 * M.span, M.span, M.heads, sc, ps);
+        else
+          launch_deberta_attention_tc_exact_multi(ctx, sp_b, ctx_blk, sp_qkv, qkv_blk, B.pos_k_s, B.pos_q_s, 2 * M.span, M.bucket_idx, M.max_rel,
+                                                  M.heads, sc, ps);
       } else {
         gemm(small ? B.qkv_s : B.qkv, l == 0 ? sp_e : sp_a, qkv, 3 * H, nullptr, ACT_NONE);
         launch_deberta_attention_f32(ctx, nullptr, sp_b, sc, qkv, B.pos_k, B.pos_q, 2 * M.span, M.bucket_idx, M.max_rel, M.heads, 64, ps);

@@ -221,6 +221,9 @@ void launch_deberta_attention_tc(const LaunchCtx& ctx, __half* ctx_out, const __
 void launch_deberta_attention_tc_exact(const LaunchCtx& ctx, __half* ctx_s, long long ctx_blk, const __half* qkv_s, long long qkv_blk,
                                        const __half* pos_k_s, const __half* pos_q_s, int n_pos, int span, int heads, float sc,
                                        const PlanarSegs& s);
+void launch_deberta_attention_tc_exact_multi(const LaunchCtx& ctx, __half* ctx_s, long long ctx_blk, const __half* qkv_s, long long qkv_blk,
+                                             const __half* pos_k_s, const __half* pos_q_s, int n_pos, const int* bucket_idx, int max_rel,
+                                             int heads, float sc, const PlanarSegs& s);
 // 129..512 tokens: 128-query tiles x 128-key tiles with an online softmax; position windows gathered through bucket_idx
 bool deberta_attention_tc_multi_supported(int head_dim, int max_rel, int max_len);
 void launch_deberta_attention_tc_multi(const LaunchCtx& ctx, __half* ctx_out, const __half* qkv, const __half* pos_k_p, const __half* pos_q_p,

@@ -463,8 +463,12 @@ __global__ void __launch_bounds__(256) utt_linear_kernel(ConvArgs a) {
   const float* __restrict__ w = a.w;
   float acc = 0.f;
   if (co < a.cout) {
+    if (a.act_in == ACT_NONE) {  // the branchy activation switch inside the loop keeps the loads from being batched
 #pragma unroll 16
-    for (int ci = c_lo; ci < c_hi; ++ci) acc = fmaf(apply_act(__ldg(in + ci), a.act_in), __ldg(w + (size_t)ci * a.cout + co), acc);
+      for (int ci = c_lo; ci < c_hi; ++ci) acc = fmaf(__ldg(in + ci), __ldg(w + (size_t)ci * a.cout + co), acc);
+    } else {
+      for (int ci = c_lo; ci < c_hi; ++ci) acc = fmaf(apply_act(__ldg(in + ci), a.act_in), __ldg(w + (size_t)ci * a.cout + co), acc);
+    }
   }
   red[ks][col] = acc;
   __syncthreads();

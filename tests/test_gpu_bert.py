@@ -134,12 +134,13 @@ def test_error_paths(tiny, S):
 
 
 @pytest.mark.parametrize("mode,smax,lens", [("fp16", 128, [128, 1, 77, 128, 5, 100]), ("exact", 128, [128, 1, 77, 128, 5, 100]),
-                                            ("fp16", 512, [512, 129, 300, 1, 128, 257, 400, 385, 256, 511])])
+                                            ("fp16", 512, [512, 129, 300, 1, 128, 257, 400, 385, 256, 511]),
+                                            ("exact", 512, [512, 129, 300, 1, 128, 257, 400, 385, 256, 511])])
 def test_tensor_core_attention_matches_cuda_core_attention(S, mode, smax, lens):
     """The disentangled attention runs on tcgen05 (bert_attention_tc.cu: one tile up to 128 tokens, 128 x 128 tile pairs
     with gathered log-bucket position windows up to 512); the CUDA-core kernel (SBV2_B200_BERT_ATTN=simt) is the
-    cross-check, on a ragged right-padded batch.  Exact mode (the default) has its own tensor-core kernel up to 128 tokens
-    (two-term fp16 splits of every operand) and keeps the fp32 CUDA-core kernel beyond."""
+    cross-check, on a ragged right-padded batch.  Exact mode (the default) has its own tensor-core kernels (two-term fp16
+    splits of every operand, fp32 bias tile), again one tile up to 128 tokens and tile pairs beyond."""
     from sbv2_b200 import assets
     cfg = od.tiny_config()
     onnx = assets.deberta_onnx(od.state_dict_numpy(od.build_model(cfg, seed=1)))

@@ -115,7 +115,7 @@ def test_text_split_convs_match_fp32_path(S):
 
 
 @pytest.mark.parametrize("env", [{"SBV2_B200_CLUSTER": "2"}, {"SBV2_B200_CLUSTER": "4"},
-                                 {"SBV2_B200_PAIR2": "1", "SBV2_B200_TEST_NBMAX": "128"}])
+                                 {"SBV2_B200_PAIR2": "1", "SBV2_B200_TEST_NBMAX": "128"}], ids=["cluster2", "cluster4", "pair2"])
 def test_conv_kernel_cluster_and_pair_variants(S, env):
     """The optional launch modes of umma_conv_kernel — thread-block clusters with multicast weight stages and CTA pairs
     (tcgen05 cta_group::2, M = 256) — against the fp32 CUDA-core conv on 20 shapes (tools/umma_conv_check.py).  The
