@@ -96,6 +96,33 @@ def test_cfg2_deberta_large_32x128(deberta_large):
         assert worst[k][0] <= FEAT_TOL[k][0] and worst[k][1] <= FEAT_TOL[k][1], (k, worst[k])
 
 
+def test_cfg2_one_sentence_split_k(deberta_large):
+    """One sentence (bert.rs:6-24 as the reference calls it): every GEMM runs split-K over a thread-block cluster, the
+    partial accumulators meet through distributed shared memory in rank order.  Deterministic (two calls bit-identical),
+    within the mode's tolerance of HF fp32, and equal to the same sentence inside a 32-sentence batch (which does not
+    split) up to the different fp32 summation order."""
+    cfg, hf, models = deberta_large
+    g = torch.Generator().manual_seed(23)
+    for t in (7, 31):
+        ids = torch.randint(3, cfg.vocab_size, (1, t), generator=g)
+        ref = od.predict(hf, ids, torch.ones_like(ids))[0].numpy()
+        batch_ids = torch.randint(3, cfg.vocab_size, (32, 128), generator=g).numpy()
+        batch_ids[5, :t] = ids[0].numpy()
+        mask = np.ones((32, 128), np.int64)
+        mask[5, t:] = 0
+        for k, model in models.items():
+            a = model.predict(ids[0].numpy(), np.ones(t, np.int64))
+            b = model.predict(ids[0].numpy(), np.ones(t, np.int64))
+            assert np.array_equal(a, b), "split-K must be deterministic"
+            e = feat_err(a, ref)
+            in_batch = model.predict_batch(batch_ids, mask)[5, :t]
+            d = feat_err(a, in_batch)
+            print(f"cfg2 one sentence T={t} [{k}] vs HF fp32: max-abs {e[0]:.3e}, rel-Frobenius {e[1]:.3e}; vs the same sentence in a "
+                  f"32 x 128 batch: rel-Frobenius {d[1]:.3e}")
+            assert e[0] <= FEAT_TOL[k][0] and e[1] <= FEAT_TOL[k][1], (k, t, e)
+            assert d[1] <= 2 * FEAT_TOL[k][1], (k, t, d)
+
+
 def test_cfg2_deberta_large_ragged_and_long(deberta_large):
     """Right-padded ragged batch (variant of cfg2: lengths U[64,128]) and one 300-token sequence (relative positions
     beyond +-128 fall into the log buckets; the graph's sequence axis is dynamic, convert_deberta.py:50)."""
