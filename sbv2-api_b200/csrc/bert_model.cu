@@ -390,6 +390,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
       c.act_out = act;
       c.tmap = true;
       c.splitk = true;
+      c.cluster = 2;  // multicast weight stages in batches (launch_umma); split-K takes over for few tokens
       launch_umma(ctx, L, G, G, c, batch);
     };
     launch_embed_rows(ctx, h, M.word_emb, M.ids.as<int>(), H, M.vocab, n);
@@ -452,6 +453,7 @@ const float* bert_forward_device(sbv2_model* mm, const int64_t* ids, const int64
     c.act_on_accum = acc32 != nullptr && act != ACT_NONE;
     c.tmap = true;
     c.splitk = true;
+    c.cluster = 2;  // multicast weight stages in batches (launch_umma); split-K takes over for few tokens
     launch_umma(ctx, L, G, G, c, batch);
   };
   // sequences of at most 128 tokens: disentangled attention on the tensor cores (SBV2_B200_BERT_ATTN=simt: CUDA cores)

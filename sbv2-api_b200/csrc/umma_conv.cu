@@ -1133,14 +1133,23 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
   // more than the divided L2 -> SM weight traffic saves — decoder 20.05 / 20.73 / 27.94 ms, flow 7.44 / 7.84 / 8.84 ms
   // for 1 / 2 / 4 CTAs per cluster (profiles/r2_cluster_multicast.log); results are identical in all three modes
   // (tools/umma_conv_check.py).  Streaming layers only: resident weights are fetched once per CTA anyway.
-  static int cluster_pref = -1;
+  // ON (2 CTAs) where it was measured to pay — the DeBERTa GEMMs ask for it through ConvCall::cluster: 32 x 128 tokens
+  // 12.9 -> 12.0 ms exact, 6.2 -> 6.0 ms fp16 (4 CTAs: 14.0 / 7.0 ms); the environment variable overrides either way.
+  static int cluster_pref = -1;  // 0: SBV2_B200_CLUSTER not set
   if (cluster_pref < 0) {
     const char* e = getenv("SBV2_B200_CLUSTER");
-    cluster_pref = e ? atoi(e) : 1;
-    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 1;
+    cluster_pref = e ? atoi(e) : 0;
+    if (cluster_pref != 0 && cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 1;
   }
-  int nc = L.b_resident ? 1 : cluster_pref;
+  int nc = L.b_resident ? 1 : (cluster_pref > 0 ? cluster_pref : (c.cluster == 2 || c.cluster == 4 ? c.cluster : 1));
   while (nc > 1 && (gi.n_tiles[slot] < nc || (size_t(L.nb) * L.kc * 2) % (size_t(16) * nc) != 0)) nc >>= 1;
+  if (cluster_pref == 0 && nc > 1) {
+    // a caller's preference must not turn one wave into two (dummy tiles of a ragged last cluster count as CTAs):
+    // three short sentences, 144 items -> 192 clustered CTAs, measured 5.5 -> 6.1 ms
+    const long long plain = (long long)gi.n_tiles[slot] * L.n_nblk * L.n_groups;
+    const long long clustered = (long long)((gi.n_tiles[slot] + nc - 1) / nc) * nc * L.n_nblk * L.n_groups;
+    if (clustered > num_sms && plain < 2LL * num_sms) nc = 1;
+  }
   // CTA pairs (cta_group::2, SBV2_B200_PAIR2=1 or ConvCall::pair): two adjacent N blocks of the layer's packing form the N
   // of one M = 256 MMA, each CTA of the pair streams one of them.  Needs an even number of N blocks, N = 2 * nb <= 256 and
   // both accumulator sets (2 * mt * N columns) in TMEM.
@@ -1158,23 +1167,28 @@ void launch_umma(const LaunchCtx& ctx, const ConvLayer& L, const Geom& gi, const
     a.tmem_cols = pow2_at_least(4 * L.mt * L.nb);
     a.idesc = (1u << 4) | ((unsigned)(a.nb >> 3) << 17) | ((unsigned)(256 >> 4) << 24);  // M = 256 across the pair
   }
+  // split-K (below) takes precedence over multicast clusters: it is decided on the single-CTA item count
+  int splitk = 1;
+  {
+    static int splitk_env = -1;
+    if (splitk_env < 0) {
+      const char* e = getenv("SBV2_B200_SPLITK");
+      splitk_env = e ? atoi(e) : 1;
+    }
+    const int n_items1 = gi.n_tiles[slot] * L.n_nblk * L.n_groups;
+    if (c.splitk && splitk_env != 0 && !pair && L.mt == 1 && !L.b_resident && L.n_groups == 1 && c.gate_half == 0 && L.nkc >= 8 &&
+        size_t(128) * (L.nb + 4) * 4 <= size_t(L.a_slots) * (L.kc / 8) * (128 + L.halo_lo + L.halo_hi) * 16) {
+      for (int sk = 8; sk >= 2 && splitk == 1; sk >>= 1)
+        if (n_items1 * sk <= num_sms && L.nkc % sk == 0 && L.nkc / sk >= 2) splitk = sk;
+    }
+    if (splitk > 1) nc = 1;
+  }
   a.cluster = nc;
   a.n_tiles = gi.n_tiles[slot];
   a.n_items = ((gi.n_tiles[slot] + nc - 1) / nc) * a.n_nblk * L.n_groups;  // cluster items
   // Split-K over a cluster (ConvCall::splitk: DeBERTa's GEMMs when a call has few tokens).  With 16-64 items each CTA
   // walks the whole K alone: K / 16 MMAs in a row and K * nb * 2 bytes of weights through one SM's few stages in flight
   // (one 7-token sentence: 40 us per GEMM for 1-2 us of work).  S CTAs per item divide both.  SBV2_B200_SPLITK=0: off.
-  static int splitk_env = -1;
-  if (splitk_env < 0) {
-    const char* e = getenv("SBV2_B200_SPLITK");
-    splitk_env = e ? atoi(e) : 1;
-  }
-  int splitk = 1;
-  if (c.splitk && splitk_env != 0 && nc == 1 && !pair && L.mt == 1 && !L.b_resident && L.n_groups == 1 && c.gate_half == 0 && L.nkc >= 8 &&
-      size_t(128) * (L.nb + 4) * 4 <= size_t(L.a_slots) * (L.kc / 8) * (128 + L.halo_lo + L.halo_hi) * 16) {
-    for (int sk = 8; sk >= 2 && splitk == 1; sk >>= 1)
-      if (a.n_items * sk <= num_sms && L.nkc % sk == 0 && L.nkc / sk >= 2) splitk = sk;
-  }
   dim3 grid(std::min(a.n_items, num_sms / nc) * nc);
   if (splitk > 1) {
     nc = splitk;

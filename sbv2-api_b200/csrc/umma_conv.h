@@ -138,6 +138,8 @@ struct ConvCall {
   // synthesizer's few-rows layers lose 4 % (the box always carries all rows of the tile, the bulk copies only the valid
   // ones), batches are unchanged — so DeBERTa asks for it and the synthesizer does not.
   bool tmap = false;
+  // thread-block clusters of 2 / 4 CTAs with multicast weight stages (0: none unless SBV2_B200_CLUSTER says otherwise)
+  int cluster = 0;
   // run as CTA pairs (tcgen05 cta_group::2, M = 256) when the layer's packing allows it (see launch_umma)
   bool pair = false;
   // split K over a thread-block cluster when the launch has few items (see launch_umma): the fp32 sums are formed in a
