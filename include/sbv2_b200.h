@@ -89,7 +89,7 @@ int sbv2_model_describe(const sbv2_model* model, const char** json);
  * return SBV2_ERR_INVALID_ARGUMENT), and attention_mask must be a prefix of ones (right padding; a mask with holes returns
  * SBV2_ERR_UNSUPPORTED) — the reference's tokenizer only ever produces all-ones masks (tts_util.rs:120-128).
  * Numerics: SBV2_B200_BERT (read at sbv2_model_create) = "exact" (default: two-term fp16 operand splits, fp32 activations;
- * features reproduce HF fp32 to ~3e-4 and the synthesizer's durations exactly) or "fp16" (single-term operands, ~4x
+ * features reproduce HF fp32 to ~3e-4 and the synthesizer's durations exactly) or "fp16" (single-term operands, ~2x
  * faster, ~1 duration in 2000 differs downstream).  The disentangled attention runs on the tensor cores in both modes for
  * every length up to 512 (SBV2_B200_BERT_ATTN=simt: CUDA-core cross-check kernels). */
 int sbv2_bert_predict(sbv2_model* bert, const int64_t* input_ids, const int64_t* attention_mask,
