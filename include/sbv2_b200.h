@@ -233,6 +233,9 @@ int sbv2_get_style_vector(const float* style_vectors, int64_t rows, int64_t cols
 
 /* float32 mono 44.1 kHz WAV (WAVE_FORMAT_EXTENSIBLE/IEEE float, as hound writes it). */
 int sbv2_wav_from_f32(const float* samples, int64_t n, void** wav_bytes, size_t* wav_n);
+/* Optional (the reference only writes float): 16-bit PCM mono 44.1 kHz WAV, 44-byte header; samples
+ * clamped to [-1, 1], scaled by 32767, rounded to nearest; NaN -> 0. */
+int sbv2_wav_pcm16_from_f32(const float* samples, int64_t n, void** wav_bytes, size_t* wav_n);
 
 /* ---- TTSModelHolder  (crates/sbv2_core/src/tts.rs:40-349) ------------------------------------ */
 

@@ -466,4 +466,15 @@ int sbv2_wav_from_f32(const float* samples, int64_t n, void** wav_bytes, size_t*
   });
 }
 
+int sbv2_wav_pcm16_from_f32(const float* samples, int64_t n, void** wav_bytes, size_t* wav_n) {
+  return guarded([&] {
+    SBV2_REQUIRE((samples || n == 0) && wav_bytes && wav_n, "null argument");
+    auto w = wav_pcm16_from_f32(samples, n);
+    void* p = alloc_out(w.size(), false);
+    memcpy(p, w.data(), w.size());
+    *wav_bytes = p;
+    *wav_n = w.size();
+  });
+}
+
 }  // extern "C"

@@ -425,6 +425,7 @@ std::vector<uint8_t> wav_from_f32(const float* samples, int64_t n) {
   // Layout hound 3.5 produces for WavSpec{channels:1, sample_rate:44100, bits_per_sample:32,
   // sample_format:Float}: RIFF / fmt (WAVE_FORMAT_EXTENSIBLE, 40 bytes) / data.
   if (n < 0) fail(SBV2_ERR_INVALID_ARGUMENT, "negative sample count");
+  if (n > (int64_t(0xFFFFFFFF) - 60) / 4) fail(SBV2_ERR_INVALID_ARGUMENT, "too many samples for a RIFF container (4 GiB)");
   const uint32_t data_bytes = uint32_t(n * 4);
   std::vector<uint8_t> w(68 + size_t(data_bytes));
   uint8_t* p = w.data();
@@ -439,6 +440,30 @@ std::vector<uint8_t> wav_from_f32(const float* samples, int64_t n) {
   memcpy(p, guid_float, 16); p += 16;
   tag("data"); u32(data_bytes);
   if (n) memcpy(p, samples, size_t(data_bytes));
+  return w;
+}
+
+// SURVEY.md 8f row 3, optional: 16-bit PCM (plain 44-byte WAVE_FORMAT_PCM header), half the bytes of the
+// float container.  Samples are clamped to [-1, 1] and scaled by 32767 with round-to-nearest-even.
+std::vector<uint8_t> wav_pcm16_from_f32(const float* samples, int64_t n) {
+  if (n < 0) fail(SBV2_ERR_INVALID_ARGUMENT, "negative sample count");
+  if (n > (int64_t(0xFFFFFFFF) - 36) / 2) fail(SBV2_ERR_INVALID_ARGUMENT, "too many samples for a RIFF container (4 GiB)");
+  const uint32_t data_bytes = uint32_t(n * 2);
+  std::vector<uint8_t> w(44 + size_t(data_bytes));
+  uint8_t* p = w.data();
+  auto u16 = [&](uint16_t v) { memcpy(p, &v, 2); p += 2; };
+  auto u32 = [&](uint32_t v) { memcpy(p, &v, 4); p += 4; };
+  auto tag = [&](const char* t) { memcpy(p, t, 4); p += 4; };
+  tag("RIFF"); u32(36 + data_bytes); tag("WAVE");
+  tag("fmt "); u32(16);
+  u16(1); u16(1); u32(44100); u32(44100 * 2); u16(2); u16(16);
+  tag("data"); u32(data_bytes);
+  int16_t* o = reinterpret_cast<int16_t*>(p);
+  for (int64_t i = 0; i < n; ++i) {
+    float x = samples[i];
+    x = x != x ? 0.f : (x < -1.f ? -1.f : (x > 1.f ? 1.f : x));  // NaN -> silence
+    o[i] = int16_t(std::nearbyint(x * 32767.f));
+  }
   return w;
 }
 

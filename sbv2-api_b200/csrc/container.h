@@ -36,5 +36,6 @@ std::vector<float> get_style_vector(const StyleVectors& s, int32_t style_id, flo
 
 std::vector<uint8_t> base64_decode(const char* p, size_t n);
 std::vector<uint8_t> wav_from_f32(const float* samples, int64_t n);
+std::vector<uint8_t> wav_pcm16_from_f32(const float* samples, int64_t n);
 
 }  // namespace sbv2

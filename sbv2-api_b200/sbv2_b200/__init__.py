@@ -101,6 +101,7 @@ def _load() -> C.CDLL:
         "sbv2_load_style_npy_base64": (C.c_int, [C.c_char_p, sz, C.POINTER(pf), pi64, pi64]),
         "sbv2_get_style_vector": (C.c_int, [pf, i64, i64, i32, f32, pf]),
         "sbv2_wav_from_f32": (C.c_int, [pf, i64, C.POINTER(vp), C.POINTER(sz)]),
+        "sbv2_wav_pcm16_from_f32": (C.c_int, [pf, i64, C.POINTER(vp), C.POINTER(sz)]),
         "sbv2_holder_new": (C.c_int, [vp, sz, vp, sz, i64, C.c_int, C.POINTER(vp)]),
         "sbv2_holder_free": (None, [vp]),
         "sbv2_holder_load_sbv2file": (C.c_int, [vp, C.c_char_p, vp, sz]),
@@ -273,6 +274,15 @@ def wav_from_f32(samples: np.ndarray) -> bytes:
     s = _f32(samples).reshape(-1)
     p, n = C.c_void_p(), C.c_size_t()
     _check(lib.sbv2_wav_from_f32(_pf(s), s.size, C.byref(p), C.byref(n)))
+    out = C.string_at(p, n.value)
+    lib.sbv2_free(p)
+    return out
+
+
+def wav_pcm16_from_f32(samples: np.ndarray) -> bytes:
+    s = _f32(samples).reshape(-1)
+    p, n = C.c_void_p(), C.c_size_t()
+    _check(lib.sbv2_wav_pcm16_from_f32(_pf(s), s.size, C.byref(p), C.byref(n)))
     out = C.string_at(p, n.value)
     lib.sbv2_free(p)
     return out

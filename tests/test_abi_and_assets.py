@@ -132,6 +132,23 @@ def test_wav_container(S):
     assert len(S.wav_from_f32(np.zeros(0, np.float32))) == 68
 
 
+def test_wav_pcm16_container(S):
+    """Optional 16-bit PCM container: canonical 44-byte header, clamp + round-to-nearest, readable by the
+    standard library's wave module."""
+    import io
+    import wave
+    x = np.array([0.0, 1.0, -1.0, 0.5, -0.25, 2.0, -3.0, np.nan, 1e-6], np.float32)
+    w = S.wav_pcm16_from_f32(x)
+    assert len(w) == 44 + 2 * x.size and w[:4] == b"RIFF" and w[8:16] == b"WAVEfmt " and w[36:40] == b"data"
+    assert struct.unpack("<I", w[4:8])[0] == len(w) - 8
+    assert struct.unpack("<IHHIIHH", w[16:36]) == (16, 1, 1, 44100, 88200, 2, 16)
+    got = np.frombuffer(w[44:], dtype="<i2")
+    assert got.tolist() == [0, 32767, -32767, 16384, -8192, 32767, -32767, 0, 0]
+    with wave.open(io.BytesIO(w)) as r:
+        assert (r.getnchannels(), r.getsampwidth(), r.getframerate(), r.getnframes()) == (1, 2, 44100, x.size)
+    assert len(S.wav_pcm16_from_f32(np.zeros(0, np.float32))) == 44
+
+
 def test_onnx_reader_rejects_garbage(S):
     if S.device_count() != 0:
         pytest.skip("covered by GPU tests")
